@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/s of the STFT -> mask -> PIT hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic 4 s / 16 kHz 2-speaker mixtures:
+  kernel 1  |Y| = |STFT(y)|                      (front-end feature, b2s_stft_forward, ABS epilogue)
+  kernel 2  fused STFT(s_k) -> mask (*) |Y| -> K x K SSE -> permutation search (b2s_stft_pit_forward)
+The mask network between the two is NOT part of the path: masks are
+synthetic U(0,1) tensors resident in HBM.  Rank r of N processes its own batch (weak scaling, no
+data-path collective: utterances are independent, DESIGN.md "Multi-GPU").
+
+Prints ONE JSON line (see the task contract): value = device-timed utterances/s with inputs resident
+in HBM; e2e = the same through the public call with pinned HOST buffers, H2D/D2H inside the timed
+region; roofline = achieved algorithmic GB/s of the dominant kernel vs the measured HBM peak;
+cpu_baseline = the CPU oracle port of the reference ops timed on this box's host cores.
+--impl reference times that CPU implementation as the headline instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 64            # utterances per GPU per step (north star: batch 64 x 4 s x 16 kHz)
+SAMPLES = 64000       # 4 s @ 16 kHz
+SOURCES = 2
+SIZE, SHIFT = 1024, 256
+FRAMES, BINS = 253, 513
+ROTATE = 3            # input sets cycled so a step's 215 MB of inputs were evicted from the 126 MB L2
+WORKLOAD = ('fused STFT->mask->PIT-loss path, batch 64 x 4 s x 16 kHz, 2 speakers, STFT(1024,256) '
+            '(253 frames x 513 bins); masks synthetic U(0,1), mask network excluded (SURVEY 8d(i))')
+
+# algorithmic (compulsory) bytes per utterance, SURVEY.md section 8(d) / BASELINE.md section 2
+BYTES_FRONT = 4 * SAMPLES + 4 * FRAMES * BINS                                  # y -> |Y|
+BYTES_LOSS = 4 * SAMPLES * (1 + SOURCES) + 4 * FRAMES * BINS * SOURCES         # mask, y, s -> loss, perm
+BYTES_PATH = BYTES_FRONT + BYTES_LOSS                                          # 2 581 468 B/utt
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fd:
+            return float(json.load(fd)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    BAD = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown')
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.thread, self.nvml, self.handle, self.max_mhz = None, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _reasons(self):
+        n = self.nvml
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            except Exception:
+                return []
+        table = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+                 'sw_power_cap': 0x4, 'hw_power_brake': 0x80}
+        return [name for name, bit in table.items() if mask & bit]
+
+    def _run(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                self.samples.append((time.perf_counter(), mhz, self._reasons()))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join()
+
+    def summary(self, t0, t1):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        if not inside:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': [], 'samples': 0}
+        reasons = sorted({r for s in inside for r in s[2]})
+        return {'sm_mhz': statistics.median(s[1] for s in inside), 'sm_max_mhz': self.max_mhz,
+                'reasons': reasons, 'samples': len(inside)}
+
+
+# ------------------------------------------------------------------------------------------------ data
+def synthetic_batch(seed, device=None, pin=False):
+    """s ~ 0.1 N(0,1) [B, K, T], y = sum_k s_k, masks ~ U(0,1) [B, M, K, F]."""
+    gen = torch.Generator().manual_seed(seed)
+    s = 0.1 * torch.randn(BATCH, SOURCES, SAMPLES, generator=gen)
+    y = s.sum(1)
+    masks = torch.rand(BATCH, FRAMES, SOURCES, BINS, generator=gen)
+    out = dict(y=y, s=s, masks=masks)
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    if device is not None:
+        out = {k: v.to(device) for k, v in out.items()}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step(batch, stft, n_utt):
+    """The reference's ops for the same step on the host: pt.ops.STFT (dense DFT convolution) of y
+    and s, abs, then the per-example pit_loss loop of pit/model.py:117-128 (oracle port)."""
+    from oracle import path as oracle_path
+    with torch.no_grad():
+        return oracle_path.stft_mask_pit_step(batch['y'][:n_utt], batch['s'][:n_utt],
+                                              batch['masks'][:n_utt], stft=stft)
+
+
+def time_cpu(steps, warmup, n_utt=BATCH, seed=1234):
+    from oracle.stft import ReferenceSTFT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = synthetic_batch(seed)
+    stft = ReferenceSTFT(SIZE, SHIFT)
+    for _ in range(warmup):
+        cpu_step(batch, stft, n_utt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(batch, stft, n_utt)
+    elapsed = time.perf_counter() - t0
+    return n_utt * steps / elapsed, elapsed / steps, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    value, per_step, cores = time_cpu(args.steps, args.warmup)
+    cpu_model = ''
+    try:
+        with open('/proc/cpuinfo') as fd:
+            cpu_model = next(l.split(':', 1)[1].strip() for l in fd if l.startswith('model name'))
+    except Exception:
+        pass
+    line = {
+        'impl': 'reference', 'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'l2': 'n/a (CPU)'},
+        'cpu_baseline': {'value': value, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps} x one full batch of {BATCH} utterances through the '
+                                   f'oracle port of pt.ops.STFT + pit_loss loop, {cores} threads, {cpu_model}'},
+        'e2e': {'value': value, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import padertorch_b200 as b2s
+    from padertorch_b200 import review
+
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    stft = b2s.ops.STFT(SIZE, SHIFT)
+    sets = [synthetic_batch(100 * rank + i, device=device) for i in range(ROTATE)]
+    torch.cuda.synchronize()
+
+    def step(data):
+        y_abs = stft.magnitude(data['y'])                                        # kernel 1
+        return review.stft_mask_pit_step(None, data['s'], data['masks'], stft=stft,
+                                         observation_abs=y_abs)                  # kernel 2
+
+    for i in range(max(args.warmup, 3)):
+        loss, perm = step(sets[i % ROTATE])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    start.record()
+    for i in range(args.steps):
+        loss, perm = step(sets[i % ROTATE])
+    end.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    elapsed_ms = start.elapsed_time(end)
+    if distributed:
+        t = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        dist.barrier()
+
+    # keep the GPU under the same load long enough for NVML to see it (not part of any number)
+    t_hold = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_hold < 1.0:
+        step(sets[i % ROTATE])
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    t_wall2 = time.perf_counter()
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall2)
+    clocks['window'] = 'timed region + 1 s of identical steps'
+
+    # ---- per-kernel durations (CUDA events on the launching stream), for the roofline object
+    n_probe = min(max(args.steps, 20), 200)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_probe)]
+    for i in range(n_probe):
+        data = sets[i % ROTATE]
+        ev[i][0].record()
+        y_abs = stft.magnitude(data['y'])
+        ev[i][1].record()
+        review.stft_mask_pit_step(None, data['s'], data['masks'], stft=stft, observation_abs=y_abs)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    front_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    loss_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+
+    # ---- end to end through the public call with HOST buffers
+    host_sets = [synthetic_batch(100 * rank + i, pin=True) for i in range(2)]
+    h2d = sum(v.numel() * 4 for v in host_sets[0].values())
+    out_loss = torch.empty(BATCH, dtype=torch.float32).pin_memory()
+    out_perm = torch.empty((BATCH, SOURCES), dtype=torch.int32).pin_memory()
+    d2h = out_loss.numel() * 4 + out_perm.numel() * 4
+
+    def e2e_step(host):
+        data = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        loss, perm = step(data)
+        out_loss.copy_(loss, non_blocking=True)
+        out_perm.copy_(perm, non_blocking=True)
+
+    e2e_steps = max(5, min(args.steps, 30))
+    for i in range(3):
+        e2e_step(host_sets[i % 2])
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(host_sets[i % 2])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        ms_per_step = elapsed_ms / args.steps
+        value = world * BATCH * args.steps / (elapsed_ms * 1e-3)
+        achieved = BYTES_LOSS * BATCH / (loss_ms * 1e-3) / 1e9
+        path_gbs = BYTES_PATH * BATCH / (ms_per_step * 1e-3) / 1e9
+        cpu_value, cpu_step_s, cores = time_cpu(3, 1)
+        line = {
+            'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'samples': SAMPLES, 'sources': SOURCES,
+                       'l2': f'inputs larger than L2: {ROTATE} rotating input sets of 215 MB each',
+                       'parallelism': f'{world} independent shard(s), no data-path collective'},
+            'e2e': {'value': world * BATCH * e2e_steps / e2e_s, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
+            'gpu_launches': 2 * args.steps,
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'stft_pit_fused_kernel', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind,
+                         'algorithmic_bytes_per_launch': BYTES_LOSS * BATCH, 'kernel_ms': loss_ms},
+            'path_roofline': {'achieved': path_gbs, 'frac': path_gbs / peak, 'unit': 'GB/s',
+                              'algorithmic_bytes_per_step': BYTES_PATH * BATCH,
+                              'front_end_kernel_ms': front_ms,
+                              'front_end_frac': BYTES_FRONT * BATCH / (front_ms * 1e-3) / 1e9 / peak},
+            'cpu_baseline': {'value': cpu_value, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'3 x one full batch of {BATCH} utterances (oracle port of pt.ops.STFT '
+                                       f'+ pit_loss loop), {cpu_step_s:.2f} s per batch'},
+        }
+        traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as fd:
+                line['roofline']['traffic'] = json.load(fd).get('stft_pit_fused_kernel')
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=300)
+    parser.add_argument('--warmup', type=int, default=10)
+    parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = parser.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: padertorch_b200 has no CPU fallback')
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

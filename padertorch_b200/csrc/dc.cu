@@ -1,0 +1,256 @@
+// Deep-clustering affinity loss: one streaming pass builds the (E+K) x (E+K) Gram matrix of the
+// stacked [embedding | target mask] channels per example, straight from the model's native 't e f'
+// layout; the loss is a function of that matrix only.
+// Reference: deep_clustering_loss, padertorch/ops/losses/source_separation.py:13-31 (three tall-skinny
+// einsums) called per example after two transpose copies in padertorch/contrib/tcl/dc.py:76-84.
+//
+// Register blocking: a warp owns one 8 x 8 block pair of the Gram matrix (64 accumulators per lane),
+// lanes own consecutive time-frequency points (coalesced along f); the warps of a CTA walk the same
+// point tiles, so the repeated channel reads hit L1.  fp32 FFMA on CUDA cores: 5.5 FLOP/B keeps this
+// HBM-bound, tensor cores would need a 3x split to hold fp32 accuracy and lose to the padding.
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace b2s;
+
+namespace {
+
+constexpr int BS = 8;            // Gram block edge
+constexpr int kMaxBlocks = B2S_DC_MAX_CHANNELS / BS;
+constexpr int kMaxWarps = 8;
+
+struct DcGrid { int blocks, pairs, warps, nchunks, cp; };
+
+DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
+  DcGrid g;
+  g.blocks = (channels + BS - 1) / BS;
+  g.cp = g.blocks * BS;
+  g.pairs = g.blocks * (g.blocks + 1) / 2;
+  g.warps = std::min(g.pairs, kMaxWarps);
+  const int per_sm = std::max(1, std::min(2048 / (32 * g.warps), 65536 / (144 * 32 * g.warps)));
+  const int64_t capacity = (int64_t)kNumSMs * per_sm;
+  const int64_t points = std::max<int64_t>(1, max_frames * bins);
+  int64_t c = capacity / std::max<int64_t>(1, batch);
+  c = std::min<int64_t>(c, std::max<int64_t>(1, points / 2048));
+  g.nchunks = (int)std::max<int64_t>(1, c);
+  return g;
+}
+
+struct Strides { int64_t t, c, f; };
+
+__global__ void __launch_bounds__(32 * kMaxWarps)
+dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+               const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
+               int K, int blocks, int pairs, double* __restrict__ partial, int* __restrict__ counters,
+               double* __restrict__ gram, float* __restrict__ loss) {
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int C = E + K, cp = blocks * BS;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  const int64_t N = T * F;
+  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * cp * cp;
+
+  for (int pair = warp; pair < pairs; pair += nwarps) {
+    // pair index -> (ba <= bb), row-major over the upper triangle
+    int ba = 0, rem = pair;
+    while (rem >= blocks - ba) { rem -= blocks - ba; ++ba; }
+    const int bb = ba + rem;
+    // per-channel base pointers (nullptr: padding channel)
+    const float* pa[BS]; const float* pb[BS];
+    bool ea[BS], eb[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      const int ca = ba * BS + i, cb = bb * BS + i;
+      ea[i] = ca < E; eb[i] = cb < E;
+      pa[i] = ca < E ? e_ + ca * se.c : (ca < C ? t_ + (ca - E) * st.c : nullptr);
+      pb[i] = cb < E ? e_ + cb * se.c : (cb < C ? t_ + (cb - E) * st.c : nullptr);
+    }
+    float acc[BS][BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
+    for (int64_t q = q0 + lane; q < q1; q += 32) {
+      const int64_t t = q / F, f = q - t * F;
+      const int64_t oe = t * se.t + f * se.f, ot = t * st.t + f * st.f;
+      float va[BS], vb[BS];
+#pragma unroll
+      for (int i = 0; i < BS; ++i) va[i] = pa[i] ? __ldg(pa[i] + (ea[i] ? oe : ot)) : 0.f;
+      if (ba == bb) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) vb[i] = va[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) vb[i] = pb[i] ? __ldg(pb[i] + (eb[i] ? oe : ot)) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) acc[i][j] = fmaf(va[i], vb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const float s = warp_sum(acc[i][j]);
+        if (lane == 0) {
+          mine[(ba * BS + i) * cp + bb * BS + j] = (double)s;
+          mine[(bb * BS + j) * cp + ba * BS + i] = (double)s;
+        }
+      }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: fold chunks in order -> gram[b][C][C]; loss = (|A|^2 - 2|Cx|^2 + |D|^2) / N^2
+  __shared__ double red[32 * kMaxWarps];
+  double local = 0.0;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int r = idx / C, c = idx - r * C;
+    double s = 0.0;
+    const volatile double* p = partial + (int64_t)b * nchunks * cp * cp + r * cp + c;
+    for (int ch = 0; ch < nchunks; ++ch) s += p[(int64_t)ch * cp * cp];
+    gram[(int64_t)b * C * C + idx] = s;
+    const bool re = r < E, ce = c < E;
+    const double w = (re == ce) ? 1.0 : -1.0;  // the two mixed blocks together give -2 |V^T Y|^2
+    local += w * s * s;
+  }
+  red[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) s += red[i];
+    loss[b] = (float)(s / ((double)N * (double)N));
+    counters[b] = 0;
+  }
+}
+
+// grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
+// Thread = 2 points x one block of 8 output channels; the coefficient matrix sits in shared memory.
+__global__ void __launch_bounds__(256)
+dc_backward_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                   const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
+                   int K, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                   float* __restrict__ grad_emb) {
+  extern __shared__ float coef[];  // [C][Ep], Ep = E rounded up to BS
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int C = E + K, eblocks = (E + BS - 1) / BS, Ep = eblocks * BS;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const int64_t eoff = meta[b * B2S_DC_META + 1];
+  const float* e_ = emb + eoff;
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
+  const int64_t N = T * F;
+  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  for (int idx = threadIdx.x; idx < C * Ep; idx += blockDim.x) {
+    const int c = idx / Ep, e = idx - c * Ep;
+    double v = 0.0;
+    if (e < E) v = (c < E ? 1.0 : -1.0) * scale * gram[(int64_t)b * C * C + c * C + e];
+    coef[idx] = (float)v;
+  }
+  __syncthreads();
+  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // work item = (tile of 64 points, output block); warps stride over items
+  const int64_t tiles = ceil_div(q1 - q0, 64);
+  for (int64_t item = warp; item < tiles * eblocks; item += nwarps) {
+    const int64_t tile = item / eblocks;
+    const int eb = (int)(item - tile * eblocks);
+    const int64_t qa = q0 + tile * 64 + lane, qb = qa + 32;
+    const bool oka = qa < q1, okb = qb < q1;
+    const int64_t ta = qa / F, fa = qa - ta * F, tb = qb / F, fb = qb - tb * F;
+    float ga[BS], gb[BS];
+#pragma unroll
+    for (int j = 0; j < BS; ++j) { ga[j] = 0.f; gb[j] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+      float za, zb;
+      if (c < E) {
+        za = oka ? __ldg(e_ + ta * se.t + c * se.c + fa * se.f) : 0.f;
+        zb = okb ? __ldg(e_ + tb * se.t + c * se.c + fb * se.f) : 0.f;
+      } else {
+        za = oka ? __ldg(t_ + ta * st.t + (c - E) * st.c + fa * st.f) : 0.f;
+        zb = okb ? __ldg(t_ + tb * st.t + (c - E) * st.c + fb * st.f) : 0.f;
+      }
+      const float4 c0 = *reinterpret_cast<const float4*>(coef + c * Ep + eb * BS);
+      const float4 c1 = *reinterpret_cast<const float4*>(coef + c * Ep + eb * BS + 4);
+      const float cf[BS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int j = 0; j < BS; ++j) { ga[j] = fmaf(za, cf[j], ga[j]); gb[j] = fmaf(zb, cf[j], gb[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      const int e = eb * BS + j;
+      if (e < E) {
+        if (oka) g_[ta * se.t + e * se.c + fa * se.f] = ga[j];
+        if (okb) g_[tb * se.t + e * se.c + fb * se.f] = gb[j];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t b2s_dc_workspace_bytes(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
+  if (batch <= 0 || channels <= 0) return 16;
+  const DcGrid g = dc_grid(batch, max_frames, bins, channels);
+  return kTicketBytes + (int64_t)sizeof(double) * batch * g.nchunks * g.cp * g.cp + 16;
+}
+
+int b2s_dc_forward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                   int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                   const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
+                   double* gram, void* workspace, b2s_stream stream) {
+  const int C = embedding_dim + sources;
+  B2S_REQUIRE(embedding_dim >= 1 && sources >= 1 && C <= B2S_DC_MAX_CHANNELS,
+              "embedding_dim + sources = %d outside 2..%d", C, B2S_DC_MAX_CHANNELS);
+  B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
+  if (batch == 0) return B2S_OK;
+  B2S_REQUIRE(embedding && target && meta && embedding_strides && target_strides && loss && gram &&
+              workspace, "NULL pointer");
+  const DcGrid g = dc_grid(batch, max_frames, bins, C);
+  double* partial = ws_partials(workspace);
+  int* counters = ws_counters(workspace);
+  const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
+  const Strides st{target_strides[0], target_strides[1], target_strides[2]};
+  dc_gram_kernel<<<dim3((unsigned)batch, g.nchunks), 32 * g.warps, 0, (cudaStream_t)stream>>>(
+      embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, g.blocks, g.pairs, partial,
+      counters, gram, loss);
+  B2S_LAUNCH_CHECK("dc_gram_kernel");
+  return B2S_OK;
+}
+
+int b2s_dc_backward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                    int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                    const int64_t* embedding_strides, const int64_t* target_strides, const double* gram,
+                    const float* grad_loss, float* grad_embedding, b2s_stream stream) {
+  const int C = embedding_dim + sources;
+  B2S_REQUIRE(embedding_dim >= 1 && sources >= 1 && C <= B2S_DC_MAX_CHANNELS,
+              "embedding_dim + sources = %d outside 2..%d", C, B2S_DC_MAX_CHANNELS);
+  B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
+  if (batch == 0) return B2S_OK;
+  B2S_REQUIRE(embedding && target && meta && embedding_strides && target_strides && gram && grad_loss &&
+              grad_embedding, "NULL pointer");
+  const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
+  const Strides st{target_strides[0], target_strides[1], target_strides[2]};
+  const int64_t points = std::max<int64_t>(1, max_frames * bins);
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 4096, 256));
+  const int Ep = (embedding_dim + BS - 1) / BS * BS;
+  const size_t smem = sizeof(float) * C * Ep;
+  dc_backward_kernel<<<dim3((unsigned)batch, nchunks), 256, smem, (cudaStream_t)stream>>>(
+      embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss,
+      grad_embedding);
+  B2S_LAUNCH_CHECK("dc_backward_kernel");
+  return B2S_OK;
+}
+
+}  // extern "C"

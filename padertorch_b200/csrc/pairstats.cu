@@ -1,0 +1,395 @@
+// Time-domain regression losses (MSE / log-MSE / log1p-MSE / SDR / SI-SDR / SA-SDR) and their PIT
+// wrapper, computed from one streaming pass of double-precision pair statistics.
+// Reference: padertorch/ops/losses/regression.py:4-376 and the loop of TasNet.loss
+// (padertorch/contrib/examples/source_separation/tasnet/model.py:154-176: 3 loss fns x K! permutations
+// x B examples of ~12 small ATen reductions each).
+//
+// Every loss on this path is a function of {<e_i,t_j>, |e_i|^2, |t_j|^2, sum e_i, sum t_j}: products of
+// fp32 inputs are exact in fp64, so the expansions |e - a t|^2 = Ee - 2 a D + a^2 Tt do not suffer the
+// cancellation they would in fp32, and one read of (estimate, target) serves all K^2 pairs, all K!
+// permutations and all loss kinds.  The gradient is a per-row affine map a e_i + b t_k + c.
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+#include "perm.cuh"
+
+using namespace b2s;
+
+namespace {
+
+constexpr int kStatsThreads = 256;
+constexpr double kLn10 = 2.302585092994045684;
+
+__host__ __device__ inline int stats_per_group(int K) { return K * K + 4 * K; }
+
+int pair_chunks(int64_t groups, int64_t max_length) {
+  const int64_t capacity = (int64_t)kNumSMs * (2048 / kStatsThreads);
+  int64_t c = capacity / std::max<int64_t>(1, groups);
+  const int64_t most = std::max<int64_t>(1, max_length / (kStatsThreads * 8));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(c, most));
+}
+
+template <int K>
+__global__ void __launch_bounds__(kStatsThreads)
+pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                  const int64_t* __restrict__ meta, int nchunks, int64_t est_stride, int64_t tgt_stride,
+                  double* __restrict__ partial, int* __restrict__ counters, double* __restrict__ stats) {
+  constexpr int NV = K * K + 4 * K;
+  __shared__ double sm[NV * (kStatsThreads / 32)];
+  const int g = blockIdx.x, chunk = blockIdx.y;
+  const int64_t T = meta[g * B2S_PAIR_META + 0];
+  const float* e_ = est + meta[g * B2S_PAIR_META + 1];
+  const float* t_ = tgt + meta[g * B2S_PAIR_META + 2];
+  const int64_t n0 = T * chunk / nchunks, n1 = T * (chunk + 1) / nchunks;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  auto fold = [&](const float (&e)[K], const float (&t)[K]) {
+    double ed[K], td[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) { ed[i] = (double)e[i]; td[i] = (double)t[i]; }
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc[i * K + j] = fma(ed[i], td[j], acc[i * K + j]);
+      acc[K * K + i] = fma(ed[i], ed[i], acc[K * K + i]);
+      acc[K * K + K + i] = fma(td[i], td[i], acc[K * K + K + i]);
+      acc[K * K + 2 * K + i] += ed[i];
+      acc[K * K + 3 * K + i] += td[i];
+    }
+  };
+  int64_t n = n0 + threadIdx.x;
+  for (; n + kStatsThreads < n1; n += 2 * kStatsThreads) {  // two samples in flight per row
+    float e0[K], t0[K], e1[K], t1[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      e0[i] = __ldg(e_ + i * est_stride + n);
+      t0[i] = __ldg(t_ + i * tgt_stride + n);
+      e1[i] = __ldg(e_ + i * est_stride + n + kStatsThreads);
+      t1[i] = __ldg(t_ + i * tgt_stride + n + kStatsThreads);
+    }
+    fold(e0, t0);
+    fold(e1, t1);
+  }
+  if (n < n1) {
+    float e0[K], t0[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      e0[i] = __ldg(e_ + i * est_stride + n);
+      t0[i] = __ldg(t_ + i * tgt_stride + n);
+    }
+    fold(e0, t0);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = kStatsThreads / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = warp_sum(acc[i]);
+    if (lane == 0) sm[i * nwarps + warp] = s;
+  }
+  __syncthreads();
+  double* mine = partial + ((int64_t)g * nchunks + chunk) * NV;
+  for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sm[i * nwarps + w];
+    mine[i] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + g, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
+    double s = 0.0;
+    const volatile double* p = partial + (int64_t)g * nchunks * NV + i;
+    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
+    stats[(int64_t)g * NV + i] = s;
+  }
+  if (threadIdx.x == 0) counters[g] = 0;
+}
+
+// Value of one pair loss and its partial derivatives w.r.t. the estimate-side statistics.
+struct PairEval { double value, dEe, dD, dSe; };
+
+__device__ inline PairEval eval_pair(int kind, int flags, double tau, double T, double Ee, double D,
+                                     double Tt, double Se, double St) {
+  PairEval r;
+  r.dSe = 0.0;
+  const bool offset = (flags & B2S_FLAG_OFFSET_INVARIANT) != 0;
+  const double Se0 = Se, St0 = St;
+  if (offset) {  // statistics of the mean-removed signals
+    Ee -= Se * Se / T;
+    D -= Se * St / T;
+    Tt -= St * St / T;
+  }
+  switch (kind) {
+    case B2S_LOSS_MSE: {
+      r.value = (Ee - 2.0 * D + Tt) / T;
+      r.dEe = 1.0 / T; r.dD = -2.0 / T;
+    } break;
+    case B2S_LOSS_LOG_MSE: {
+      double m = (Ee - 2.0 * D + Tt) / T;
+      if (tau >= 0.0) m += tau * Tt / T;
+      r.value = log10(m);
+      const double dm = 1.0 / (m * kLn10);
+      r.dEe = dm / T; r.dD = -2.0 * dm / T;
+    } break;
+    case B2S_LOSS_LOG1P_MSE: {
+      const double m = (Ee - 2.0 * D + Tt) / T;
+      r.value = log10(1.0 + m);
+      const double dm = 1.0 / ((1.0 + m) * kLn10);
+      r.dEe = dm / T; r.dD = -2.0 * dm / T;
+    } break;
+    case B2S_LOSS_SDR: {
+      double den = Ee - 2.0 * D + Tt;
+      if (tau >= 0.0) den += tau * Tt;
+      r.value = -10.0 * log10(Tt / den);
+      const double dden = 10.0 / (kLn10 * den);
+      r.dEe = dden; r.dD = -2.0 * dden;
+    } break;
+    default: {  // B2S_LOSS_SI_SDR
+      const double alpha = D / Tt;
+      const double sig = alpha * alpha * Tt;
+      const double noise = Ee - 2.0 * alpha * D + alpha * alpha * Tt;
+      const double den = tau >= 0.0 ? noise + tau * sig : noise;
+      r.value = -10.0 * log10(sig / den);
+      const double dnoise = 10.0 / (kLn10 * den);
+      r.dEe = dnoise;
+      if (flags & B2S_FLAG_GRAD_STOP) {
+        r.dD = -2.0 * alpha * dnoise;
+      } else {
+        // sig = D^2/Tt, noise = Ee - D^2/Tt
+        const double dsig = -10.0 / kLn10 * (1.0 / sig - (tau >= 0.0 ? tau / den : 0.0));
+        r.dD = 2.0 * alpha * (dsig - dnoise);
+      }
+    } break;
+  }
+  if (offset) r.dSe = r.dEe * (-2.0 * Se0 / T) + r.dD * (-St0 / T);
+  return r;
+}
+
+// one CTA per example (= `inner` consecutive groups)
+__global__ void __launch_bounds__(128)
+pair_loss_kernel(const double* __restrict__ stats, const int64_t* __restrict__ meta, int64_t inner, int K,
+                 int kind, int flags, double tau, int reduction, int pit, float* __restrict__ loss,
+                 int32_t* __restrict__ perm) {
+  __shared__ double cost[B2S_MAX_SOURCES * B2S_MAX_SOURCES];
+  const int ex = blockIdx.x;
+  const int NV = stats_per_group(K);
+  if (kind == B2S_LOSS_SA_SDR) {
+    // aggregated over every row of the example: -10 log10(sum Tt / (sum |e-t|^2 [+ tau sum Tt]))
+    if (threadIdx.x == 0) {
+      double st = 0.0, sn = 0.0;
+      for (int64_t c = 0; c < inner; ++c) {
+        const double* s = stats + (ex * inner + c) * NV;
+        for (int k = 0; k < K; ++k) {
+          const double Ee = s[K * K + k], Tt = s[K * K + K + k], D = s[k * K + k];
+          st += Tt; sn += Ee - 2.0 * D + Tt;
+        }
+      }
+      if (tau >= 0.0) sn += tau * st;
+      loss[ex] = (float)(-10.0 * log10(st / sn));
+    }
+    return;
+  }
+  if (!pit) {
+    for (int64_t idx = threadIdx.x; idx < inner * K; idx += blockDim.x) {
+      const int64_t c = idx / K; const int k = (int)(idx - c * K);
+      const int64_t g = ex * inner + c;
+      const double* s = stats + g * NV;
+      const double T = (double)meta[g * B2S_PAIR_META];
+      const PairEval r = eval_pair(kind, flags, tau, T, s[K * K + k], s[k * K + k], s[K * K + K + k],
+                                   s[K * K + 2 * K + k], s[K * K + 3 * K + k]);
+      loss[g * K + k] = (float)r.value;
+    }
+    return;
+  }
+  for (int ij = threadIdx.x; ij < K * K; ij += blockDim.x) {
+    const int i = ij / K, j = ij - i * K;
+    double v = 0.0;
+    for (int64_t c = 0; c < inner; ++c) {  // fixed order
+      const int64_t g = ex * inner + c;
+      const double* s = stats + g * NV;
+      const double T = (double)meta[g * B2S_PAIR_META];
+      v += eval_pair(kind, flags, tau, T, s[K * K + i], s[i * K + j], s[K * K + K + j],
+                     s[K * K + 2 * K + i], s[K * K + 3 * K + j]).value;
+    }
+    cost[ij] = v;
+  }
+  __syncthreads();
+  double best;
+  int bp[B2S_MAX_SOURCES];
+  search_permutations(cost, K, best, bp);
+  if (threadIdx.x == 0) {
+    if (reduction == B2S_REDUCE_MEAN) best /= (double)(K * inner);
+    loss[ex] = (float)best;
+    for (int k = 0; k < K; ++k) perm[(int64_t)ex * K + k] = bp[k];
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kStatsThreads)
+pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                     const int64_t* __restrict__ meta, int nchunks, int64_t inner, int64_t est_stride,
+                     int64_t tgt_stride, const double* __restrict__ stats, int kind, int flags, double tau,
+                     int reduction, int pit, const int32_t* __restrict__ perm,
+                     const float* __restrict__ grad_loss, float* __restrict__ grad_est) {
+  constexpr int NV = K * K + 4 * K;
+  __shared__ float ca[K], cb[K], cc[K];
+  __shared__ int match[K];  // target index matched to estimate row i
+  const int g = blockIdx.x, chunk = blockIdx.y;
+  const int64_t ex = g / inner;
+  const int64_t T = meta[g * B2S_PAIR_META + 0];
+  const int64_t eoff = meta[g * B2S_PAIR_META + 1];
+  const float* e_ = est + eoff;
+  const float* t_ = tgt + meta[g * B2S_PAIR_META + 2];
+  float* g_ = grad_est + eoff;
+  if (threadIdx.x < K) {
+    const int i = threadIdx.x;
+    int k = i;
+    if (pit && perm) {
+      for (int kk = 0; kk < K; ++kk) if (perm[ex * K + kk] == i) k = kk;
+    }
+    const double* s = stats + (int64_t)g * NV;
+    double dEe, dD, dSe = 0.0, up;
+    if (kind == B2S_LOSS_SA_SDR) {
+      double st = 0.0, sn = 0.0;
+      for (int64_t c = 0; c < inner; ++c) {
+        const double* sc = stats + (ex * inner + c) * NV;
+        for (int kk = 0; kk < K; ++kk) {
+          st += sc[K * K + K + kk];
+          sn += sc[K * K + kk] - 2.0 * sc[kk * K + kk] + sc[K * K + K + kk];
+        }
+      }
+      if (tau >= 0.0) sn += tau * st;
+      dEe = 10.0 / (kLn10 * sn); dD = -2.0 * dEe;
+      up = (double)grad_loss[ex];
+    } else {
+      const PairEval r = eval_pair(kind, flags, tau, (double)T, s[K * K + i], s[i * K + k], s[K * K + K + k],
+                                   s[K * K + 2 * K + i], s[K * K + 3 * K + k]);
+      dEe = r.dEe; dD = r.dD; dSe = r.dSe;
+      if (pit) {
+        up = (double)grad_loss[ex];
+        if (reduction == B2S_REDUCE_MEAN) up /= (double)(K * inner);
+      } else {
+        up = (double)grad_loss[(int64_t)g * K + i];
+      }
+    }
+    ca[i] = (float)(up * 2.0 * dEe);
+    cb[i] = (float)(up * dD);
+    cc[i] = (float)(up * dSe);
+    match[i] = k;
+  }
+  __syncthreads();
+  const int64_t n0 = T * chunk / nchunks, n1 = T * (chunk + 1) / nchunks;
+  for (int64_t n = n0 + threadIdx.x; n < n1; n += kStatsThreads) {
+    float t[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) t[k] = __ldg(t_ + k * tgt_stride + n);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float tm = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) if (match[i] == k) tm = t[k];
+      const float e = __ldg(e_ + i * est_stride + n);
+      g_[i * est_stride + n] = fmaf(ca[i], e, fmaf(cb[i], tm, cc[i]));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t b2s_pair_workspace_bytes(int64_t groups, int64_t max_length, int sources) {
+  if (groups <= 0 || sources <= 0) return 16;
+  const int chunks = pair_chunks(groups, max_length);
+  return kTicketBytes + (int64_t)sizeof(double) * groups * chunks * stats_per_group(sources) + 16;
+}
+
+int b2s_pair_stats_forward(const float* estimate, const float* target, const int64_t* meta,
+                           int64_t groups, int64_t max_length, int sources,
+                           int64_t estimate_source_stride, int64_t target_source_stride, double* stats,
+                           void* workspace, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
+              "sources=%d outside the supported range 1..%d", sources, B2S_MAX_SOURCES);
+  B2S_REQUIRE(groups >= 0 && groups <= kMaxTickets && max_length >= 0, "bad extents (groups=%lld)",
+              (long long)groups);
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(estimate && target && meta && stats && workspace, "NULL device pointer");
+  const int chunks = pair_chunks(groups, max_length);
+  double* partial = ws_partials(workspace);
+  int* counters = ws_counters(workspace);
+  const dim3 grid((unsigned)groups, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(K) pair_stats_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
+      estimate_source_stride, target_source_stride, partial, counters, stats)
+  switch (sources) {
+    case 1: CALL(1); break;
+    case 2: CALL(2); break;
+    case 3: CALL(3); break;
+    case 4: CALL(4); break;
+    case 5: CALL(5); break;
+    case 6: CALL(6); break;
+    case 7: CALL(7); break;
+    default: CALL(8); break;
+  }
+#undef CALL
+  B2S_LAUNCH_CHECK("pair_stats_kernel");
+  return B2S_OK;
+}
+
+int b2s_pair_loss(const double* stats, const int64_t* meta, int64_t groups, int64_t inner, int sources,
+                  int kind, int flags, double tau, int reduction, int pit, float* loss, int32_t* perm,
+                  b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
+  B2S_REQUIRE(kind >= B2S_LOSS_MSE && kind <= B2S_LOSS_SA_SDR, "unknown loss kind %d", kind);
+  B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
+  B2S_REQUIRE(!pit || (reduction == B2S_REDUCE_SUM || reduction == B2S_REDUCE_MEAN),
+              "PIT needs reduction sum or mean");
+  B2S_REQUIRE(!(pit && kind == B2S_LOSS_SA_SDR), "SA-SDR is not additive over sources: no PIT variant");
+  B2S_REQUIRE(!(flags & B2S_FLAG_OFFSET_INVARIANT) || kind == B2S_LOSS_SI_SDR,
+              "offset_invariant exists for si_sdr only");
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(stats && meta && loss && (!pit || perm), "NULL device pointer");
+  pair_loss_kernel<<<(unsigned)(groups / inner), 128, 0, (cudaStream_t)stream>>>(
+      stats, meta, inner, sources, kind, flags, tau, reduction, pit, loss, perm);
+  B2S_LAUNCH_CHECK("pair_loss_kernel");
+  return B2S_OK;
+}
+
+int b2s_pair_backward(const float* estimate, const float* target, const int64_t* meta, int64_t groups,
+                      int64_t inner, int64_t max_length, int sources, int64_t estimate_source_stride,
+                      int64_t target_source_stride, const double* stats, int kind, int flags, double tau,
+                      int reduction, int pit, const int32_t* perm, const float* grad_loss,
+                      float* grad_estimate, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
+  B2S_REQUIRE(kind >= B2S_LOSS_MSE && kind <= B2S_LOSS_SA_SDR, "unknown loss kind %d", kind);
+  B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(estimate && target && meta && stats && grad_loss && grad_estimate, "NULL device pointer");
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_length / (kStatsThreads * 4) + 1, 64));
+  const dim3 grid((unsigned)groups, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(K) pair_backward_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
+      inner, estimate_source_stride, target_source_stride, stats, kind, flags, tau, reduction, pit, perm, \
+      grad_loss, grad_estimate)
+  switch (sources) {
+    case 1: CALL(1); break;
+    case 2: CALL(2); break;
+    case 3: CALL(3); break;
+    case 4: CALL(4); break;
+    case 5: CALL(5); break;
+    case 6: CALL(6); break;
+    case 7: CALL(7); break;
+    default: CALL(8); break;
+  }
+#undef CALL
+  B2S_LAUNCH_CHECK("pair_backward_kernel");
+  return B2S_OK;
+}
+
+}  // extern "C"

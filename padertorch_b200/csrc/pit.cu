@@ -1,0 +1,322 @@
+// Permutation-invariant MSE over spectrogram-shaped blocks: fused mask (*) observation, K x K
+// sum-of-squared-error matrix, permutation search -- one launch for a whole ragged batch.
+// Reference: padertorch/ops/losses/source_separation.py:34-124 driven by the per-example loop of
+// padertorch/contrib/examples/source_separation/pit/model.py:117-135 (which materialises mask*Y twice
+// and launches ~20 ATen kernels per example).
+//
+// HBM-bound streaming reduction: every input element is read exactly once with coalesced 4-byte
+// loads (F = 513 rows are not 16-byte aligned), two frames in flight per thread; partial sums leave
+// the CTA as doubles and the last CTA of an example (ticket counter) folds them in a fixed order.
+#include <algorithm>
+
+#include "common.cuh"
+#include "perm.cuh"
+
+using namespace b2s;
+
+namespace {
+
+struct PitGrid {
+  int bx, by, tchunks, fchunks;
+  int nchunks() const { return tchunks * fchunks; }
+  int threads() const { return bx * by; }
+};
+
+constexpr int64_t kBinsPerChunk = 8192;
+
+PitGrid pit_grid(int64_t batch, int64_t max_frames, int64_t bins) {
+  PitGrid g;
+  g.bx = (int)std::min<int64_t>((bins + 31) / 32 * 32, 576);
+  g.by = std::max(1, 512 / g.bx);
+  g.fchunks = (int)ceil_div(std::max<int64_t>(bins, 1), kBinsPerChunk);
+  const int per_sm = std::max(1, 2048 / g.threads());
+  const int64_t capacity = (int64_t)kNumSMs * per_sm;
+  int64_t t = capacity / std::max<int64_t>(1, batch * g.fchunks);
+  const int64_t most = std::max<int64_t>(1, max_frames / (2 * g.by));
+  g.tchunks = (int)std::max<int64_t>(1, std::min<int64_t>(t, most));
+  return g;
+}
+
+template <int K, bool DUAL>
+__global__ void __launch_bounds__(576)
+pit_sse_forward_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
+                       const float* __restrict__ tgt, const float* __restrict__ scale,
+                       const int64_t* __restrict__ meta, int tchunks, int fchunks, int64_t F,
+                       double* __restrict__ partial, int* __restrict__ counters,
+                       float* __restrict__ loss, int32_t* __restrict__ perm, double* __restrict__ sse,
+                       int64_t batch) {
+  constexpr int NV = (DUAL ? 2 : 1) * K * K;
+  extern __shared__ double sm[];  // [NV * nwarps] reduction scratch, then [NV] totals
+  const int b = blockIdx.x;
+  const int chunk = blockIdx.y, nchunks = tchunks * fchunks;
+  const int tc = chunk / fchunks, fc = chunk - tc * fchunks;
+  const int64_t T = meta[b * B2S_PIT_META + 0];
+  const float* m_ = mask + meta[b * B2S_PIT_META + 1];
+  const float* o_ = obs ? obs + meta[b * B2S_PIT_META + 2] : nullptr;
+  const float* x_ = tgt + meta[b * B2S_PIT_META + 3];
+  const float* s_ = scale ? scale + meta[b * B2S_PIT_META + 4] : nullptr;
+  const int64_t t0 = T * tc / tchunks, t1 = T * (tc + 1) / tchunks;
+  const int64_t f0 = F * fc / fchunks, f1 = F * (fc + 1) / fchunks;
+  const int by = blockDim.y;
+
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+
+  auto body = [&](int64_t t, int64_t f) {
+    float e[K], x[K], xs[K];
+    const float o = o_ ? __ldg(o_ + t * F + f) : 1.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      e[i] = __ldg(m_ + (t * K + i) * F + f) * o;
+      x[i] = __ldg(x_ + (t * K + i) * F + f);
+      xs[i] = s_ ? x[i] * __ldg(s_ + (t * K + i) * F + f) : x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (DUAL) {
+          const float d0 = e[i] - x[j], d1 = e[i] - xs[j];
+          acc[i * K + j] = fmaf(d0, d0, acc[i * K + j]);
+          acc[K * K + i * K + j] = fmaf(d1, d1, acc[K * K + i * K + j]);
+        } else {
+          const float d = e[i] - xs[j];
+          acc[i * K + j] = fmaf(d, d, acc[i * K + j]);
+        }
+      }
+  };
+
+  for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+    int64_t t = t0 + threadIdx.y;
+    for (; t + by < t1; t += 2 * by) {  // two frames in flight
+      body(t, f);
+      body(t + by, f);
+    }
+    if (t < t1) body(t, f);
+  }
+
+  // ---- CTA reduction (fixed tree) -> partial[b][chunk][NV]
+  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) sm[i * nwarps + warp] = (double)s;
+  }
+  __syncthreads();
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * NV;
+  for (int i = tid; i < NV; i += nthreads) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sm[i * nwarps + w];
+    mine[i] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (tid == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- last CTA of this example: fold the chunks in order, pick the permutation
+  double* total = sm + NV * nwarps;
+  for (int i = tid; i < NV; i += nthreads) {
+    double s = 0.0;
+    const volatile double* p = partial + (int64_t)b * nchunks * NV + i;
+    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
+    total[i] = s;
+    sse[(int64_t)b * NV + i] = s;
+  }
+  __syncthreads();
+  const double count = (double)T * (double)K * (double)F;
+#pragma unroll
+  for (int slot = 0; slot < (DUAL ? 2 : 1); ++slot) {
+    double best;
+    int bp[B2S_MAX_SOURCES];
+    search_permutations(total + slot * K * K, K, best, bp);
+    if (tid == 0) {
+      loss[slot * batch + b] = (float)(best / count);
+      for (int k = 0; k < K; ++k) perm[(slot * batch + b) * K + k] = bp[k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counters[b] = 0;  // leave the workspace ready for the next call
+}
+
+// grad_mask[t,i,f] = sum_slot c_slot * o * (m*o - x_slot[inv_slot[i]]),  c = grad_loss * 2 / (T K F)
+template <int K, bool DUAL>
+__global__ void __launch_bounds__(576)
+pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
+                        const float* __restrict__ tgt, const float* __restrict__ scale,
+                        const int64_t* __restrict__ meta, int tchunks, int fchunks, int64_t F,
+                        const int32_t* __restrict__ perm, const float* __restrict__ grad_loss,
+                        float* __restrict__ grad_mask, float* __restrict__ grad_target, int64_t batch) {
+  const int b = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int tc = chunk / fchunks, fc = chunk - tc * fchunks;
+  const int64_t T = meta[b * B2S_PIT_META + 0];
+  const float* m_ = mask + meta[b * B2S_PIT_META + 1];
+  const float* o_ = obs ? obs + meta[b * B2S_PIT_META + 2] : nullptr;
+  const float* x_ = tgt + meta[b * B2S_PIT_META + 3];
+  const float* s_ = scale ? scale + meta[b * B2S_PIT_META + 4] : nullptr;
+  float* gm_ = grad_mask + meta[b * B2S_PIT_META + 5];
+  float* gt_ = grad_target ? grad_target + meta[b * B2S_PIT_META + 5] : nullptr;
+  const int64_t t0 = T * tc / tchunks, t1 = T * (tc + 1) / tchunks;
+  const int64_t f0 = F * fc / fchunks, f1 = F * (fc + 1) / fchunks;
+  const double count = (double)T * (double)K * (double)F;
+  int inv0[K], inv1[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i0 = perm[(int64_t)b * K + k];
+#pragma unroll
+    for (int i = 0; i < K; ++i) if (i == i0) inv0[i] = k;
+    if (DUAL) {
+      const int i1 = perm[(batch + b) * K + k];
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (i == i1) inv1[i] = k;
+    }
+  }
+  const float c0 = (float)(2.0 * (double)grad_loss[b] / count);
+  const float c1 = DUAL ? (float)(2.0 * (double)grad_loss[batch + b] / count) : 0.f;
+  for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+    for (int64_t t = t0 + threadIdx.y; t < t1; t += blockDim.y) {
+      const float o = o_ ? __ldg(o_ + t * F + f) : 1.f;
+      float e[K], x[K], xs[K], sc[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        e[i] = __ldg(m_ + (t * K + i) * F + f) * o;
+        x[i] = __ldg(x_ + (t * K + i) * F + f);
+        sc[i] = s_ ? __ldg(s_ + (t * K + i) * F + f) : 1.f;
+        xs[i] = x[i] * sc[i];
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float xa = 0.f, xb = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (inv0[i] == k) xa = DUAL ? x[k] : xs[k];
+          if (DUAL && inv1[i] == k) xb = xs[k];
+        }
+        float g = c0 * (e[i] - xa);
+        if (DUAL) g = fmaf(c1, e[i] - xb, g);
+        gm_[(t * K + i) * F + f] = g * o;
+      }
+      if (gt_) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float ek = 0.f;
+#pragma unroll
+          for (int i = 0; i < K; ++i) if (inv0[i] == k) ek = e[i];
+          gt_[(t * K + k) * F + f] = -c0 * (ek - xs[k]) * sc[k];
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+int launch_forward_k(const float* mask, const float* obs, const float* tgt, const float* scale,
+                     const int64_t* meta, int64_t batch, int64_t max_frames, int64_t F, int dual,
+                     float* loss, int32_t* perm, double* sse, void* workspace, cudaStream_t stream) {
+  const PitGrid g = pit_grid(batch, max_frames, F);
+  const int nv = (dual ? 2 : 1) * K * K;
+  (void)nv;
+  double* partial = ws_partials(workspace);
+  int* counters = ws_counters(workspace);
+  const dim3 grid((unsigned)batch, g.nchunks()), block(g.bx, g.by);
+  const size_t smem = sizeof(double) * nv * (g.threads() / 32 + 1);
+  if (dual)
+    pit_sse_forward_kernel<K, true><<<grid, block, smem, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
+        g.fchunks, F, partial, counters, loss, perm, sse, batch);
+  else
+    pit_sse_forward_kernel<K, false><<<grid, block, smem, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
+        g.fchunks, F, partial, counters, loss, perm, sse, batch);
+  B2S_LAUNCH_CHECK("pit_sse_forward_kernel");
+  return B2S_OK;
+}
+
+template <int K>
+int launch_backward_k(const float* mask, const float* obs, const float* tgt, const float* scale,
+                      const int64_t* meta, int64_t batch, int64_t max_frames, int64_t F, int dual,
+                      const int32_t* perm, const float* grad_loss, float* grad_mask,
+                      float* grad_target, cudaStream_t stream) {
+  PitGrid g = pit_grid(batch, max_frames, F);
+  // elementwise: more CTAs than the reduction wants are fine
+  g.tchunks = (int)std::max<int64_t>(g.tchunks, std::min<int64_t>(max_frames / (4 * g.by) + 1, 64));
+  const dim3 grid((unsigned)batch, g.nchunks()), block(g.bx, g.by);
+  if (dual)
+    pit_sse_backward_kernel<K, true><<<grid, block, 0, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
+        g.fchunks, F, perm, grad_loss, grad_mask, grad_target, batch);
+  else
+    pit_sse_backward_kernel<K, false><<<grid, block, 0, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
+        g.fchunks, F, perm, grad_loss, grad_mask, grad_target, batch);
+  B2S_LAUNCH_CHECK("pit_sse_backward_kernel");
+  return B2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t b2s_pit_workspace_bytes(int64_t batch, int64_t max_frames, int64_t bins, int sources, int dual) {
+  if (batch <= 0 || sources <= 0 || bins <= 0) return 16;
+  const PitGrid g = pit_grid(batch, max_frames, bins);
+  const int64_t nv = (dual ? 2 : 1) * (int64_t)sources * sources;
+  return kTicketBytes + (int64_t)sizeof(double) * batch * g.nchunks() * nv + 16;
+}
+
+int b2s_pit_sse_forward(const float* mask, const float* observation, const float* target,
+                        const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                        int sources, int64_t bins, int dual, float* loss, int32_t* perm, double* sse,
+                        void* workspace, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
+              "sources=%d outside the supported range 1..%d", sources, B2S_MAX_SOURCES);
+  B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
+  B2S_REQUIRE(!dual || scale, "dual PIT needs the target scale (cos phase difference)");
+  if (batch == 0) return B2S_OK;
+  B2S_REQUIRE(mask && target && meta && loss && perm && sse && workspace, "NULL device pointer");
+#define CALL_FWD(K) launch_forward_k<K>(mask, observation, target, scale, meta, batch, max_frames, bins, \
+                                        dual, loss, perm, sse, workspace, (cudaStream_t)stream)
+  switch (sources) {
+    case 1: return CALL_FWD(1);
+    case 2: return CALL_FWD(2);
+    case 3: return CALL_FWD(3);
+    case 4: return CALL_FWD(4);
+    case 5: return CALL_FWD(5);
+    case 6: return CALL_FWD(6);
+    case 7: return CALL_FWD(7);
+    default: return CALL_FWD(8);
+  }
+#undef CALL_FWD
+}
+
+int b2s_pit_sse_backward(const float* mask, const float* observation, const float* target,
+                         const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                         int sources, int64_t bins, int dual, const int32_t* perm,
+                         const float* grad_loss, float* grad_mask, float* grad_target,
+                         b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
+              "sources=%d outside the supported range 1..%d", sources, B2S_MAX_SOURCES);
+  B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
+  B2S_REQUIRE(!(dual && grad_target), "grad_target is not available in dual mode");
+  B2S_REQUIRE(!dual || scale, "dual PIT needs the target scale");
+  if (batch == 0) return B2S_OK;
+  B2S_REQUIRE(mask && target && meta && perm && grad_loss && grad_mask, "NULL device pointer");
+#define CALL_BWD(K) launch_backward_k<K>(mask, observation, target, scale, meta, batch, max_frames, bins, \
+                                         dual, perm, grad_loss, grad_mask, grad_target, (cudaStream_t)stream)
+  switch (sources) {
+    case 1: return CALL_BWD(1);
+    case 2: return CALL_BWD(2);
+    case 3: return CALL_BWD(3);
+    case 4: return CALL_BWD(4);
+    case 5: return CALL_BWD(5);
+    case 6: return CALL_BWD(6);
+    case 7: return CALL_BWD(7);
+    default: return CALL_BWD(8);
+  }
+#undef CALL_BWD
+}
+
+}  // extern "C"

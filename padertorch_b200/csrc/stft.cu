@@ -1,0 +1,480 @@
+// STFT / iSTFT kernels and their C ABI (include/b200sep.h).
+//
+// Two transform engines behind one plan:
+//   * size == 1024: warp-per-frame register FFT (fft1024.cuh); forward fuses zero padding, window,
+//     FFT, real split and the magnitude / log1p epilogue; inverse fuses Hermitian extension, inverse
+//     FFT, synthesis window and overlap-add in shared memory (halo frames recomputed per CTA so no
+//     floating-point atomics are needed).
+//   * every other size (any even size, any window_length <= size, any shift): table-driven DFT,
+//     O(window_length * bins) per frame -- cheap for the short windows of TasNet's StftEncoder
+//     (padertorch/contrib/examples/source_separation/tasnet/tas_coders.py:170) and exact for
+//     non-power-of-two sizes.
+// Reference arithmetic: padertorch/ops/_stft.py:103-263.
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+#include "fft1024.cuh"
+#include "stft_plan.cuh"
+
+using namespace b2s;
+
+
+namespace {
+
+// ------------------------------------------------------------------------------------------- epilogue
+__device__ __forceinline__ void store_bin(float* __restrict__ out, int64_t frame, int k, float2 y,
+                                          int layout, int bins) {
+  if (layout == B2S_SPEC_INTERLEAVED) {
+    reinterpret_cast<float2*>(out)[frame * bins + k] = y;
+  } else if (layout == B2S_SPEC_CONCAT) {
+    out[frame * 2 * bins + k] = y.x;
+    out[frame * 2 * bins + bins + k] = y.y;
+  } else {
+    float m = sqrtf(fmaf(y.x, y.x, y.y * y.y));
+    out[frame * bins + k] = layout == B2S_SPEC_ABS ? m : log1pf(m);
+  }
+}
+
+__device__ __forceinline__ float2 load_bin(const float* __restrict__ in, int64_t frame, int k,
+                                           int layout, int bins) {
+  if (layout == B2S_SPEC_INTERLEAVED) return reinterpret_cast<const float2*>(in)[frame * bins + k];
+  return make_float2(in[frame * 2 * bins + k], in[frame * 2 * bins + bins + k]);
+}
+
+// ------------------------------------------------------------------------------------------- fast forward
+// One warp per frame, persistent over frames.  `win` is the (zero-extended) window the samples are
+// multiplied with: the analysis window for STFT, the synthesis window for the adjoint of iSTFT, in
+// which case interior bins are doubled (`interior_scale` = 2).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
+                        int64_t pad_left, int64_t frames, int shift, int wlen,
+                        const float* __restrict__ win, const float2* __restrict__ twtab, int layout,
+                        float interior_scale, float* __restrict__ out) {
+  __shared__ float2 tiles[8][fft::kHalf];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* tile = tiles[warp];
+  fft::LaneTwiddles<false> tw;
+  tw.init(twtab, lane);
+  // window pairs of this lane's 16 packed samples
+  float2 wa[8], wb[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    wa[r] = reinterpret_cast<const float2*>(win)[lane + 64 * r];
+    wb[r] = reinterpret_cast<const float2*>(win)[lane + 32 + 64 * r];
+  }
+  const int64_t total = rows * frames;
+  for (int64_t fr = (int64_t)blockIdx.x * 8 + warp; fr < total; fr += (int64_t)gridDim.x * 8) {
+    const int64_t row = fr / frames, m = fr - row * frames;
+    const float* xr = x + row * row_stride;
+    const int64_t s0 = m * shift - pad_left;  // signal index of frame sample 0
+    const bool interior = s0 >= 0 && s0 + wlen <= samples && wlen == fft::kSize;
+    float2 ya[8], yb[8];
+    float ydc, ynyq;
+    auto loadz = [&](int n) -> float2 {
+      // n = lane + 64 r (a side) or lane + 32 + 64 r (b side); recover r and side for the window
+      const int q = n - lane;            // 64 r or 32 + 64 r
+      const int r = q >> 6;
+      const bool bside = (q & 32) != 0;
+      float2 w = bside ? wb[r] : wa[r];  // r is a compile-time constant after unrolling
+      float2 v;
+      if (interior) {
+        if (VEC) {
+          v = __ldg(reinterpret_cast<const float2*>(xr + s0) + n);
+        } else {
+          v.x = __ldg(xr + s0 + 2 * n);
+          v.y = __ldg(xr + s0 + 2 * n + 1);
+        }
+      } else {
+        const int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
+        v.x = (2 * n < wlen && i0 >= 0 && i0 < samples) ? __ldg(xr + i0) : 0.f;
+        v.y = (2 * n + 1 < wlen && i1 >= 0 && i1 < samples) ? __ldg(xr + i1) : 0.f;
+      }
+      return make_float2(v.x * w.x, v.y * w.y);
+    };
+    fft::rfft1024(loadz, tile, tw, lane, ya, yb, ydc, ynyq);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int k = fft::bin_a(lane, p);
+      float2 u = ya[p], v = yb[p];
+      u.x *= interior_scale; u.y *= interior_scale; v.x *= interior_scale; v.y *= interior_scale;
+      store_bin(out, fr, k, u, layout, fft::kBins);
+      if (fft::bin_b_valid(lane, p)) store_bin(out, fr, fft::kHalf - k, v, layout, fft::kBins);
+    }
+    if (lane == 0) {
+      store_bin(out, fr, 0, make_float2(ydc, 0.f), layout, fft::kBins);
+      store_bin(out, fr, fft::kHalf, make_float2(ynyq, 0.f), layout, fft::kBins);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- generic forward
+// One CTA per frame: the windowed frame is staged in shared memory, thread f accumulates bin f with
+// the twiddle index (f k mod size) advanced incrementally.
+__global__ void __launch_bounds__(256)
+dft_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
+                   int64_t pad_left, int64_t frames, int size, int shift, int wlen,
+                   const float* __restrict__ win, const float2* __restrict__ twtab, int layout,
+                   float interior_scale, float* __restrict__ out) {
+  extern __shared__ float frame[];
+  const int bins = size / 2 + 1;
+  for (int64_t fr = blockIdx.x; fr < rows * frames; fr += gridDim.x) {
+    const int64_t row = fr / frames, m = fr - row * frames;
+    const float* xr = x + row * row_stride;
+    const int64_t s0 = m * shift - pad_left;
+    __syncthreads();
+    for (int k = threadIdx.x; k < wlen; k += blockDim.x) {
+      const int64_t i = s0 + k;
+      frame[k] = (i >= 0 && i < samples) ? __ldg(xr + i) * win[k] : 0.f;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < bins; f += blockDim.x) {
+      float re = 0.f, im = 0.f;
+      int idx = 0;
+      for (int k = 0; k < wlen; ++k) {
+        const float2 w = __ldg(twtab + idx);
+        const float v = frame[k];
+        re = fmaf(v, w.x, re);
+        im = fmaf(v, w.y, im);
+        idx += f;
+        if (idx >= size) idx -= size;
+      }
+      const float sc = (f == 0 || f == size / 2) ? 1.f : interior_scale;
+      store_bin(out, fr, f, make_float2(re * sc, im * sc), layout, bins);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- fast inverse
+// CTA = (row, chunk of `hops` output hops).  Phase 1: the frames overlapping the chunk are inverse
+// transformed, windowed and parked in shared memory (frame slot == the warp's FFT tile).  Phase 2:
+// every output sample sums its <= ceil(wlen/shift) contributions in increasing frame order.
+constexpr int kInvSlots = 24;  // 24 x 4 KB = 96 KB of shared memory -> 2 CTAs per SM
+
+__global__ void __launch_bounds__(256)
+istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int layout, int shift,
+                 int wlen, int overlap /*ceil(wlen/shift)*/, int hops, int64_t chunks,
+                 int64_t crop_left, int64_t samples_out, const float* __restrict__ win,
+                 const float2* __restrict__ twtab, float interior_in_scale, float* __restrict__ out) {
+  extern __shared__ float2 slots[];  // [kInvSlots][512]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  fft::LaneTwiddles<true> tw;
+  tw.init(twtab, lane);
+  float2 wa[8], wb[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    wa[r] = reinterpret_cast<const float2*>(win)[lane + 64 * r];
+    wb[r] = reinterpret_cast<const float2*>(win)[lane + 32 + 64 * r];
+  }
+  for (int64_t job = blockIdx.x; job < rows * chunks; job += gridDim.x) {
+    const int64_t row = job / chunks, chunk = job - row * chunks;
+    const int64_t h0 = chunk * hops;                       // first hop (padded sample h0*shift)
+    const int64_t m_first = max((int64_t)0, h0 - overlap + 1);
+    const int64_t m_last = min(frames - 1, h0 + hops - 1);  // inclusive
+    __syncthreads();
+    for (int64_t m = m_first + warp; m <= m_last; m += 8) {
+      const int64_t fr = row * frames + m;
+      float2 ya[8], yb[8];
+      float ydc = 0.f, ynyq = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int k = fft::bin_a(lane, p);
+        float2 u = load_bin(spec, fr, k, layout, fft::kBins);
+        float2 v = load_bin(spec, fr, fft::kHalf - k, layout, fft::kBins);
+        ya[p] = make_float2(u.x * interior_in_scale, u.y * interior_in_scale);
+        yb[p] = make_float2(v.x * interior_in_scale, v.y * interior_in_scale);
+      }
+      if (lane == 0) {
+        ydc = load_bin(spec, fr, 0, layout, fft::kBins).x;
+        ynyq = load_bin(spec, fr, fft::kHalf, layout, fft::kBins).x;
+      }
+      float2* tile = slots + (m - m_first) * fft::kHalf;
+      float2 a[8], b[8];
+      fft::irfft1024(ya, yb, ydc, ynyq, tile, tw, lane, a, b);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        tile[lane + 64 * r] = make_float2(a[r].x * wa[r].x, a[r].y * wa[r].y);
+        tile[lane + 32 + 64 * r] = make_float2(b[r].x * wb[r].x, b[r].y * wb[r].y);
+      }
+    }
+    __syncthreads();
+    const float* fbuf = reinterpret_cast<const float*>(slots);
+    const int64_t p_begin = h0 * shift, p_end = p_begin + (int64_t)hops * shift;
+    for (int64_t p = p_begin + threadIdx.x; p < p_end; p += blockDim.x) {
+      const int64_t n = p - crop_left;
+      if (n < 0 || n >= samples_out) continue;
+      // frames m with m*shift <= p < m*shift + wlen
+      int64_t lo = (p - wlen + shift) / shift;  // ceil((p - wlen + 1)/shift) for p - wlen + 1 >= 0
+      if (p - wlen + 1 <= 0) lo = 0;
+      lo = max(lo, m_first);
+      const int64_t hi = min(p / shift, m_last);
+      float acc = 0.f;
+      for (int64_t m = lo; m <= hi; ++m) acc += fbuf[(m - m_first) * fft::kSize + (p - m * shift)];
+      out[row * samples_out + n] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- generic inverse
+// Kernel A: one CTA per frame writes win[k] * (G0 + (-1)^k G_{N/2} + c sum_{0<f<N/2} Re(G_f e^{+i theta}))
+// to scratch[row, m, wlen].  Kernel B gathers the overlap-add.
+__global__ void __launch_bounds__(256)
+dft_inverse_frames_kernel(const float* __restrict__ spec, int64_t total_frames, int layout, int size,
+                          int wlen, const float* __restrict__ win, const float2* __restrict__ twtab,
+                          float interior_scale, float* __restrict__ scratch) {
+  extern __shared__ float2 bins_sm[];
+  const int bins = size / 2 + 1;
+  for (int64_t fr = blockIdx.x; fr < total_frames; fr += gridDim.x) {
+    __syncthreads();
+    for (int f = threadIdx.x; f < bins; f += blockDim.x) bins_sm[f] = load_bin(spec, fr, f, layout, bins);
+    __syncthreads();
+    for (int k = threadIdx.x; k < wlen; k += blockDim.x) {
+      float acc = 0.f;
+      int idx = k;  // (f k) mod size for f = 1
+      for (int f = 1; f < size / 2; ++f) {
+        const float2 w = __ldg(twtab + idx);  // (cos, -sin)
+        const float2 g = bins_sm[f];
+        acc = fmaf(g.x, w.x, acc);
+        acc = fmaf(g.y, w.y, acc);             // Re(g e^{+i theta}) = g.x cos - g.y sin
+        idx += k;
+        if (idx >= size) idx -= size;
+      }
+      const float edge = bins_sm[0].x + ((k & 1) ? -bins_sm[size / 2].x : bins_sm[size / 2].x);
+      scratch[fr * wlen + k] = win[k] * fmaf(interior_scale, acc, edge);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+overlap_add_gather_kernel(const float* __restrict__ scratch, int64_t rows, int64_t frames, int shift,
+                          int wlen, int64_t crop_left, int64_t samples_out, float* __restrict__ out) {
+  const int64_t total = rows * samples_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / samples_out, n = i - row * samples_out;
+    const int64_t p = n + crop_left;
+    int64_t lo = (p - wlen + 1 <= 0) ? 0 : (p - wlen + shift) / shift;
+    const int64_t hi = min(p / shift, frames - 1);
+    float acc = 0.f;
+    for (int64_t m = lo; m <= hi; ++m) acc += scratch[(row * frames + m) * wlen + (p - m * shift)];
+    out[i] = acc;
+  }
+}
+
+int fading_extra(int wlen, int shift, int fading) {
+  if (fading == 0) return 0;
+  return (fading == 2 ? 1 : 2) * (wlen - shift);
+}
+
+int64_t floor_div(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+int check_plan(const b2s_stft_plan* plan) {
+  B2S_REQUIRE(plan != nullptr, "stft plan is NULL");
+  B2S_CUDA(cudaSetDevice(plan->device));
+  return B2S_OK;
+}
+
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
+// forward-type launch shared by b2s_stft_forward and b2s_istft_backward
+int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int64_t samples,
+                   int64_t row_stride, int64_t pad_left, int64_t frames, int layout, const float* win,
+                   float interior_scale, float* out, cudaStream_t stream) {
+  const int64_t total = rows * frames;
+  if (total == 0) return B2S_OK;
+  if (plan->fast) {
+    const int64_t want = ceil_div(total, 8);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 6);
+    const bool vec = aligned8(x) && row_stride % 2 == 0 && plan->shift % 2 == 0 && pad_left % 2 == 0;
+    if (vec)
+      stft1024_forward_kernel<true><<<grid, 256, 0, stream>>>(x, rows, samples, row_stride, pad_left,
+          frames, plan->shift, plan->wlen, win, plan->tw, layout, interior_scale, out);
+    else
+      stft1024_forward_kernel<false><<<grid, 256, 0, stream>>>(x, rows, samples, row_stride, pad_left,
+          frames, plan->shift, plan->wlen, win, plan->tw, layout, interior_scale, out);
+    B2S_LAUNCH_CHECK("stft1024_forward_kernel");
+  } else {
+    const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 64);
+    const size_t smem = sizeof(float) * plan->wlen;
+    dft_forward_kernel<<<grid, 256, smem, stream>>>(x, rows, samples, row_stride, pad_left, frames,
+        plan->size, plan->shift, plan->wlen, win, plan->tw, layout, interior_scale, out);
+    B2S_LAUNCH_CHECK("dft_forward_kernel");
+  }
+  return B2S_OK;
+}
+
+bool fused_inverse_ok(const b2s_stft_plan* plan) {
+  const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
+  return plan->fast && overlap <= 8;
+}
+
+// inverse-type launch shared by b2s_istft_forward and b2s_stft_backward
+int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, int64_t frames,
+                   int layout, int64_t crop_left, int64_t samples_out, const float* win,
+                   float interior_scale /*2: iSTFT, 1: adjoint of STFT*/, float* out, float* scratch,
+                   cudaStream_t stream) {
+  if (rows * samples_out == 0) return B2S_OK;
+  if (frames == 0) {
+    B2S_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * rows * samples_out, stream));
+    return B2S_OK;
+  }
+  if (fused_inverse_ok(plan)) {
+    const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
+    const int hops = kInvSlots - overlap + 1;
+    // padded samples that can receive output: [crop_left, crop_left + samples_out)
+    const int64_t total_hops = ceil_div(crop_left + samples_out, plan->shift);
+    const int64_t chunks = ceil_div(total_hops, hops);
+    const size_t smem = sizeof(float2) * fft::kHalf * kInvSlots;
+    static bool configured[64] = {};
+    if (!configured[plan->device & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(istft1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[plan->device & 63] = true;
+    }
+    const int grid = (int)std::min<int64_t>(rows * chunks, (int64_t)kNumSMs * 2 * 8);
+    // irfft1024 yields S = edge + 2 * interior; the adjoint wants edge + 1 * interior: halve interior bins
+    istft1024_kernel<<<grid, 256, smem, stream>>>(spec, rows, frames, layout, plan->shift, plan->wlen,
+        overlap, hops, chunks, crop_left, samples_out, win, plan->tw, 0.5f * interior_scale, out);
+    B2S_LAUNCH_CHECK("istft1024_kernel");
+  } else {
+    B2S_REQUIRE(scratch != nullptr, "inverse transform of this plan needs scratch (b2s_stft_scratch_bytes)");
+    const int64_t total = rows * frames;
+    const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 64);
+    const size_t smem = sizeof(float2) * plan->bins;
+    dft_inverse_frames_kernel<<<grid, 256, smem, stream>>>(spec, total, layout, plan->size, plan->wlen,
+        win, plan->tw, interior_scale, scratch);
+    B2S_LAUNCH_CHECK("dft_inverse_frames_kernel");
+    const int grid2 = (int)std::min<int64_t>(ceil_div(rows * samples_out, 256), (int64_t)kNumSMs * 32);
+    overlap_add_gather_kernel<<<grid2, 256, 0, stream>>>(scratch, rows, frames, plan->shift, plan->wlen,
+        crop_left, samples_out, out);
+    B2S_LAUNCH_CHECK("overlap_add_gather_kernel");
+  }
+  return B2S_OK;
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int64_t b2s_stft_frames(int64_t samples, int window_length, int shift, int pad, int fading) {
+  const int64_t total = samples + fading_extra(window_length, shift, fading);
+  const int64_t num = total - window_length + shift;
+  return pad ? -floor_div(-num, shift) : floor_div(num, shift);
+}
+
+int64_t b2s_stft_samples(int64_t frames, int window_length, int shift, int fading) {
+  return frames * shift + window_length - shift - fading_extra(window_length, shift, fading);
+}
+
+int64_t b2s_stft_frame_index(int64_t sample_index, int window_length, int shift, int fading) {
+  // PARITY UNPINNED: no reference test pins it; window-centre convention.
+  int64_t offset = 0;
+  if (fading == 2) offset = (window_length - shift) / 2;
+  else if (fading == 1) offset = window_length - shift;
+  const int64_t v = floor_div(sample_index + offset - window_length / 2, shift);
+  return v < 0 ? 0 : v;
+}
+
+int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, int window_length,
+                         const double* analysis_window, const double* synthesis_window) {
+  B2S_REQUIRE(out != nullptr, "plan output pointer is NULL");
+  B2S_REQUIRE(size >= 2 && size % 2 == 0, "only even FFT sizes are supported (got %d)", size);
+  B2S_REQUIRE(size <= 16384, "FFT size %d exceeds the supported maximum 16384", size);
+  B2S_REQUIRE(shift >= 1, "shift must be positive (got %d)", shift);
+  B2S_REQUIRE(window_length >= 1 && window_length <= size,
+              "window_length must be in [1, size] (got %d, size %d)", window_length, size);
+  B2S_REQUIRE(analysis_window && synthesis_window, "window pointers must not be NULL");
+  B2S_CUDA(cudaSetDevice(device));
+  std::vector<float> aw(size, 0.f), sw(size, 0.f);
+  for (int k = 0; k < window_length; ++k) {
+    aw[k] = (float)analysis_window[k];
+    sw[k] = (float)synthesis_window[k];
+  }
+  std::vector<float2> tw(size);
+  for (int q = 0; q < size; ++q) {
+    const double ang = -2.0 * M_PI * (double)q / (double)size;
+    tw[q] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  b2s_stft_plan* plan = new b2s_stft_plan();
+  plan->device = device; plan->size = size; plan->shift = shift; plan->wlen = window_length;
+  plan->bins = size / 2 + 1;
+  plan->fast = size == fft::kSize;
+  plan->awin = nullptr; plan->swin = nullptr; plan->tw = nullptr;
+  cudaError_t e = cudaMalloc(&plan->awin, sizeof(float) * size);
+  if (e == cudaSuccess) e = cudaMalloc(&plan->swin, sizeof(float) * size);
+  if (e == cudaSuccess) e = cudaMalloc(&plan->tw, sizeof(float2) * size);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->awin, aw.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->swin, sw.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(plan->tw, tw.data(), sizeof(float2) * size, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("stft plan allocation failed: %s", cudaGetErrorString(e));
+    b2s_stft_plan_destroy(plan);
+    return B2S_ERR_CUDA;
+  }
+  *out = plan;
+  return B2S_OK;
+}
+
+int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
+  if (!plan) return B2S_OK;
+  cudaSetDevice(plan->device);
+  cudaFree(plan->awin); cudaFree(plan->swin); cudaFree(plan->tw);
+  delete plan;
+  return B2S_OK;
+}
+
+int b2s_stft_plan_is_fast(const b2s_stft_plan* plan) { return plan && plan->fast; }
+
+int64_t b2s_stft_scratch_bytes(const b2s_stft_plan* plan, int64_t rows, int64_t frames) {
+  if (!plan || fused_inverse_ok(plan)) return 0;
+  return (int64_t)sizeof(float) * rows * frames * plan->wlen;
+}
+
+int b2s_stft_forward(const b2s_stft_plan* plan, const float* signal, int64_t rows, int64_t samples,
+                     int64_t row_stride, int64_t pad_left, int64_t frames, int layout, float* spec,
+                     b2s_stream stream) {
+  if (int rc = check_plan(plan)) return rc;
+  B2S_REQUIRE(layout >= 0 && layout <= 3, "unknown spectrum layout %d", layout);
+  B2S_REQUIRE(rows >= 0 && samples >= 0 && frames >= 0 && pad_left >= 0, "negative extent");
+  B2S_REQUIRE(rows * frames == 0 || (signal && spec), "NULL device pointer");
+  return launch_forward(plan, signal, rows, samples, row_stride, pad_left, frames, layout, plan->awin,
+                        1.f, spec, (cudaStream_t)stream);
+}
+
+int b2s_istft_backward(const b2s_stft_plan* plan, const float* grad_signal, int64_t rows,
+                       int64_t samples_out, int64_t crop_left, int64_t frames, int layout,
+                       float* grad_spec, b2s_stream stream) {
+  if (int rc = check_plan(plan)) return rc;
+  B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
+  B2S_REQUIRE(rows * frames == 0 || (grad_signal && grad_spec), "NULL device pointer");
+  // d signal / d Re,Im = c_f * STFT with the synthesis window (c_f = 2 for interior bins)
+  return launch_forward(plan, grad_signal, rows, samples_out, samples_out, crop_left, frames, layout,
+                        plan->swin, 2.f, grad_spec, (cudaStream_t)stream);
+}
+
+int b2s_istft_forward(const b2s_stft_plan* plan, const float* spec, int64_t rows, int64_t frames,
+                      int layout, int64_t crop_left, int64_t samples_out, float* signal,
+                      float* scratch, b2s_stream stream) {
+  if (int rc = check_plan(plan)) return rc;
+  B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
+  B2S_REQUIRE(rows * samples_out == 0 || (spec || frames == 0) && signal, "NULL device pointer");
+  return launch_inverse(plan, spec, rows, frames, layout, crop_left, samples_out, plan->swin, 2.f,
+                        signal, scratch, (cudaStream_t)stream);
+}
+
+int b2s_stft_backward(const b2s_stft_plan* plan, const float* grad_spec, int64_t rows, int64_t frames,
+                      int layout, int64_t pad_left, int64_t samples, float* grad_signal,
+                      float* scratch, b2s_stream stream) {
+  if (int rc = check_plan(plan)) return rc;
+  B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
+  B2S_REQUIRE(rows * samples == 0 || (grad_spec || frames == 0) && grad_signal, "NULL device pointer");
+  return launch_inverse(plan, grad_spec, rows, frames, layout, pad_left, samples, plan->awin, 1.f,
+                        grad_signal, scratch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

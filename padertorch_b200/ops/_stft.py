@@ -1,0 +1,353 @@
+"""Host-side mirror of ``padertorch.ops.STFT`` (padertorch/ops/_stft.py:46-307) over the sm_100a
+kernels of libb200sep.so.  Same constructor, attributes (all of them may be mutated after
+construction, as the reference's tests do with ``stft.fading``), call surface and error behaviour;
+the arithmetic runs in ``b2s_stft_forward`` / ``b2s_istft_forward`` and their adjoints.
+"""
+import ctypes
+import threading
+import typing
+from math import ceil
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+_LEGAL_FADING = [None, True, False, 'full', 'half']
+
+
+def _get_window(window, symmetric_window, window_length):
+    """paderbox ``_get_window`` (call site padertorch/ops/_stft.py:91-95): a name resolves to
+    ``scipy.signal.windows.<name>``; periodic form ``w(L + 1)[:-1]`` unless symmetric."""
+    if isinstance(window, str):
+        from scipy.signal import windows
+        window = getattr(windows, window)
+    if callable(window):
+        if symmetric_window:
+            return np.asarray(window(window_length), dtype=np.float64)
+        return np.asarray(window(window_length + 1), dtype=np.float64)[:-1]
+    window = np.asarray(window, dtype=np.float64)
+    assert window.shape == (window_length,), (window.shape, window_length)
+    return window
+
+
+def _biorthogonal_window(analysis_window, shift):
+    """paderbox ``_biorthogonal_window_fastest`` (call site padertorch/ops/_stft.py:27-28):
+    ``ws[n] = w[n] / sum_j w[(n mod shift) + j shift]^2``."""
+    w = np.asarray(analysis_window, dtype=np.float64)
+    energy = np.zeros_like(w)
+    for r in range(min(shift, len(w))):
+        energy[r::shift] = np.sum(w[r::shift] ** 2)
+    return w / energy
+
+
+def _fading_code(fading):
+    if fading in (None, False):
+        return 0
+    return 2 if fading == 'half' else 1
+
+
+class _Plan:
+    """Owner of a ``b2s_stft_plan`` (immutable device tables for one device and one window)."""
+
+    def __init__(self, device_index, size, shift, window_length, window):
+        lib = _lib.load()
+        synthesis = _biorthogonal_window(window, shift) / size
+        analysis = np.ascontiguousarray(window, dtype=np.float64)
+        synthesis = np.ascontiguousarray(synthesis, dtype=np.float64)
+        handle = ctypes.c_void_p()
+        rc = lib.b2s_stft_plan_create(
+            ctypes.byref(handle), device_index, size, shift, window_length,
+            analysis.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            synthesis.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        _lib.check(rc, 'b2s_stft_plan_create')
+        self.handle = handle
+        self.fast = bool(lib.b2s_stft_plan_is_fast(handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _lib.load().b2s_stft_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+def _plan_for(device, size, shift, window_length, window):
+    key = (device.index, size, shift, window_length, window.tobytes())
+    plan = _plans.get(key)
+    if plan is None:
+        with _plans_lock:     # Trainer's parallel_apply calls us from one thread per GPU
+            plan = _plans.get(key)
+            if plan is None:
+                plan = _Plan(device.index, size, shift, window_length, window)
+                _plans[key] = plan
+    return plan
+
+
+class _STFTForward(torch.autograd.Function):
+    """[rows, T] -> spectrum in a kernel layout; backward = b2s_stft_backward."""
+
+    @staticmethod
+    def forward(ctx, signal, plan, shift, pad_left, frames, layout, bins):
+        lib = _lib.load()
+        rows, samples = signal.shape
+        if layout == _lib.SPEC_INTERLEAVED:
+            out = torch.empty((rows, frames, bins, 2), dtype=torch.float32, device=signal.device)
+        elif layout == _lib.SPEC_CONCAT:
+            out = torch.empty((rows, frames, 2 * bins), dtype=torch.float32, device=signal.device)
+        else:
+            out = torch.empty((rows, frames, bins), dtype=torch.float32, device=signal.device)
+        with torch.cuda.device(signal.device):
+            rc = lib.b2s_stft_forward(plan.handle, _lib.ptr(signal), rows, samples, signal.stride(0),
+                                      pad_left, frames, layout, _lib.ptr(out),
+                                      _lib.stream_of(signal.device))
+        _lib.check(rc, 'b2s_stft_forward')
+        ctx.plan, ctx.pad_left, ctx.layout, ctx.samples = plan, pad_left, layout, samples
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.layout not in (_lib.SPEC_INTERLEAVED, _lib.SPEC_CONCAT):
+            raise NotImplementedError(
+                'the fused magnitude epilogue is forward-only; differentiate through '
+                'STFT(...)(x).abs() instead')
+        lib = _lib.load()
+        grad_out = grad_out.contiguous()
+        rows, frames = grad_out.shape[0], grad_out.shape[1]
+        grad_signal = torch.empty((rows, ctx.samples), dtype=torch.float32, device=grad_out.device)
+        scratch = _scratch(ctx.plan, rows, frames, grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            rc = lib.b2s_stft_backward(ctx.plan.handle, _lib.ptr(grad_out), rows, frames, ctx.layout,
+                                       ctx.pad_left, ctx.samples, _lib.ptr(grad_signal),
+                                       _lib.ptr(scratch), _lib.stream_of(grad_out.device))
+        _lib.check(rc, 'b2s_stft_backward')
+        return grad_signal, None, None, None, None, None, None
+
+
+class _ISTFTForward(torch.autograd.Function):
+    """spectrum [rows, frames, ...] -> [rows, samples_out]; backward = b2s_istft_backward."""
+
+    @staticmethod
+    def forward(ctx, spec, plan, crop_left, samples_out, layout):
+        lib = _lib.load()
+        rows, frames = spec.shape[0], spec.shape[1]
+        signal = torch.empty((rows, samples_out), dtype=torch.float32, device=spec.device)
+        scratch = _scratch(plan, rows, frames, spec.device)
+        with torch.cuda.device(spec.device):
+            rc = lib.b2s_istft_forward(plan.handle, _lib.ptr(spec), rows, frames, layout, crop_left,
+                                       samples_out, _lib.ptr(signal), _lib.ptr(scratch),
+                                       _lib.stream_of(spec.device))
+        _lib.check(rc, 'b2s_istft_forward')
+        ctx.plan, ctx.crop_left, ctx.layout, ctx.spec_shape = plan, crop_left, layout, spec.shape
+        return signal
+
+    @staticmethod
+    def backward(ctx, grad_signal):
+        lib = _lib.load()
+        grad_signal = grad_signal.contiguous()
+        rows, samples_out = grad_signal.shape
+        frames = ctx.spec_shape[1]
+        grad_spec = torch.empty(ctx.spec_shape, dtype=torch.float32, device=grad_signal.device)
+        with torch.cuda.device(grad_signal.device):
+            rc = lib.b2s_istft_backward(ctx.plan.handle, _lib.ptr(grad_signal), rows, samples_out,
+                                        ctx.crop_left, frames, ctx.layout, _lib.ptr(grad_spec),
+                                        _lib.stream_of(grad_signal.device))
+        _lib.check(rc, 'b2s_istft_backward')
+        return grad_spec, None, None, None, None
+
+
+def _scratch(plan, rows, frames, device):
+    nbytes = _lib.load().b2s_stft_scratch_bytes(plan.handle, rows, frames)
+    if nbytes == 0:
+        return None
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
+class STFT:
+    def __init__(
+            self,
+            size: int = 1024,
+            shift: int = 256,
+            *,
+            window: typing.Union[str, typing.Callable] = 'blackman',
+            window_length: int = None,
+            fading: typing.Optional[typing.Union[bool, str]] = 'full',
+            pad: bool = True,
+            symmetric_window: bool = False,
+            complex_representation: str = 'complex'
+    ):
+        """Drop-in for ``padertorch.ops.STFT`` (padertorch/ops/_stft.py:47-101).
+
+        Unlike the reference the object holds no tensors: the fp32 window / twiddle tables live
+        in a per-(device, window) plan inside libb200sep.so, so the object can sit on a module
+        that ``torch.nn.parallel.replicate`` copies (Trainer's multi-GPU branch).
+        """
+        self.possible_out_types = ['concat', 'stacked', 'complex']
+        assert complex_representation in self.possible_out_types, (
+            f'Please choose one of the predefined output_types'
+            f' {self.possible_out_types}, not {complex_representation}'
+        )
+        self.complex_representation = complex_representation
+        assert size % 2 == 0, 'At the moment we only support even FFT sizes'
+        self.size = size
+        self.shift = shift
+        self.window_length = window_length if window_length is not None else size
+        self.window = _get_window(window=window, symmetric_window=symmetric_window,
+                                  window_length=self.window_length)
+        assert fading in _LEGAL_FADING, fading
+        self.fading = fading
+        self.pad = pad
+
+    # ------------------------------------------------------------------ geometry helpers
+    def _pad_widths(self):
+        assert self.fading in _LEGAL_FADING, self.fading
+        if self.fading in (None, False):
+            return 0, 0
+        if self.fading == 'half':
+            return ((self.window_length - self.shift) // 2,
+                    ceil((self.window_length - self.shift) / 2))
+        return self.window_length - self.shift, self.window_length - self.shift
+
+    def _frames_of_call(self, samples):
+        """Frame count ``__call__`` produces (padertorch/ops/_stft.py:137-158: fading pads, tail
+        pad, then a stride-``shift`` convolution over the padded signal)."""
+        left, right = self._pad_widths()
+        length = samples + left + right
+        if self.pad:
+            if length < self.window_length:
+                length = self.window_length
+            elif self.shift != 1 and (length + self.shift - self.window_length) % self.shift != 0:
+                length += self.shift - ((length + self.shift - self.window_length) % self.shift)
+        if length < self.window_length:
+            raise RuntimeError(
+                f'Input of {samples} samples is shorter than the window ({self.window_length}) '
+                f'and pad=False')
+        return (length - self.window_length) // self.shift + 1, left
+
+    def _plan(self, device):
+        return _plan_for(device, self.size, self.shift, self.window_length, self.window)
+
+    def _spectrum(self, inputs, layout):
+        _lib.require_cuda_float(inputs, 'inputs')
+        org_shape = inputs.shape
+        x = inputs.reshape(-1, org_shape[-1])
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        frames, pad_left = self._frames_of_call(org_shape[-1])
+        bins = self.size // 2 + 1
+        out = _STFTForward.apply(x, self._plan(x.device), self.shift, pad_left, frames, layout, bins)
+        return out.view(*org_shape[:-1], *out.shape[1:])
+
+    # ------------------------------------------------------------------ reference call surface
+    def __call__(self, inputs):
+        """
+        Args:
+            inputs: shape: [..., T], T is #samples (float32, CUDA)
+
+        Returns: [..., frames, F] complex64 ('complex'), [..., frames, 2F] ('concat') or
+            [..., frames, F, 2] ('stacked'), as padertorch/ops/_stft.py:160-174.
+        """
+        if self.complex_representation == 'concat':
+            return self._spectrum(inputs, _lib.SPEC_CONCAT)
+        encoded = self._spectrum(inputs, _lib.SPEC_INTERLEAVED)
+        if self.complex_representation == 'stacked':
+            return encoded
+        elif self.complex_representation == 'complex':
+            return torch.view_as_complex(encoded)
+        raise ValueError(
+            f'Please choose one of the predefined output_types'
+            f'{self.possible_out_types} not {self.complex_representation}')
+
+    def magnitude(self, inputs, log1p=False):
+        """Fused feature front-end ``|STFT(x)|`` (or ``log1p|STFT(x)|``, the PIT model's input
+        transform, pit/model.py:93) without materialising the complex spectrum.  Forward only."""
+        layout = _lib.SPEC_LOG1P_ABS if log1p else _lib.SPEC_ABS
+        return self._spectrum(inputs.detach(), layout)
+
+    def inverse(self, stft_signal):
+        """
+        Args:
+            stft_signal: [..., frames, F] complex64, [..., frames, 2F] or [..., frames, F, 2]
+                according to ``complex_representation``.
+
+        Returns: [..., samples] (padertorch/ops/_stft.py:176-263).
+        """
+        if self.complex_representation == 'complex':
+            if not torch.is_complex(stft_signal):
+                raise TypeError('complex_representation="complex" expects a complex tensor')
+            spec = torch.view_as_real(stft_signal)
+            layout = _lib.SPEC_INTERLEAVED
+        elif self.complex_representation == 'stacked':
+            spec, layout = stft_signal, _lib.SPEC_INTERLEAVED
+        elif self.complex_representation == 'concat':
+            spec, layout = stft_signal, _lib.SPEC_CONCAT
+        else:
+            raise ValueError(
+                f'Please choose one of the predefined output_types'
+                f'{self.possible_out_types} not {self.complex_representation}')
+        _lib.require_cuda_float(spec, 'stft_signal')
+        bins = self.size // 2 + 1
+        if layout == _lib.SPEC_INTERLEAVED:
+            assert spec.shape[-2:] == (bins, 2), (spec.shape, bins)
+            lead, frames = spec.shape[:-3], spec.shape[-3]
+        else:
+            assert spec.shape[-1] == 2 * bins, (spec.shape, bins)
+            lead, frames = spec.shape[:-2], spec.shape[-2]
+        spec = spec.reshape(-1, frames, *spec.shape[len(lead) + 1:]).contiguous()
+        total = (frames - 1) * self.shift + self.window_length
+        crop_left, samples_out = 0, total
+        assert self.fading in _LEGAL_FADING, self.fading
+        if self.fading not in [None, False]:
+            pad_width = (self.window_length - self.shift)
+            if self.fading == 'half':
+                pad_width /= 2
+            crop_left = int(pad_width)
+            samples_out = max(total - ceil(pad_width) - crop_left, 0)
+        signal = _ISTFTForward.apply(spec, self._plan(spec.device), crop_left, samples_out, layout)
+        return signal.view(*lead, samples_out)
+
+    def samples_to_frames(self, samples):
+        """Number of STFT frames for a number of samples (padertorch/ops/_stft.py:265-279)."""
+        return _samples_to_stft_frames(samples, self.window_length, self.shift,
+                                       pad=self.pad, fading=self.fading)
+
+    def sample_index_to_frame_index(self, sample_index):
+        """Best frame index for a sample index (padertorch/ops/_stft.py:281-293).  Parity
+        unpinned: no reference test exercises it."""
+        lib = _lib.load()
+        code = _fading_code(self.fading)
+        if np.ndim(sample_index) == 0:
+            return int(lib.b2s_stft_frame_index(int(sample_index), self.window_length, self.shift, code))
+        flat = [lib.b2s_stft_frame_index(int(v), self.window_length, self.shift, code)
+                for v in np.asarray(sample_index).ravel()]
+        return np.asarray(flat, dtype=np.int64).reshape(np.shape(sample_index))
+
+    def frames_to_samples(self, frames):
+        """Samples in the time signal for a number of frames (padertorch/ops/_stft.py:295-307)."""
+        return _stft_frames_to_samples(frames, self.window_length, self.shift, fading=self.fading)
+
+
+def _samples_to_stft_frames(samples, size, shift, *, pad=True, fading=None):
+    """paderbox ``_samples_to_stft_frames`` through the C ABI (ints) or vectorised (arrays)."""
+    assert fading in _LEGAL_FADING, fading
+    code = _fading_code(fading)
+    if np.ndim(samples) == 0 and not isinstance(samples, torch.Tensor):
+        return int(_lib.load().b2s_stft_frames(int(samples), size, shift, int(bool(pad)), code))
+    values = np.asarray(samples)
+    extra = 0 if code == 0 else (1 if code == 2 else 2) * (size - shift)
+    numerator = values + extra - size + shift
+    return -((-numerator) // shift) if pad else numerator // shift
+
+
+def _stft_frames_to_samples(frames, size, shift, fading=None):
+    assert fading in _LEGAL_FADING, fading
+    code = _fading_code(fading)
+    if np.ndim(frames) == 0 and not isinstance(frames, torch.Tensor):
+        return int(_lib.load().b2s_stft_samples(int(frames), size, shift, code))
+    extra = 0 if code == 0 else (1 if code == 2 else 2) * (size - shift)
+    return np.asarray(frames) * shift + size - shift - extra

@@ -1,0 +1,197 @@
+"""Batched replacements for the per-example loss loops of the three hot-path models -- the callers
+one level above the ops:
+
+* ``pit_review_losses``  <- PermutationInvariantTrainingModel.review
+                            (padertorch/contrib/examples/source_separation/pit/model.py:112-140)
+* ``dc_review_loss``     <- DeepClusteringModel.review (padertorch/contrib/tcl/dc.py:76-84)
+* ``tasnet_losses``      <- TasNet.loss (padertorch/contrib/examples/source_separation/tasnet/model.py:154-176)
+* ``stft_mask_pit_step`` <- the STFT -> |.| -> mask -> PIT step of BASELINE.json's metric
+                            (pit/data.py:49-77 + pit/model.py:117-128), one fused kernel.
+
+Each processes the whole (ragged) minibatch in one or two kernel launches and returns the same
+values the reference loops produce: the batch mean of per-example losses.
+"""
+import torch
+
+from . import _lib
+from ._workspace import meta_tensor, workspace
+from .ops.losses import _pairs, _sse
+from .ops.losses.source_separation import DcFunction, DcProblem, _check_dc_target
+from .ops._stft import STFT
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else None
+
+
+def pit_losses_per_example(masks, observations, targets, cos_phase_difference=None, lengths=None):
+    """Per-example PIT losses of a minibatch.
+
+    masks / targets / cos_phase_difference: lists of [T_b, K, F] tensors, or padded [B, T, K, F]
+    tensors with `lengths`; observations: list of [T_b, F] or padded [B, T, F].
+    Returns (mse [B], mse_perm [B, K] int32, ips [B] or None, ips_perm or None).
+    """
+    dual = cos_phase_difference is not None
+    mask_list = _as_list(masks)
+    if mask_list is not None:
+        for m in mask_list:
+            _lib.require_cuda_float(m, 'mask')
+        problem, inputs = _sse.list_problem(mask_list, _as_list(observations), _as_list(targets),
+                                            _as_list(cos_phase_difference) if dual else None, dual)
+        loss, perm, _ = _sse.PitSseFunction.apply(problem, len(inputs), *inputs)
+    else:
+        _lib.require_cuda_float(masks, 'mask')
+        problem, dense = _sse.padded_problem(masks, observations, targets,
+                                             cos_phase_difference if dual else None, lengths, dual)
+        loss, perm, _ = _sse.PitSseFunction.apply(problem, 1, dense)
+    if dual:
+        return loss[0], perm[0], loss[1], perm[1]
+    return loss[0], perm[0], None, None
+
+
+def pit_review_losses(masks, observations, targets, cos_phase_difference=None, lengths=None):
+    """``dict(pit_mse_loss=..., pit_ips_loss=...)`` exactly as the ``losses`` entry of
+    PermutationInvariantTrainingModel.review (pit/model.py:137-140): batch means."""
+    mse, _, ips, _ = pit_losses_per_example(masks, observations, targets, cos_phase_difference, lengths)
+    out = {'pit_mse_loss': mse.mean()}
+    if ips is not None:
+        out['pit_ips_loss'] = ips.mean()
+    return out
+
+
+def dc_losses_per_example(embeddings, target_masks, lengths=None):
+    """Per-example deep-clustering losses.  embeddings: list of [T_b, E, F] (the model's native
+    't e f' layout, tcl/dc.py:66-74) or padded [B, T, E, F] with `lengths`; target_masks likewise
+    [T_b, K, F]."""
+    emb_list = _as_list(embeddings)
+    if emb_list is not None:
+        tgt_list = _as_list(target_masks)
+        emb_list = [e if e.is_contiguous() else e.contiguous() for e in emb_list]
+        tgt_list = [t if t.is_contiguous() else t.contiguous() for t in tgt_list]
+        for e, t in zip(emb_list, tgt_list):
+            _lib.require_cuda_float(e, 'embedding')
+            _lib.require_cuda_float(t, 'target_mask')
+            _check_dc_target(t)
+        e_dim, bins = emb_list[0].shape[1:]
+        k = tgt_list[0].shape[1]
+        rows, splits, cursor = [], [], 0
+        for e, t in zip(emb_list, tgt_list):
+            assert e.shape[1:] == (e_dim, bins) and t.shape == (e.shape[0], k, bins), (e.shape, t.shape)
+            rows.append([e.shape[0], _sse._offset(e, emb_list[0]), _sse._offset(t, tgt_list[0]), cursor])
+            splits.append((cursor, e.numel(), e.shape))
+            cursor += e.numel()
+        meta = meta_tensor(rows, emb_list[0].device)
+        problem = DcProblem(emb_list[0], tgt_list[0], meta, len(emb_list),
+                            max(e.shape[0] for e in emb_list), bins, e_dim, k,
+                            (e_dim * bins, bins, 1), (k * bins, bins, 1), cursor, splits,
+                            (emb_list, tgt_list))
+        return DcFunction.apply(problem, *emb_list)
+    emb = _lib.require_cuda_float(embeddings, 'embedding').contiguous()
+    tgt = _lib.require_cuda_float(target_masks, 'target_mask').contiguous()
+    _check_dc_target(tgt)
+    batch, frames, e_dim, bins = emb.shape
+    k = tgt.shape[2]
+    assert tgt.shape == (batch, frames, k, bins), (emb.shape, tgt.shape)
+    lengths = [frames] * batch if lengths is None else [int(v) for v in lengths]
+    rows = [[lengths[b], b * frames * e_dim * bins, b * frames * k * bins, b * frames * e_dim * bins]
+            for b in range(batch)]
+    meta = meta_tensor(rows, emb.device, cache_key=('dc-padded', frames, e_dim, k, bins, tuple(lengths)))
+    problem = DcProblem(emb, tgt, meta, batch, frames, bins, e_dim, k, (e_dim * bins, bins, 1),
+                        (k * bins, bins, 1), emb.numel(), [(0, emb.numel(), emb.shape)])
+    return DcFunction.apply(problem, emb)
+
+
+def dc_review_loss(embeddings, target_masks, lengths=None):
+    """``dc_loss`` of DeepClusteringModel.review (tcl/dc.py:83-84): batch mean."""
+    return dc_losses_per_example(embeddings, target_masks, lengths).mean()
+
+
+_TASNET_KINDS = {
+    'si-sdr': (_lib.LOSS_SI_SDR, _lib.REDUCE_MEAN),
+    'log-mse': (_lib.LOSS_LOG_MSE, _lib.REDUCE_SUM),
+    'log1p-mse': (_lib.LOSS_LOG1P_MSE, _lib.REDUCE_SUM),
+}
+
+
+class _TasnetFunction(torch.autograd.Function):
+    """One statistics pass, three loss kinds (TasNet.loss evaluates all of them every step)."""
+
+    @staticmethod
+    def forward(ctx, estimate, problem, names):
+        stats = problem.stats()
+        outs, perms = [], []
+        for name in names:
+            kind, reduction = _TASNET_KINDS[name]
+            loss, perm = problem.loss(stats, kind, 0, -1.0, reduction, True)
+            outs.append(loss)
+            perms.append(perm)
+        ctx.problem, ctx.stats, ctx.perms, ctx.names = problem, stats, perms, names
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        total = None
+        for name, perm, grad in zip(ctx.names, ctx.perms, grads):
+            if grad is None:
+                continue
+            kind, reduction = _TASNET_KINDS[name]
+            g = ctx.problem.backward(ctx.stats, kind, 0, -1.0, reduction, True, perm, grad)
+            total = g if total is None else total + g
+        return total, None, None
+
+
+def tasnet_losses(estimates, targets, num_samples, names=('si-sdr', 'log-mse', 'log1p-mse')):
+    """Batch means of ``pit_loss(estimate[..., :n], target[..., :n], axis=0, loss_fn)`` for the three
+    loss functions of TasNet.loss (tasnet/model.py:154-176).  estimates / targets: [B, K, T]."""
+    _lib.require_cuda_float(estimates, 'estimates')
+    _lib.require_cuda_float(targets, 'targets')
+    _pairs.check_target(targets)
+    e = estimates.contiguous()
+    t = targets.contiguous()
+    batch, k, length = e.shape
+    num_samples = [int(n) for n in num_samples]
+    assert len(num_samples) == batch and max(num_samples) <= length, (num_samples, e.shape)
+    rows = [[num_samples[b], b * k * length, b * k * length] for b in range(batch)]
+    meta = meta_tensor(rows, e.device, cache_key=('tasnet', k, length, tuple(num_samples)))
+    problem = _pairs.PairProblem(e, t, meta, batch, 1, k, max(num_samples), length, length)
+    values = _TasnetFunction.apply(e, problem, tuple(names))
+    return {name: v.mean() for name, v in zip(names, values)}
+
+
+def stft_mask_pit_step(mixture, sources, masks, stft=None, observation_abs=None, num_samples=None):
+    """The fused north-star step: per example ``pit_loss(mask * |STFT(y)|[:, None, :],
+    |STFT(s)|, axis=-2)`` with the target spectra recomputed in registers (b2s_stft_pit_forward).
+
+    mixture [B, T] (may be None when `observation_abs` [B, M, F] is given), sources [B, K, T],
+    masks [B, M, K, F].  Returns (loss [B], permutation [B, K] int32).  Forward only.
+    """
+    stft = STFT(1024, 256) if stft is None else stft
+    lib = _lib.load()
+    sources = _lib.require_cuda_float(sources, 'sources').contiguous()
+    masks = _lib.require_cuda_float(masks, 'masks').contiguous()
+    batch, k, samples = sources.shape
+    frames_call, pad_left = stft._frames_of_call(samples)
+    assert masks.shape == (batch, frames_call, k, stft.size // 2 + 1), (masks.shape, frames_call)
+    if mixture is not None:
+        mixture = _lib.require_cuda_float(mixture, 'mixture').contiguous()
+        assert mixture.shape == (batch, samples), (mixture.shape, sources.shape)
+    if observation_abs is not None:
+        observation_abs = _lib.require_cuda_float(observation_abs, 'observation_abs').contiguous()
+        assert observation_abs.shape == (batch, frames_call, stft.size // 2 + 1)
+    meta = None
+    if num_samples is not None:
+        rows = [[int(n), stft._frames_of_call(int(n))[0]] for n in num_samples]
+        meta = meta_tensor(rows, sources.device, cache_key=('fused', tuple(map(tuple, rows))))
+    device = sources.device
+    plan = stft._plan(device)
+    loss = torch.empty(batch, dtype=torch.float32, device=device)
+    perm = torch.empty((batch, k), dtype=torch.int32, device=device)
+    sse = torch.empty((batch, k, k), dtype=torch.float64, device=device)
+    ws = workspace(device, lib.b2s_stft_pit_workspace_bytes(batch, frames_call, k), 'fused')
+    with torch.cuda.device(device):
+        rc = lib.b2s_stft_pit_forward(
+            plan.handle, _lib.ptr(mixture), _lib.ptr(observation_abs), _lib.ptr(sources),
+            _lib.ptr(masks), _lib.ptr(meta), batch, samples, k, frames_call, pad_left, _lib.ptr(loss),
+            _lib.ptr(perm), _lib.ptr(sse), _lib.ptr(ws), _lib.stream_of(device))
+    _lib.check(rc, 'b2s_stft_pit_forward')
+    return loss, perm

@@ -1,0 +1,507 @@
+"""GPU parity: the sm_100a kernels (called through the C ABI via padertorch_b200) against
+
+* the golden fixtures recorded from the UNMODIFIED reference (tests/golden, oracle/make_golden.py),
+* the CPU oracle (oracle/) on fresh seeded inputs,
+* size-independent properties at BASELINE.json's full sizes.
+
+Tolerances follow BASELINE.json's north star: integer results (frame counts, permutations) bit exact;
+fp32 spectra within 1e-4 of the per-tensor maximum; losses within 1e-4 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SPEC_RTOL = 1e-4      # relative to max |reference| of the tensor
+LOSS_RTOL = 1e-4
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def assert_spec_close(got, want, rtol=SPEC_RTOL, what=''):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(float(np.abs(want).max()), 1e-30) if want.size else 1.0
+    err = float(np.abs(got - want).max()) if want.size else 0.0
+    assert err <= rtol * scale, f'{what}: max err {err:.3e} > {rtol} * {scale:.3e}'
+
+
+def assert_loss_close(got, want, rtol=LOSS_RTOL, what=''):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * 1e-2, err_msg=what)
+
+
+@pytest.fixture(scope='module')
+def b2s():
+    import padertorch_b200
+    return padertorch_b200
+
+
+def stft_cases(golden):
+    return sorted(golden.index['stft'])
+
+
+# ------------------------------------------------------------------------------------------------ STFT
+def _stft_case_names():
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'index.json')) as fd:
+        return sorted(json.load(fd)['stft'])
+
+
+@pytest.mark.parametrize('name', _stft_case_names())
+def test_stft_forward_inverse_golden(b2s, golden, name):
+    entry = golden.index['stft'][name]
+    kwargs = dict(entry['kwargs'])
+    x = golden(f'stft/{name}/x').astype(np.float32)
+    reps = [r for r in ('complex', 'concat', 'stacked') if golden.has(f'stft/{name}/{r}')]
+    assert reps
+    for rep in reps:
+        stft = b2s.ops.STFT(complex_representation=rep, **kwargs)
+        out = stft(cuda(x))
+        want = golden(f'stft/{name}/{rep}')
+        assert tuple(out.shape) == want.shape
+        got = out.cpu().numpy()
+        if rep == 'complex':
+            assert out.dtype == torch.complex64
+            got = np.stack([got.real, got.imag], -1)
+            want_cmp = np.stack([want.real, want.imag], -1)
+        else:
+            want_cmp = want
+        assert_spec_close(got, want_cmp, what=f'{name}/{rep}')
+        # inverse of the reference's own spectrum
+        spec = torch.from_numpy(want.astype(np.complex64 if rep == 'complex' else np.float32)).to(dev())
+        back = stft.inverse(spec)
+        assert_spec_close(back.cpu().numpy(), golden(f'stft/{name}/{rep}_inverse'),
+                          what=f'{name}/{rep}_inverse')
+
+
+@pytest.mark.parametrize('name', _stft_case_names())
+def test_stft_frame_arithmetic_golden(b2s, golden, name):
+    entry = golden.index['stft'][name]
+    stft = b2s.ops.STFT(**entry['kwargs'])
+    for samples, frames in entry['frames'].items():
+        assert stft.samples_to_frames(int(samples)) == frames      # bit exact
+    for frames, samples in entry['frames_to_samples'].items():
+        assert stft.frames_to_samples(int(frames)) == samples
+    arr = np.array([int(s) for s in entry['frames']])
+    np.testing.assert_array_equal(stft.samples_to_frames(arr), [entry['frames'][str(s)] for s in arr])
+
+
+@pytest.mark.parametrize('name', _stft_case_names())
+def test_stft_autograd_golden(b2s, golden, name):
+    entry = golden.index['stft'][name]
+    stft = b2s.ops.STFT(complex_representation='stacked', **entry['kwargs'])
+    x = cuda(golden(f'stft/{name}/x').astype(np.float32)).requires_grad_(True)
+    g = cuda(golden(f'stft/{name}/grad_out_stacked').astype(np.float32))
+    out = stft(x)
+    (grad_x,) = torch.autograd.grad((out * g).sum(), x)
+    assert_spec_close(grad_x.cpu().numpy(), golden(f'stft/{name}/grad_x'), what=f'{name}/grad_x')
+    spec = cuda(golden(f'stft/{name}/inv_in_stacked').astype(np.float32)).requires_grad_(True)
+    sig = stft.inverse(spec)
+    assert_spec_close(sig.detach().cpu().numpy(), golden(f'stft/{name}/inv_out'), what=f'{name}/inv_out')
+    gs = cuda(golden(f'stft/{name}/inv_grad_out').astype(np.float32))
+    (grad_spec,) = torch.autograd.grad((sig * gs).sum(), spec)
+    assert_spec_close(grad_spec.cpu().numpy(), golden(f'stft/{name}/inv_grad_in'),
+                      what=f'{name}/inv_grad_in')
+
+
+def test_stft_literal_vector(b2s):
+    # padertorch/contrib/cb/transform.py:219-232
+    expect = np.array([[0.5 + 0j, 0 + 0.5j, -0.5 + 0j],
+                       [4 + 0j, -2 + 1j, 0 + 0j],
+                       [8 + 0j, -4 + 1j, 0 + 0j],
+                       [12 + 0j, -6 + 1j, 0 + 0j],
+                       [3.5 + 0j, 0 - 3.5j, -3.5 + 0j]])
+    out = b2s.ops.STFT(4, 2, window='hann')(cuda(np.arange(8, dtype=np.float32))).cpu().numpy()
+    np.testing.assert_allclose(out, expect, atol=1e-5)
+
+
+@pytest.mark.parametrize('size,shift,wl,samples,plain,faded', [
+    (1024, 256, 1024, (1023, 1024, 1025), (1, 1, 2), (7, 7, 8)),       # tests/test_ops/test_stft.py:44-70
+    (512, 20, 40, (1019, 1020, 1021), (50, 50, 51), (52, 52, 53)),     # :139-165
+])
+def test_stft_frame_counts_reference_tests(b2s, size, shift, wl, samples, plain, faded):
+    stft = b2s.ops.STFT(size, shift, window_length=wl, complex_representation='concat')
+    for fading, expect in ((False, plain), (True, faded)):
+        stft.fading = fading       # mutated after construction, like the reference test
+        for n, m in zip(samples, expect):
+            assert stft(torch.rand(n, device=dev())).shape == (m, 2 * (size // 2 + 1))
+            assert stft.samples_to_frames(n) == m
+
+
+@pytest.mark.parametrize('kwargs', [
+    dict(size=1024, shift=256), dict(size=1024, shift=512, window='hann'),
+    dict(size=1024, shift=128, window='hamming'), dict(size=1024, shift=256, window_length=800),
+    dict(size=1024, shift=300), dict(size=1024, shift=255), dict(size=1024, shift=256, fading='half'),
+    dict(size=1024, shift=256, fading=None, pad=False), dict(size=512, shift=128),
+    dict(size=2048, shift=512), dict(size=400, shift=160, window='hann'),
+])
+def test_stft_against_oracle_fp64(b2s, kwargs):
+    """Fresh inputs, float64 rfft formulation of the oracle as the truth; ragged lengths."""
+    from oracle import stft as OS
+    rng = np.random.RandomState(7)
+    for samples in (5000, 4097, 1000 if kwargs.get('pad', True) else 2100):
+        x = rng.randn(3, samples).astype(np.float32)
+        want = OS.stft_rfft(x.astype(np.float64), **kwargs)
+        stft = b2s.ops.STFT(**kwargs)
+        got = stft(cuda(x)).cpu().numpy()
+        assert_spec_close(np.stack([got.real, got.imag], -1), np.stack([want.real, want.imag], -1),
+                          what=f'{kwargs} T={samples}')
+        mag = stft.magnitude(cuda(x)).cpu().numpy()
+        assert_spec_close(mag, np.abs(want), what=f'abs {kwargs}')
+        lmag = stft.magnitude(cuda(x), log1p=True).cpu().numpy()
+        assert_spec_close(lmag, np.log1p(np.abs(want)), what=f'log1p {kwargs}')
+        back = stft.inverse(torch.from_numpy(want.astype(np.complex64)).to(dev())).cpu().numpy()
+        want_back = OS.istft_rfft(want, **{k: v for k, v in kwargs.items() if k != 'pad'})
+        assert_spec_close(back, want_back, what=f'inverse {kwargs} T={samples}')
+
+
+def test_stft_unaligned_rows_and_views(b2s):
+    """Odd row length / offset views take the scalar-load path; results must not change."""
+    from oracle import stft as OS
+    rng = np.random.RandomState(3)
+    base = rng.randn(4, 7001).astype(np.float32)
+    x = cuda(base)[:, 1:]                      # rows start at odd element offsets
+    want = OS.stft_rfft(base[:, 1:].astype(np.float64), 1024, 256)
+    got = b2s.ops.STFT(1024, 256)(x).cpu().numpy()
+    assert_spec_close(np.stack([got.real, got.imag], -1), np.stack([want.real, want.imag], -1))
+
+
+def test_stft_errors(b2s):
+    with pytest.raises(AssertionError):
+        b2s.ops.STFT(1023, 256)
+    with pytest.raises(AssertionError):
+        b2s.ops.STFT(1024, 256, complex_representation='polar')
+    with pytest.raises(AssertionError):
+        b2s.ops.STFT(1024, 256, fading='quarter')
+    with pytest.raises(RuntimeError):
+        b2s.ops.STFT(1024, 256)(torch.zeros(2, 4000))            # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        b2s.ops.STFT(1024, 256)(torch.zeros(2, 4000, dtype=torch.float64, device=dev()))
+    with pytest.raises(RuntimeError):
+        b2s.ops.STFT(1024, 256, fading=None, pad=False)(torch.zeros(2, 100, device=dev()))
+
+
+# ------------------------------------------------------------------------------------------------ regression
+REGRESSION_FNS = ['mse_loss', 'log_mse_loss', 'log1p_mse_loss', 'sdr_loss', 'si_sdr_loss',
+                  'source_aggregated_sdr_loss']
+
+
+@pytest.mark.parametrize('shape_name', ['k2_t4000', 'k3_t1000', 'b4_k2_t501', 'vec_t100'])
+@pytest.mark.parametrize('fname', REGRESSION_FNS)
+def test_regression_golden(b2s, golden, shape_name, fname):
+    fn = getattr(b2s.ops.losses, fname)
+    for v, kwargs in golden.index['regression'][fname].items():
+        e = cuda(golden(f'regression/{shape_name}/estimate')).requires_grad_(True)
+        t = cuda(golden(f'regression/{shape_name}/target'))
+        out = fn(e, t, **kwargs)
+        want = golden(f'regression/{shape_name}/{fname}/{v}')
+        assert tuple(out.shape) == want.shape, (fname, kwargs, out.shape, want.shape)
+        assert_loss_close(out.detach().cpu().numpy(), want, what=f'{fname} {kwargs}')
+        (grad,) = torch.autograd.grad(out.sum(), e)
+        assert_spec_close(grad.cpu().numpy(), golden(f'regression/{shape_name}/{fname}/{v}/grad'),
+                          rtol=2e-4, what=f'{fname} {kwargs} grad')
+
+
+def test_regression_known_answers(b2s):
+    L = b2s.ops.losses
+    e = torch.tensor([[1., 2, 3], [4, 5, 6]], device=dev())
+    t = torch.tensor([[2., 3, 4], [4, 0, 6]], device=dev())
+    close = lambda a, b: np.testing.assert_allclose(a.cpu().numpy(), b, atol=5e-5)  # noqa: E731
+    close(L.mse_loss(e, t), 9.3333)                                  # regression.py:61-66
+    close(L.mse_loss(e, t, reduction=None), [1.0, 8.3333])
+    close(L.log_mse_loss(e, t), 0.9208)                              # :113-120
+    close(L.log_mse_loss(t, t, soft_sdr_max=20), -1.7758)
+    close(L.sdr_loss(e, t), -6.5167)                                 # :144-155
+    close(L.sdr_loss(e, t, reduction=None), [-9.8528, -3.1806])
+    close(L.sdr_loss(t, t, soft_sdr_max=20), -20.)
+    close(L.si_sdr_loss(e, t), -10.7099)                             # :202-271
+    close(L.si_sdr_loss(e, t, reduction=None), [-18.2391, -3.1806])
+    close(L.log1p_mse_loss(e, t), 1.2711)                            # :331-336
+    close(L.source_aggregated_sdr_loss(e, t), -4.6133)               # :354-366
+    e2 = torch.tensor([[1., 2, 3], [4, 2, 6]], device=dev())
+    t2 = torch.tensor([[2., 3, 4], [6, 4, 8]], device=dev())
+    close(L.source_aggregated_sdr_loss(e2, t2), -9.8528)
+    zero = torch.zeros(2, 3, device=dev())
+    assert torch.isnan(L.si_sdr_loss(zero, t)).all()                 # NaN cases :248-269
+    assert torch.isnan(L.si_sdr_loss(e, zero)).all()
+    assert float(L.si_sdr_loss(t, t)) < -130                         # perfect estimate bound
+
+
+# ------------------------------------------------------------------------------------------------ PIT / DC ops
+def _pit_fn(b2s, name):
+    L = b2s.ops.losses
+    return {'mse': torch.nn.functional.mse_loss, 'pt_mse': L.mse_loss, 'log_mse': L.log_mse_loss,
+            'log1p_mse': L.log1p_mse_loss, 'sdr': L.sdr_loss, 'si_sdr': L.si_sdr_loss}[name]
+
+
+def _pit_cases():
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'index.json')) as fd:
+        index = json.load(fd)['pit']
+    return [(case, fn) for case in sorted(index) for fn in index[case]['loss_fns']]
+
+
+@pytest.mark.parametrize('case,lname', _pit_cases())
+def test_pit_golden(b2s, golden, case, lname):
+    axis = golden.index['pit'][case]['axis']
+    e = cuda(golden(f'pit/{case}/estimate')).requires_grad_(True)
+    t = cuda(golden(f'pit/{case}/target'))
+    loss, perm = b2s.ops.pit_loss(e, t, axis=axis, loss_fn=_pit_fn(b2s, lname), return_permutation=True)
+    assert loss.dim() == 0
+    assert tuple(perm) == tuple(int(v) for v in golden(f'pit/{case}/{lname}/perm'))     # bit exact
+    assert_loss_close(loss.detach().cpu().numpy(), golden(f'pit/{case}/{lname}/loss'), what=f'{case}/{lname}')
+    (grad,) = torch.autograd.grad(loss, e)
+    assert_spec_close(grad.cpu().numpy(), golden(f'pit/{case}/{lname}/grad'), rtol=2e-4,
+                      what=f'{case}/{lname} grad')
+    if golden.has(f'pit/{case}/{lname}/pairwise'):
+        matrix = b2s.ops.compute_pairwise_losses(e.detach(), t, axis=axis, loss_fn=_pit_fn(b2s, lname))
+        assert_spec_close(matrix.cpu().numpy(), golden(f'pit/{case}/{lname}/pairwise'), rtol=2e-4,
+                          what=f'{case}/{lname} pairwise')
+        for red in ('mean', 'sum'):
+            val, cols = b2s.ops.pit_loss_from_loss_matrix(matrix, reduction=red, return_permutation=True)
+            assert_loss_close(val.cpu().numpy(), golden(f'pit/{case}/{lname}/matrix_{red}'), rtol=2e-4)
+        np.testing.assert_array_equal(cols, golden(f'pit/{case}/{lname}/matrix_cols'))
+
+
+def test_pit_known_answers(b2s):
+    pit = b2s.ops.pit_loss
+    d = dev()
+    # source_separation.py:64-93
+    assert float(pit(torch.ones(5, 3, 10, device=d), torch.zeros(5, 3, 10, device=d), axis=-2)) == 1.0
+    t = torch.randn(100, 2, 257, device=d)
+    loss, perm = pit(torch.stack([t[:, 1], t[:, 0]], 1), t, axis=-2, return_permutation=True)
+    assert float(loss) == 0.0 and perm == (1, 0)
+    assert float(pit(torch.ones(2, 3, 4, 5, 6, device=d), torch.zeros(2, 3, 4, 5, 6, device=d), axis=-3)) == 1.0
+    # exact tie: first permutation in itertools order wins (torch.min on CPU)
+    loss, perm = pit(torch.zeros(7, 3, 9, device=d), torch.zeros(7, 3, 9, device=d), axis=1,
+                     return_permutation=True)
+    assert perm == (0, 1, 2) and float(loss) == 0.0
+    # tests/test_ops/test_losses.py:137-150
+    e = torch.tensor([[0.], [2.]], device=d).view(1, 2, 1)
+    assert float(pit(e, torch.tensor([[2.], [0.]], device=d).view(1, 2, 1), axis=1)) == 0.0
+    assert float(pit(e, torch.tensor([[-1.], [0.]], device=d).view(1, 2, 1), axis=1)) == 2.5
+    # generic callable path (cross entropy variant, source_separation.py:86-93)
+    logits = torch.zeros(4, 2, 6, device=d)
+    target = torch.zeros(4, 6, dtype=torch.long, device=d)
+    ce = pit(logits, target, axis=1, loss_fn=torch.nn.functional.cross_entropy)
+    np.testing.assert_allclose(float(ce), 0.6931, atol=1e-4)
+    with pytest.raises(AssertionError):
+        pit(torch.zeros(3, 2, 4, device=d), torch.zeros(3, 2, 5, device=d), axis=1)
+    with pytest.raises(RuntimeError):
+        pit(torch.zeros(3, 2, 4), torch.zeros(3, 2, 4), axis=1)          # CPU: no fallback
+
+
+@pytest.mark.parametrize('k', [1, 2, 3, 4, 5])
+def test_pit_against_oracle_random(b2s, k):
+    from oracle import losses as OL
+    rng = np.random.RandomState(10 + k)
+    for trial in range(3):
+        t = np.abs(rng.randn(41, k, 129)).astype(np.float32)
+        order = rng.permutation(k)
+        e = (t[:, order] + 0.3 * rng.randn(*t.shape)).astype(np.float32)
+        want, want_perm = OL.pit_loss(torch.from_numpy(e).double(), torch.from_numpy(t).double(), axis=-2,
+                                      return_permutation=True)
+        got, perm = b2s.ops.pit_loss(cuda(e), cuda(t), axis=-2, return_permutation=True)
+        assert tuple(perm) == tuple(want_perm)
+        assert_loss_close(got.cpu().numpy(), want.numpy())
+        for fn_name in ('si_sdr_loss', 'log_mse_loss', 'sdr_loss'):
+            tt = rng.randn(k, 3001).astype(np.float32)
+            ee = (tt[rng.permutation(k)] + 0.5 * rng.randn(k, 3001)).astype(np.float32)
+            want, want_perm = OL.pit_loss(torch.from_numpy(ee).double(), torch.from_numpy(tt).double(),
+                                          axis=0, loss_fn=getattr(OL, fn_name), return_permutation=True)
+            got, perm = b2s.ops.pit_loss(cuda(ee), cuda(tt), axis=0,
+                                         loss_fn=getattr(b2s.ops.losses, fn_name), return_permutation=True)
+            assert tuple(perm) == tuple(want_perm), fn_name
+            assert_loss_close(got.cpu().numpy(), want.numpy(), what=fn_name)
+
+
+@pytest.mark.parametrize('case', ['n100_e20_k3', 'n4104_e20_k2', 'n999_e7_k4'])
+def test_dc_golden(b2s, golden, case):
+    x = cuda(golden(f'dc/{case}/x')).requires_grad_(True)
+    t = cuda(golden(f'dc/{case}/t'))
+    loss = b2s.ops.deep_clustering_loss(x, t)
+    assert loss.dim() == 0
+    assert_loss_close(loss.detach().cpu().numpy(), golden(f'dc/{case}/loss'), what=case)
+    (grad,) = torch.autograd.grad(loss, x)
+    assert_spec_close(grad.cpu().numpy(), golden(f'dc/{case}/grad'), rtol=2e-4, what=f'{case} grad')
+
+
+def test_dc_analytic(b2s):
+    # tests/test_ops/test_losses.py:105-116: perfect embedding -> 0; single swapped point -> 4 / N^2 scale
+    n, k = 64, 2
+    labels = np.arange(n) % k
+    t = np.eye(k, dtype=np.float32)[labels]
+    loss = b2s.ops.deep_clustering_loss(cuda(t.copy()), cuda(t))
+    np.testing.assert_allclose(float(loss), 0.0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ model-level
+def test_pit_review_golden(b2s, golden):
+    lengths = golden.index['models']['pit']['lengths']
+    masks = [cuda(golden(f'models/pit/mask_{b}')).requires_grad_(True) for b in range(len(lengths))]
+    y = [cuda(golden(f'models/pit/y_abs_{b}')) for b in range(len(lengths))]
+    x = [cuda(golden(f'models/pit/x_abs_{b}')) for b in range(len(lengths))]
+    cpd = [cuda(golden(f'models/pit/cpd_{b}')) for b in range(len(lengths))]
+    out = b2s.review.pit_review_losses(masks, y, x, cpd)
+    assert_loss_close(out['pit_mse_loss'].detach().cpu().numpy(), golden('models/pit/pit_mse_loss'))
+    assert_loss_close(out['pit_ips_loss'].detach().cpu().numpy(), golden('models/pit/pit_ips_loss'))
+    grads = torch.autograd.grad(out['pit_mse_loss'] + out['pit_ips_loss'], masks)
+    for b, g in enumerate(grads):
+        assert_spec_close(g.cpu().numpy(), golden(f'models/pit/grad_mask_{b}'), rtol=2e-4, what=f'grad {b}')
+    # padded-batch entry point gives the same numbers
+    T = max(lengths)
+    pad = lambda seq: torch.stack([torch.nn.functional.pad(a, (0, 0) * (a.dim() - 1) + (0, T - a.shape[0]))  # noqa: E731
+                                   for a in seq])
+    out2 = b2s.review.pit_review_losses(pad([m.detach() for m in masks]), pad(y), pad(x), pad(cpd), lengths)
+    assert_loss_close(out2['pit_mse_loss'].cpu().numpy(), golden('models/pit/pit_mse_loss'))
+    assert_loss_close(out2['pit_ips_loss'].cpu().numpy(), golden('models/pit/pit_ips_loss'))
+    # minibatch loss == mean of single-example losses (tests/test_models/test_bss.py:57-83)
+    singles = [b2s.review.pit_review_losses([m.detach()], [yy], [xx], [cc])['pit_mse_loss']
+               for m, yy, xx, cc in zip(masks, y, x, cpd)]
+    np.testing.assert_allclose(float(torch.stack(singles).mean()), float(out['pit_mse_loss']), atol=1e-6)
+
+
+def test_dc_review_golden(b2s, golden):
+    lengths = golden.index['models']['dc']['lengths']
+    emb = [cuda(golden(f'models/dc/embedding_{b}')).requires_grad_(True) for b in range(len(lengths))]
+    tm = [cuda(golden(f'models/dc/target_mask_{b}')) for b in range(len(lengths))]
+    loss = b2s.review.dc_review_loss(emb, tm)
+    assert_loss_close(loss.detach().cpu().numpy(), golden('models/dc/dc_loss'))
+    grads = torch.autograd.grad(loss, emb)
+    for b, g in enumerate(grads):
+        assert_spec_close(g.cpu().numpy(), golden(f'models/dc/grad_embedding_{b}'), rtol=2e-4, what=f'grad {b}')
+    T = max(lengths)
+    pad = lambda seq: torch.stack([torch.nn.functional.pad(a.detach(), (0, 0, 0, 0, 0, T - a.shape[0])) for a in seq])  # noqa: E731
+    loss2 = b2s.review.dc_review_loss(pad(emb), pad(tm), lengths)
+    assert_loss_close(loss2.cpu().numpy(), golden('models/dc/dc_loss'))
+
+
+def test_tasnet_losses_golden(b2s, golden):
+    num_samples = golden.index['models']['tasnet']['num_samples']
+    s = cuda(golden('models/tasnet/s'))
+    est = cuda(golden('models/tasnet/estimate')).requires_grad_(True)
+    out = b2s.review.tasnet_losses(est, s, num_samples)
+    for name in ('si-sdr', 'log-mse', 'log1p-mse'):
+        assert_loss_close(out[name].detach().cpu().numpy(), golden(f'models/tasnet/{name}'), what=name)
+        (grad,) = torch.autograd.grad(out[name], est, retain_graph=True)
+        assert_spec_close(grad.cpu().numpy(), golden(f'models/tasnet/{name}/grad'), rtol=2e-4, what=name)
+
+
+# ------------------------------------------------------------------------------------------------ fused step
+def test_fused_step_golden(b2s, golden):
+    y, s, masks = cuda(golden('step/y')), cuda(golden('step/s')), cuda(golden('step/masks'))
+    stft = b2s.ops.STFT(1024, 256)
+    y_abs = stft.magnitude(y)
+    assert_spec_close(y_abs.cpu().numpy(), golden('step/Y_abs'))
+    for kwargs in (dict(mixture=y), dict(mixture=None, observation_abs=y_abs)):
+        loss, perm = b2s.review.stft_mask_pit_step(sources=s, masks=masks, stft=stft, **kwargs)
+        np.testing.assert_array_equal(perm.cpu().numpy(), golden('step/perm'))          # bit exact
+        assert_loss_close(loss.cpu().numpy(), golden('step/loss'))
+    # un-fused composition of the same kernels agrees
+    x_abs = stft.magnitude(s).transpose(1, 2).contiguous()
+    mse, perm2, _, _ = b2s.review.pit_losses_per_example(masks, y_abs, x_abs)
+    np.testing.assert_array_equal(perm2.cpu().numpy(), golden('step/perm'))
+    assert_loss_close(mse.cpu().numpy(), golden('step/loss'))
+
+
+@pytest.mark.parametrize('k,seconds', [(2, 1.0), (3, 0.7)])
+def test_fused_step_against_oracle(b2s, k, seconds):
+    from oracle import path as OP
+    rng = np.random.RandomState(21)
+    B, T = 3, int(16000 * seconds)
+    s = (0.1 * rng.randn(B, k, T)).astype(np.float32)
+    y = s.sum(1)
+    stft = b2s.ops.STFT(1024, 256)
+    M = stft.samples_to_frames(T)
+    masks = rng.rand(B, M, k, 513).astype(np.float32)
+    want_loss, want_perm, want_yabs = OP.stft_mask_pit_step(torch.from_numpy(y), torch.from_numpy(s),
+                                                            torch.from_numpy(masks))
+    loss, perm = b2s.review.stft_mask_pit_step(cuda(y), cuda(s), cuda(masks), stft=stft)
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.asarray(want_perm))
+    assert_loss_close(loss.cpu().numpy(), want_loss.numpy())
+    # ragged: per-example lengths
+    num_samples = [T, T - 1234, T - 4000]
+    loss_r, perm_r = b2s.review.stft_mask_pit_step(cuda(y), cuda(s), cuda(masks), stft=stft,
+                                                   num_samples=num_samples)
+    for b, n in enumerate(num_samples):
+        m_b = stft.samples_to_frames(n)
+        w_loss, w_perm, _ = OP.stft_mask_pit_step(torch.from_numpy(y[b:b + 1, :n]),
+                                                  torch.from_numpy(s[b:b + 1, :, :n]),
+                                                  torch.from_numpy(masks[b:b + 1, :m_b]))
+        assert tuple(perm_r[b].tolist()) == tuple(w_perm[0])
+        assert_loss_close(loss_r[b].cpu().numpy(), w_loss[0].numpy())
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_properties(b2s):
+    """BASELINE.json's headline shape: batch 64 x 4 s x 16 kHz, 2 speakers, STFT(1024, 256)."""
+    torch.manual_seed(0)
+    d = dev()
+    B, K, T = 64, 2, 64000
+    s = 0.1 * torch.randn(B, K, T, device=d)
+    y = s.sum(1)
+    stft = b2s.ops.STFT(1024, 256)
+    Y = stft(y)
+    assert Y.shape == (B, 253, 513) and Y.dtype == torch.complex64
+    # round trip (tests/test_ops/test_stft.py:36-42)
+    back = stft.inverse(Y)
+    assert back.shape == (B, T)
+    assert float((back - y).abs().max()) <= 1e-4 * float(y.abs().max())
+    # linearity: STFT(y) == sum_k STFT(s_k)
+    S = stft(s)
+    assert float((S.sum(1) - Y).abs().max()) <= 1e-4 * float(Y.abs().max())
+    # Parseval-style checksum against the time domain (window energy is folded in by the round trip)
+    y_abs = stft.magnitude(y)
+    assert float((y_abs - Y.abs()).abs().max()) <= 1e-4 * float(y_abs.max())
+    # ideal-ratio masks with a known swap: permutation must follow the swap, bit exact
+    x_abs = S.abs().transpose(1, 2).contiguous()                  # [B, M, K, F]
+    ideal = x_abs / (y_abs[:, :, None, :] + 1e-3)
+    swap = torch.arange(B, device=d) % 3 == 0
+    masks = torch.where(swap[:, None, None, None], ideal.flip(2), ideal).contiguous()
+    loss, perm = b2s.review.stft_mask_pit_step(y, s, masks, stft=stft)
+    want = torch.where(swap[:, None], torch.tensor([1, 0], device=d), torch.tensor([0, 1], device=d))
+    assert torch.equal(perm.long(), want)
+    loss2, perm2 = b2s.review.stft_mask_pit_step(None, s, masks, stft=stft, observation_abs=y_abs)
+    assert torch.equal(perm2, perm)
+    mse, perm3, _, _ = b2s.review.pit_losses_per_example(masks, y_abs, x_abs)
+    assert torch.equal(perm3, perm)
+    torch.testing.assert_close(loss, mse, rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(loss2, mse, rtol=1e-4, atol=1e-9)
+    # determinism (Trainer.test_run compares two runs at 1e-5 / 1e-6): bit identical here
+    loss_again, _ = b2s.review.stft_mask_pit_step(y, s, masks, stft=stft)
+    assert torch.equal(loss, loss_again)
+    assert torch.equal(torch.view_as_real(stft(y)), torch.view_as_real(Y))
+
+
+def test_three_speaker_eight_seconds(b2s):
+    """BASELINE config 5 shape: 3 speakers, 8 s (503 frames), 3! permutations."""
+    from oracle import losses as OL
+    torch.manual_seed(1)
+    d = dev()
+    B, K, T = 4, 3, 128000
+    s = 0.1 * torch.randn(B, K, T, device=d)
+    y = s.sum(1)
+    stft = b2s.ops.STFT(1024, 256)
+    y_abs, x_abs = stft.magnitude(y), stft.magnitude(s).transpose(1, 2).contiguous()
+    assert y_abs.shape == (B, 503, 513)
+    masks = torch.rand(B, 503, K, 513, device=d)
+    order = [(2, 0, 1), (0, 1, 2), (1, 2, 0), (2, 1, 0)]
+    for b, o in enumerate(order):
+        masks[b] = (x_abs[b] / (y_abs[b][:, None] + 1e-3))[:, list(o)]
+    loss, perm = b2s.review.stft_mask_pit_step(y, s, masks, stft=stft)
+    for b in range(B):
+        w, wp = OL.pit_loss((masks[b] * y_abs[b][:, None]).cpu().double(), x_abs[b].cpu().double(), axis=-2,
+                            return_permutation=True)
+        assert tuple(perm[b].tolist()) == tuple(wp)
+        assert_loss_close(loss[b].cpu().numpy(), w.numpy())
