@@ -43,70 +43,152 @@ __device__ __forceinline__ float2 load_bin(const float* __restrict__ in, int64_t
 }
 
 // ------------------------------------------------------------------------------------------- fast forward
+template <int LAYOUT>
+__device__ __forceinline__ void store_bin_t(float* __restrict__ out, int k, float2 y) {
+  // `out` already points at the frame's first bin
+  if (LAYOUT == B2S_SPEC_INTERLEAVED) {
+    reinterpret_cast<float2*>(out)[k] = y;
+  } else if (LAYOUT == B2S_SPEC_CONCAT) {
+    out[k] = y.x;
+    out[fft::kBins + k] = y.y;
+  } else {
+    const float m = fft::sqrt_approx(fmaf(y.x, y.x, y.y * y.y));
+    out[k] = LAYOUT == B2S_SPEC_ABS ? m : log1pf(m);
+  }
+}
+
+constexpr int kFwdWarps = 4;
+
 // One warp per frame, persistent over frames.  `win` is the (zero-extended) window the samples are
 // multiplied with: the analysis window for STFT, the synthesis window for the adjoint of iSTFT, in
 // which case interior bins are doubled (`interior_scale` = 2).
-template <bool VEC>
-__global__ void __launch_bounds__(256)
+template <int LAYOUT, bool VEC>
+__global__ void __launch_bounds__(32 * kFwdWarps, 3)
 stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                         int64_t pad_left, int64_t frames, int shift, int wlen,
-                        const float* __restrict__ win, const float2* __restrict__ twtab, int layout,
+                        const float* __restrict__ win, const float2* __restrict__ twtab,
                         float interior_scale, float* __restrict__ out) {
-  __shared__ float2 tiles[8][fft::kHalf];
+  __shared__ float2 tiles[kFwdWarps][fft::kTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* tile = tiles[warp];
-  fft::LaneTwiddles<false> tw;
-  tw.init(twtab, lane);
-  // window pairs of this lane's 16 packed samples
+  fft::LaneConsts<false> k;
+  k.init(twtab, lane);
+  float2 wa[8], wb[8];   // window pairs of this lane's 16 packed samples
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
+    wb[r] = reinterpret_cast<const float2*>(win)[fft::natural_b(lane, r)];
+  }
+  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins;
+  const int64_t total = rows * frames;
+  for (int64_t fr = (int64_t)blockIdx.x * kFwdWarps + warp; fr < total;
+       fr += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t row = fr / frames, m = fr - row * frames;
+    float2 a[8], b[8], ya[8], yb[8];
+    float ydc, ynyq;
+    fft::load_frame<VEC>(x + row * row_stride, m * shift - pad_left, samples, wlen, lane, a, b);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a[r].x *= wa[r].x; a[r].y *= wa[r].y; b[r].x *= wb[r].x; b[r].y *= wb[r].y;
+    }
+    fft::rfft1024(a, b, tile, k, ya, yb, ydc, ynyq);
+    float* o = out + fr * kOutPerFrame;
+    const int k0 = fft::bin_a(lane, 0), k4 = fft::bin_a(lane, 4);   // slots 0..3 / 4..7 step by 64 bins
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int kk = (p < 4 ? k0 : k4 - 256) + 64 * p;
+      float2 u = ya[p], v = yb[p];
+      if (interior_scale != 1.f) {
+        u.x *= interior_scale; u.y *= interior_scale; v.x *= interior_scale; v.y *= interior_scale;
+      }
+      store_bin_t<LAYOUT>(o, kk, u);
+      if (p < 7 || lane != 0) store_bin_t<LAYOUT>(o, fft::kHalf - kk, v);
+    }
+    if (lane == 0) {
+      store_bin_t<LAYOUT>(o, 0, make_float2(ydc, 0.f));
+      store_bin_t<LAYOUT>(o, fft::kHalf, make_float2(ynyq, 0.f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- staged forward
+// Same transform, different feeding: a CTA of 4 warps takes 4 consecutive frames of one signal row per
+// iteration.  The 3*shift + 1024 samples they cover are brought into shared memory ONCE (frames overlap
+// 4x at shift 256) by 16-byte cp.async with zero fill outside the signal (the fading and tail pads), double
+// buffered so the copy of group i+1 is in flight while group i is transformed.  Needs 16-byte aligned rows.
+template <int LAYOUT, bool DOUBLE_INTERIOR>
+__global__ void __launch_bounds__(32 * kFwdWarps, 3)
+stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
+                       int64_t pad_left, int64_t frames, int shift, const float* __restrict__ win,
+                       const float2* __restrict__ twtab, float* __restrict__ out) {
+  extern __shared__ __align__(16) float stage[];   // [2][span]
+  __shared__ float2 tiles[kFwdWarps][fft::kTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int span = (kFwdWarps - 1) * shift + fft::kSize;
+  float2* tile = tiles[warp];
+  fft::LaneConsts<false> k;
+  k.init(twtab, lane);
   float2 wa[8], wb[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    wa[r] = reinterpret_cast<const float2*>(win)[lane + 64 * r];
-    wb[r] = reinterpret_cast<const float2*>(win)[lane + 32 + 64 * r];
+    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
+    wb[r] = reinterpret_cast<const float2*>(win)[fft::natural_b(lane, r)];
   }
-  const int64_t total = rows * frames;
-  for (int64_t fr = (int64_t)blockIdx.x * 8 + warp; fr < total; fr += (int64_t)gridDim.x * 8) {
-    const int64_t row = fr / frames, m = fr - row * frames;
-    const float* xr = x + row * row_stride;
-    const int64_t s0 = m * shift - pad_left;  // signal index of frame sample 0
-    const bool interior = s0 >= 0 && s0 + wlen <= samples && wlen == fft::kSize;
-    float2 ya[8], yb[8];
-    float ydc, ynyq;
-    auto loadz = [&](int n) -> float2 {
-      // n = lane + 64 r (a side) or lane + 32 + 64 r (b side); recover r and side for the window
-      const int q = n - lane;            // 64 r or 32 + 64 r
-      const int r = q >> 6;
-      const bool bside = (q & 32) != 0;
-      float2 w = bside ? wb[r] : wa[r];  // r is a compile-time constant after unrolling
-      float2 v;
-      if (interior) {
-        if (VEC) {
-          v = __ldg(reinterpret_cast<const float2*>(xr + s0) + n);
-        } else {
-          v.x = __ldg(xr + s0 + 2 * n);
-          v.y = __ldg(xr + s0 + 2 * n + 1);
-        }
-      } else {
-        const int64_t i0 = s0 + 2 * n, i1 = i0 + 1;
-        v.x = (2 * n < wlen && i0 >= 0 && i0 < samples) ? __ldg(xr + i0) : 0.f;
-        v.y = (2 * n + 1 < wlen && i1 >= 0 && i1 < samples) ? __ldg(xr + i1) : 0.f;
-      }
-      return make_float2(v.x * w.x, v.y * w.y);
-    };
-    fft::rfft1024(loadz, tile, tw, lane, ya, yb, ydc, ynyq);
+  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins;
+  // group indices fit 32 bits (checked by the launcher)
+  const unsigned groups_per_row = (unsigned)ceil_div(frames, kFwdWarps);
+  const unsigned total_groups = (unsigned)rows * groups_per_row;
+  unsigned g = blockIdx.x;
+  if (g < total_groups) {
+    const unsigned row = g / groups_per_row, m0 = (g - row * groups_per_row) * kFwdWarps;
+    fft::stage_group(stage, x + (int64_t)row * row_stride, (int64_t)m0 * shift - pad_left, span, samples);
+  }
+  fft::cp_async_commit();
+  int cur = 0;
+  for (; g < total_groups; g += gridDim.x, cur ^= 1) {
+    const unsigned row = g / groups_per_row, m0 = (g - row * groups_per_row) * kFwdWarps;
+    fft::cp_async_wait_all();
+    __syncthreads();   // group g is visible to every warp; everyone is done with the other buffer
+    const unsigned gn = g + gridDim.x;
+    if (gn < total_groups) {
+      const unsigned rown = gn / groups_per_row, mn = (gn - rown * groups_per_row) * kFwdWarps;
+      fft::stage_group(stage + (cur ^ 1) * span, x + (int64_t)rown * row_stride, (int64_t)mn * shift - pad_left,
+                  span, samples);
+    }
+    fft::cp_async_commit();
+    const int64_t m = m0 + warp;
+    if (m < frames) {
+      const float2* src = reinterpret_cast<const float2*>(stage + cur * span + warp * shift);
+      float2 a[8], b[8], ya[8], yb[8];
+      float ydc, ynyq;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int k = fft::bin_a(lane, p);
-      float2 u = ya[p], v = yb[p];
-      u.x *= interior_scale; u.y *= interior_scale; v.x *= interior_scale; v.y *= interior_scale;
-      store_bin(out, fr, k, u, layout, fft::kBins);
-      if (fft::bin_b_valid(lane, p)) store_bin(out, fr, fft::kHalf - k, v, layout, fft::kBins);
-    }
-    if (lane == 0) {
-      store_bin(out, fr, 0, make_float2(ydc, 0.f), layout, fft::kBins);
-      store_bin(out, fr, fft::kHalf, make_float2(ynyq, 0.f), layout, fft::kBins);
+      for (int r = 0; r < 8; ++r) {
+        const float2 va = src[fft::natural_a(lane, r)], vb = src[fft::natural_b(lane, r)];
+        a[r] = make_float2(va.x * wa[r].x, va.y * wa[r].y);
+        b[r] = make_float2(vb.x * wb[r].x, vb.y * wb[r].y);
+      }
+      fft::rfft1024(a, b, tile, k, ya, yb, ydc, ynyq);
+      float* o = out + (row * frames + m) * kOutPerFrame;
+      // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
+      float* oa0 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * fft::bin_a(lane, 0);
+      float* oa4 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::bin_a(lane, 4) - 256);
+      float* ob0 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::kHalf - fft::bin_a(lane, 0));
+      float* ob4 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::kHalf + 256 - fft::bin_a(lane, 4));
+      constexpr int kStep = (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * 64;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        float2 u = ya[p], v = yb[p];
+        if (DOUBLE_INTERIOR) { u.x *= 2.f; u.y *= 2.f; v.x *= 2.f; v.y *= 2.f; }
+        store_bin_t<LAYOUT>((p < 4 ? oa0 : oa4) + kStep * p, 0, u);
+        if (p < 7 || lane != 0) store_bin_t<LAYOUT>((p < 4 ? ob0 : ob4) - kStep * p, 0, v);
+      }
+      if (lane == 0) {
+        store_bin_t<LAYOUT>(o, 0, make_float2(ydc, 0.f));
+        store_bin_t<LAYOUT>(o, fft::kHalf, make_float2(ynyq, 0.f));
+      }
     }
   }
+  fft::cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------- generic forward
@@ -150,22 +232,22 @@ dft_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, i
 // CTA = (row, chunk of `hops` output hops).  Phase 1: the frames overlapping the chunk are inverse
 // transformed, windowed and parked in shared memory (frame slot == the warp's FFT tile).  Phase 2:
 // every output sample sums its <= ceil(wlen/shift) contributions in increasing frame order.
-constexpr int kInvSlots = 24;  // 24 x 4 KB = 96 KB of shared memory -> 2 CTAs per SM
+constexpr int kInvSlots = 24;  // 24 x 4.25 KB = 102 KB of shared memory -> 2 CTAs per SM
 
 __global__ void __launch_bounds__(256)
 istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int layout, int shift,
                  int wlen, int overlap /*ceil(wlen/shift)*/, int hops, int64_t chunks,
                  int64_t crop_left, int64_t samples_out, const float* __restrict__ win,
                  const float2* __restrict__ twtab, float interior_in_scale, float* __restrict__ out) {
-  extern __shared__ float2 slots[];  // [kInvSlots][512]
+  extern __shared__ float2 slots[];  // [kInvSlots][kTile]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  fft::LaneTwiddles<true> tw;
-  tw.init(twtab, lane);
+  fft::LaneConsts<true> k;
+  k.init(twtab, lane);
   float2 wa[8], wb[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    wa[r] = reinterpret_cast<const float2*>(win)[lane + 64 * r];
-    wb[r] = reinterpret_cast<const float2*>(win)[lane + 32 + 64 * r];
+    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
+    wb[r] = reinterpret_cast<const float2*>(win)[fft::mirrored_b(lane, r)];
   }
   for (int64_t job = blockIdx.x; job < rows * chunks; job += gridDim.x) {
     const int64_t row = job / chunks, chunk = job - row * chunks;
@@ -179,9 +261,9 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
       float ydc = 0.f, ynyq = 0.f;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        const int k = fft::bin_a(lane, p);
-        float2 u = load_bin(spec, fr, k, layout, fft::kBins);
-        float2 v = load_bin(spec, fr, fft::kHalf - k, layout, fft::kBins);
+        const int kk = fft::bin_a(lane, p);
+        float2 u = load_bin(spec, fr, kk, layout, fft::kBins);
+        float2 v = load_bin(spec, fr, fft::kHalf - kk, layout, fft::kBins);
         ya[p] = make_float2(u.x * interior_in_scale, u.y * interior_in_scale);
         yb[p] = make_float2(v.x * interior_in_scale, v.y * interior_in_scale);
       }
@@ -189,13 +271,13 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
         ydc = load_bin(spec, fr, 0, layout, fft::kBins).x;
         ynyq = load_bin(spec, fr, fft::kHalf, layout, fft::kBins).x;
       }
-      float2* tile = slots + (m - m_first) * fft::kHalf;
+      float2* tile = slots + (m - m_first) * fft::kTile;
       float2 a[8], b[8];
-      fft::irfft1024(ya, yb, ydc, ynyq, tile, tw, lane, a, b);
+      fft::irfft1024(ya, yb, ydc, ynyq, tile, k, a, b);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        tile[lane + 64 * r] = make_float2(a[r].x * wa[r].x, a[r].y * wa[r].y);
-        tile[lane + 32 + 64 * r] = make_float2(b[r].x * wb[r].x, b[r].y * wb[r].y);
+        tile[fft::natural_a(lane, r)] = make_float2(a[r].x * wa[r].x, a[r].y * wa[r].y);
+        tile[fft::mirrored_b(lane, r)] = make_float2(b[r].x * wb[r].x, b[r].y * wb[r].y);
       }
     }
     __syncthreads();
@@ -210,7 +292,7 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
       lo = max(lo, m_first);
       const int64_t hi = min(p / shift, m_last);
       float acc = 0.f;
-      for (int64_t m = lo; m <= hi; ++m) acc += fbuf[(m - m_first) * fft::kSize + (p - m * shift)];
+      for (int64_t m = lo; m <= hi; ++m) acc += fbuf[(m - m_first) * (2 * fft::kTile) + (p - m * shift)];
       out[row * samples_out + n] = acc;
     }
   }
@@ -287,16 +369,44 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                    float interior_scale, float* out, cudaStream_t stream) {
   const int64_t total = rows * frames;
   if (total == 0) return B2S_OK;
-  if (plan->fast) {
-    const int64_t want = ceil_div(total, 8);
-    const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 6);
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && row_stride % 4 == 0 &&
+                         plan->shift % 4 == 0 && pad_left % 4 == 0;
+  if (plan->fast && plan->wlen == fft::kSize && aligned16 && plan->shift <= fft::kSize &&
+      rows * ceil_div(frames, kFwdWarps) < (int64_t)1 << 30) {
+    const int64_t groups = rows * ceil_div(frames, kFwdWarps);
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * 3);
+    const int span = (kFwdWarps - 1) * plan->shift + fft::kSize;
+    const size_t smem = sizeof(float) * 2 * span;
+#define B2S_STAGED(L, D)                                                                                \
+    stft1024_staged_kernel<L, D><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows, samples, row_stride,  \
+        pad_left, frames, plan->shift, win, plan->tw, out)
+    const bool twice = interior_scale == 2.f;
+    switch (layout) {
+      case B2S_SPEC_INTERLEAVED: if (twice) B2S_STAGED(B2S_SPEC_INTERLEAVED, true); else B2S_STAGED(B2S_SPEC_INTERLEAVED, false); break;
+      case B2S_SPEC_CONCAT: if (twice) B2S_STAGED(B2S_SPEC_CONCAT, true); else B2S_STAGED(B2S_SPEC_CONCAT, false); break;
+      case B2S_SPEC_ABS: B2S_STAGED(B2S_SPEC_ABS, false); break;
+      default: B2S_STAGED(B2S_SPEC_LOG1P_ABS, false); break;
+    }
+#undef B2S_STAGED
+    B2S_LAUNCH_CHECK("stft1024_staged_kernel");
+  } else if (plan->fast) {
+    const int64_t want = ceil_div(total, kFwdWarps);
+    const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 3 * 4);
     const bool vec = aligned8(x) && row_stride % 2 == 0 && plan->shift % 2 == 0 && pad_left % 2 == 0;
-    if (vec)
-      stft1024_forward_kernel<true><<<grid, 256, 0, stream>>>(x, rows, samples, row_stride, pad_left,
-          frames, plan->shift, plan->wlen, win, plan->tw, layout, interior_scale, out);
-    else
-      stft1024_forward_kernel<false><<<grid, 256, 0, stream>>>(x, rows, samples, row_stride, pad_left,
-          frames, plan->shift, plan->wlen, win, plan->tw, layout, interior_scale, out);
+#define B2S_FWD(L, V)                                                                                  \
+    stft1024_forward_kernel<L, V><<<grid, 32 * kFwdWarps, 0, stream>>>(x, rows, samples, row_stride,   \
+        pad_left, frames, plan->shift, plan->wlen, win, plan->tw, interior_scale, out)
+    switch (layout * 2 + (vec ? 1 : 0)) {
+      case 0: B2S_FWD(B2S_SPEC_INTERLEAVED, false); break;
+      case 1: B2S_FWD(B2S_SPEC_INTERLEAVED, true); break;
+      case 2: B2S_FWD(B2S_SPEC_CONCAT, false); break;
+      case 3: B2S_FWD(B2S_SPEC_CONCAT, true); break;
+      case 4: B2S_FWD(B2S_SPEC_ABS, false); break;
+      case 5: B2S_FWD(B2S_SPEC_ABS, true); break;
+      case 6: B2S_FWD(B2S_SPEC_LOG1P_ABS, false); break;
+      default: B2S_FWD(B2S_SPEC_LOG1P_ABS, true); break;
+    }
+#undef B2S_FWD
     B2S_LAUNCH_CHECK("stft1024_forward_kernel");
   } else {
     const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 64);
@@ -329,7 +439,7 @@ int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, i
     // padded samples that can receive output: [crop_left, crop_left + samples_out)
     const int64_t total_hops = ceil_div(crop_left + samples_out, plan->shift);
     const int64_t chunks = ceil_div(total_hops, hops);
-    const size_t smem = sizeof(float2) * fft::kHalf * kInvSlots;
+    const size_t smem = sizeof(float2) * fft::kTile * kInvSlots;
     static bool configured[64] = {};
     if (!configured[plan->device & 63]) {
       B2S_CUDA(cudaFuncSetAttribute(istft1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
