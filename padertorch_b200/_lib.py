@@ -10,7 +10,7 @@ import threading
 import torch  # noqa: F401  (loads libcudart / initialises the allocator the pointers come from)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, 'libb200sep.so')
+LIBRARY_PATH = os.environ.get('B200SEP_LIBRARY', os.path.join(_HERE, 'libb200sep.so'))
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

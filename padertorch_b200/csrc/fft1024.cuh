@@ -28,8 +28,28 @@ constexpr int kHalf = 512;     // complex transform length
 constexpr int kBins = 513;
 constexpr int kTile = 544;     // float2 slots of a warp's exchange tile (512 + padding of exchange 1)
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): a complex value lives in an aligned
+// register pair, so complex add / subtract is ONE instruction instead of two.  The packing moves below
+// are register-allocation hints, ptxas emits no MOVs for them.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; "
+      "mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; "
+      "mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+// component-wise product (window multiply, real scaling)
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; "
+      "mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -43,10 +63,19 @@ __device__ __forceinline__ float2 mul_i(float2 a) {
   return SIGN < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
 
+// 4-point DFT with the +-i rotation of the odd difference folded into scalar adds
 template <int SIGN>
 __device__ __forceinline__ void dft4(float2& c0, float2& c1, float2& c2, float2& c3) {
-  float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), o0 = cadd(c1, c3), o1 = mul_i<SIGN>(csub(c1, c3));
-  c0 = cadd(e0, o0); c1 = cadd(e1, o1); c2 = csub(e0, o0); c3 = csub(e1, o1);
+  const float2 e0 = cadd(c0, c2), e1 = csub(c0, c2), o0 = cadd(c1, c3), d = csub(c1, c3);
+  c0 = cadd(e0, o0);
+  c2 = csub(e0, o0);
+  if (SIGN < 0) {   // o1 = -i d = (d.y, -d.x)
+    c1 = make_float2(e1.x + d.y, e1.y - d.x);
+    c3 = make_float2(e1.x - d.y, e1.y + d.x);
+  } else {          // o1 = +i d = (-d.y, d.x)
+    c1 = make_float2(e1.x - d.y, e1.y + d.x);
+    c3 = make_float2(e1.x + d.y, e1.y - d.x);
+  }
 }
 
 // In-place 8-point DFT, v[q] = sum_r v[r] exp(SIGN 2 pi i r q / 8), natural order in and out.
@@ -57,12 +86,13 @@ __device__ __forceinline__ void radix8(float2 (&v)[8]) {
   float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
   float2 b0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
   float2 b1, b2, b3;
+  const float2 cc = make_float2(c, c);
   if (SIGN < 0) {
-    b1 = make_float2(c * (d1.x + d1.y), c * (d1.y - d1.x));   // * (c - ic)
-    b3 = make_float2(c * (d3.y - d3.x), -c * (d3.x + d3.y));  // * (-c - ic)
+    b1 = pmul(make_float2(d1.x + d1.y, d1.y - d1.x), cc);      // * (c - ic)
+    b3 = pmul(make_float2(d3.y - d3.x, -(d3.x + d3.y)), cc);   // * (-c - ic)
   } else {
-    b1 = make_float2(c * (d1.x - d1.y), c * (d1.x + d1.y));   // * (c + ic)
-    b3 = make_float2(-c * (d3.x + d3.y), c * (d3.x - d3.y));  // * (-c + ic)
+    b1 = pmul(make_float2(d1.x - d1.y, d1.x + d1.y), cc);      // * (c + ic)
+    b3 = pmul(make_float2(-(d3.x + d3.y), d3.x - d3.y), cc);   // * (-c + ic)
   }
   b2 = mul_i<SIGN>(d2);
   dft4<SIGN>(a0, a1, a2, a3);   // even outputs 0,2,4,6

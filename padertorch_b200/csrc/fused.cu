@@ -25,7 +25,10 @@ using namespace b2s;
 namespace {
 
 constexpr int kFusedWarps = 4;
-constexpr int kFusedCtasPerSm = 3;
+#ifndef B2S_FUSED_CTAS_PER_SM
+#define B2S_FUSED_CTAS_PER_SM 3
+#endif
+constexpr int kFusedCtasPerSm = B2S_FUSED_CTAS_PER_SM;
 
 struct FusedGrid {
   int grid;            // persistent CTAs
@@ -205,8 +208,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float2 va = src[fft::natural_a(lane, r)], vb = src[fft::natural_b(lane, r)];
-          a[r] = make_float2(va.x * wa[r].x, va.y * wa[r].y);
-          bb[r] = make_float2(vb.x * wb[r].x, vb.y * wb[r].y);
+          a[r] = fft::pmul(va, wa[r]);
+          bb[r] = fft::pmul(vb, wb[r]);
         }
         fft::rfft1024(a, bb, tile, k, ya, yb, ydc, ynyq);
 #pragma unroll

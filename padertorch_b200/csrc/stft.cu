@@ -58,6 +58,10 @@ __device__ __forceinline__ void store_bin_t(float* __restrict__ out, int k, floa
 }
 
 constexpr int kFwdWarps = 4;
+#ifndef B2S_FWD_CTAS_PER_SM
+#define B2S_FWD_CTAS_PER_SM 3
+#endif
+constexpr int kFwdCtasPerSm = B2S_FWD_CTAS_PER_SM;
 
 // One warp per frame, persistent over frames.  `win` is the (zero-extended) window the samples are
 // multiplied with: the analysis window for STFT, the synthesis window for the adjoint of iSTFT, in
@@ -89,7 +93,7 @@ stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t sampl
     fft::load_frame<VEC>(x + row * row_stride, m * shift - pad_left, samples, wlen, lane, a, b);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      a[r].x *= wa[r].x; a[r].y *= wa[r].y; b[r].x *= wb[r].x; b[r].y *= wb[r].y;
+      a[r] = fft::pmul(a[r], wa[r]); b[r] = fft::pmul(b[r], wb[r]);
     }
     fft::rfft1024(a, b, tile, k, ya, yb, ydc, ynyq);
     float* o = out + fr * kOutPerFrame;
@@ -117,7 +121,7 @@ stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t sampl
 // 4x at shift 256) by 16-byte cp.async with zero fill outside the signal (the fading and tail pads), double
 // buffered so the copy of group i+1 is in flight while group i is transformed.  Needs 16-byte aligned rows.
 template <int LAYOUT, bool DOUBLE_INTERIOR>
-__global__ void __launch_bounds__(32 * kFwdWarps, 3)
+__global__ void __launch_bounds__(32 * kFwdWarps, kFwdCtasPerSm)
 stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                        int64_t pad_left, int64_t frames, int shift, const float* __restrict__ win,
                        const float2* __restrict__ twtab, float* __restrict__ out) {
@@ -164,8 +168,8 @@ stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t sample
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float2 va = src[fft::natural_a(lane, r)], vb = src[fft::natural_b(lane, r)];
-        a[r] = make_float2(va.x * wa[r].x, va.y * wa[r].y);
-        b[r] = make_float2(vb.x * wb[r].x, vb.y * wb[r].y);
+        a[r] = fft::pmul(va, wa[r]);
+        b[r] = fft::pmul(vb, wb[r]);
       }
       fft::rfft1024(a, b, tile, k, ya, yb, ydc, ynyq);
       float* o = out + (row * frames + m) * kOutPerFrame;
@@ -276,8 +280,8 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
       fft::irfft1024(ya, yb, ydc, ynyq, tile, k, a, b);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        tile[fft::natural_a(lane, r)] = make_float2(a[r].x * wa[r].x, a[r].y * wa[r].y);
-        tile[fft::mirrored_b(lane, r)] = make_float2(b[r].x * wb[r].x, b[r].y * wb[r].y);
+        tile[fft::natural_a(lane, r)] = fft::pmul(a[r], wa[r]);
+        tile[fft::mirrored_b(lane, r)] = fft::pmul(b[r], wb[r]);
       }
     }
     __syncthreads();
@@ -374,7 +378,7 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
   if (plan->fast && plan->wlen == fft::kSize && aligned16 && plan->shift <= fft::kSize &&
       rows * ceil_div(frames, kFwdWarps) < (int64_t)1 << 30) {
     const int64_t groups = rows * ceil_div(frames, kFwdWarps);
-    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * 3);
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * kFwdCtasPerSm);
     const int span = (kFwdWarps - 1) * plan->shift + fft::kSize;
     const size_t smem = sizeof(float) * 2 * span;
 #define B2S_STAGED(L, D)                                                                                \
