@@ -131,9 +131,39 @@ def synthetic_batch(seed, device=None, pin=False):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def import_reference():
+    """The unmodified reference package if it was pip-installed into baseline/_ref, with the
+    stand-ins of oracle/ref_standins for its un-vendored dependencies; None otherwise."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'padertorch')):
+        return None
+    for path in (os.path.join(ROOT, 'oracle', 'ref_standins'), ref):
+        if path not in sys.path:
+            sys.path.insert(0, path)
+    try:
+        import warnings
+        warnings.filterwarnings('ignore')
+        import padertorch
+        return padertorch
+    except Exception:
+        return None
+
+
+def reference_step(pt, batch, stft, n_utt):
+    """The reference's own code for the step: pt.ops.STFT on y and s, abs (pit/data.py:49-77), then the
+    per-example pit_loss loop of pit/model.py:117-128."""
+    with torch.no_grad():
+        y_abs = stft(batch['y'][:n_utt]).abs()
+        x_abs = stft(batch['s'][:n_utt]).abs().transpose(1, 2)
+        out = []
+        for b in range(n_utt):
+            out.append(pt.ops.losses.pit_loss(batch['masks'][b] * y_abs[b][:, None, :], x_abs[b], axis=-2,
+                                              return_permutation=True))
+        return out
+
+
 def cpu_step(batch, stft, n_utt):
-    """The reference's ops for the same step on the host: pt.ops.STFT (dense DFT convolution) of y
-    and s, abs, then the per-example pit_loss loop of pit/model.py:117-128 (oracle port)."""
+    """Oracle port of the same step (used when the reference package is not installed)."""
     from oracle import path as oracle_path
     with torch.no_grad():
         return oracle_path.stft_mask_pit_step(batch['y'][:n_utt], batch['s'][:n_utt],
@@ -141,24 +171,31 @@ def cpu_step(batch, stft, n_utt):
 
 
 def time_cpu(steps, warmup, n_utt=BATCH, seed=1234):
-    from oracle.stft import ReferenceSTFT
+    """Returns (utt/s, seconds per step, threads, kind) of the CPU implementation of the step."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     batch = synthetic_batch(seed)
-    stft = ReferenceSTFT(SIZE, SHIFT)
+    pt = import_reference()
+    if pt is not None:
+        stft = pt.ops.STFT(SIZE, SHIFT)
+        run, kind = (lambda: reference_step(pt, batch, stft, n_utt)), 'reference'
+    else:
+        from oracle.stft import ReferenceSTFT
+        stft = ReferenceSTFT(SIZE, SHIFT)
+        run, kind = (lambda: cpu_step(batch, stft, n_utt)), 'port'
     for _ in range(warmup):
-        cpu_step(batch, stft, n_utt)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(batch, stft, n_utt)
+        run()
     elapsed = time.perf_counter() - t0
-    return n_utt * steps / elapsed, elapsed / steps, cores
+    return n_utt * steps / elapsed, elapsed / steps, cores, kind
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    value, per_step, cores = time_cpu(args.steps, args.warmup)
+    value, per_step, cores, kind = time_cpu(args.steps, args.warmup)
     cpu_model = ''
     try:
         with open('/proc/cpuinfo') as fd:
@@ -170,9 +207,11 @@ def run_reference(args, rank, world):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': {'workload': WORKLOAD, 'l2': 'n/a (CPU)'},
-        'cpu_baseline': {'value': value, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{args.steps} x one full batch of {BATCH} utterances through the '
-                                   f'oracle port of pt.ops.STFT + pit_loss loop, {cores} threads, {cpu_model}'},
+        'cpu_baseline': {'value': value, 'unit': 'utt/s', 'cores': cores, 'kind': kind,
+                         'sample': f'{args.steps} x one full batch of {BATCH} utterances through '
+                                   + ('the unmodified reference (baseline/_ref): ' if kind == 'reference'
+                                      else 'the oracle port of ')
+                                   + f'pt.ops.STFT + per-example pit_loss loop, {cores} threads, {cpu_model}'},
         'e2e': {'value': value, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -324,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
         value = world * BATCH * args.steps / (elapsed_ms * 1e-3)
         achieved = BYTES_LOSS * BATCH / (loss_ms * 1e-3) / 1e9
         path_gbs = BYTES_PATH * BATCH / (ms_per_step * 1e-3) / 1e9
-        cpu_value, cpu_step_s, cores = time_cpu(3, 1)
+        cpu_value, cpu_step_s, cores, cpu_kind = time_cpu(3, 1)
         line = {
             'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
@@ -345,9 +384,11 @@ def run_ours(args, rank, world, local_rank):
                               'algorithmic_bytes_per_step': BYTES_PATH * BATCH,
                               'front_end_kernel_ms': front_ms,
                               'front_end_frac': BYTES_FRONT * BATCH / (front_ms * 1e-3) / 1e9 / peak},
-            'cpu_baseline': {'value': cpu_value, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'3 x one full batch of {BATCH} utterances (oracle port of pt.ops.STFT '
-                                       f'+ pit_loss loop), {cpu_step_s:.2f} s per batch'},
+            'cpu_baseline': {'value': cpu_value, 'unit': 'utt/s', 'cores': cores, 'kind': cpu_kind,
+                             'sample': f'3 x one full batch of {BATCH} utterances ('
+                                       + ('unmodified reference from baseline/_ref: ' if cpu_kind == 'reference'
+                                          else 'oracle port of ')
+                                       + f'pt.ops.STFT + per-example pit_loss loop), {cpu_step_s:.2f} s per batch'},
         }
         traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(traffic_file):

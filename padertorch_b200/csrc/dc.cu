@@ -17,8 +17,8 @@ using namespace b2s;
 namespace {
 
 constexpr int BS = 8;            // Gram block edge
-constexpr int kMaxBlocks = B2S_DC_MAX_CHANNELS / BS;
 constexpr int kMaxWarps = 8;
+constexpr int kDcBinBlock = 2048;   // bins per work unit (long [N, E] inputs are split along the points)
 
 struct DcGrid { int blocks, pairs, warps, nchunks, cp; };
 
@@ -30,9 +30,9 @@ DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
   g.warps = std::min(g.pairs, kMaxWarps);
   const int per_sm = std::max(1, std::min(2048 / (32 * g.warps), 65536 / (144 * 32 * g.warps)));
   const int64_t capacity = (int64_t)kNumSMs * per_sm;
-  const int64_t points = std::max<int64_t>(1, max_frames * bins);
+  const int64_t units = std::max<int64_t>(1, max_frames * ceil_div(std::max<int64_t>(bins, 1), (int64_t)kDcBinBlock));
   int64_t c = capacity / std::max<int64_t>(1, batch);
-  c = std::min<int64_t>(c, std::max<int64_t>(1, points / 2048));
+  c = std::min<int64_t>(c, units);
   g.nchunks = (int)std::max<int64_t>(1, c);
   return g;
 }
@@ -51,7 +51,10 @@ dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
   const float* e_ = emb + meta[b * B2S_DC_META + 1];
   const float* t_ = tgt + meta[b * B2S_DC_META + 2];
   const int64_t N = T * F;
-  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
+  // work units = (frame, block of kDcBinBlock bins); this CTA owns the contiguous range [u0, u1)
+  const int64_t fblocks = ceil_div(F, (int64_t)kDcBinBlock);
+  const int64_t units = T * fblocks;
+  const int64_t u0 = units * chunk / nchunks, u1 = units * (chunk + 1) / nchunks;
   double* mine = partial + ((int64_t)b * nchunks + chunk) * cp * cp;
 
   for (int pair = warp; pair < pairs; pair += nwarps) {
@@ -59,7 +62,7 @@ dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
     int ba = 0, rem = pair;
     while (rem >= blocks - ba) { rem -= blocks - ba; ++ba; }
     const int bb = ba + rem;
-    // per-channel base pointers (nullptr: padding channel)
+    // per-channel base pointers (nullptr: padding channel) and the per-channel point strides
     const float* pa[BS]; const float* pb[BS];
     bool ea[BS], eb[BS];
 #pragma unroll
@@ -74,23 +77,27 @@ dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
     for (int i = 0; i < BS; ++i)
 #pragma unroll
       for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
-    for (int64_t q = q0 + lane; q < q1; q += 32) {
-      const int64_t t = q / F, f = q - t * F;
-      const int64_t oe = t * se.t + f * se.f, ot = t * st.t + f * st.f;
-      float va[BS], vb[BS];
+    for (int64_t u = u0; u < u1; ++u) {
+      const int64_t t = u / fblocks;
+      const int64_t fbeg = (u - t * fblocks) * kDcBinBlock, fend = min(F, fbeg + kDcBinBlock);
+      const int64_t oe0 = t * se.t, ot0 = t * st.t;
+      for (int64_t f = fbeg + lane; f < fend; f += 32) {
+        const int64_t oe = oe0 + f * se.f, ot = ot0 + f * st.f;
+        float va[BS], vb[BS];
 #pragma unroll
-      for (int i = 0; i < BS; ++i) va[i] = pa[i] ? __ldg(pa[i] + (ea[i] ? oe : ot)) : 0.f;
-      if (ba == bb) {
+        for (int i = 0; i < BS; ++i) va[i] = pa[i] ? __ldg(pa[i] + (ea[i] ? oe : ot)) : 0.f;
+        if (ba == bb) {
 #pragma unroll
-        for (int i = 0; i < BS; ++i) vb[i] = va[i];
-      } else {
+          for (int i = 0; i < BS; ++i) vb[i] = va[i];
+        } else {
 #pragma unroll
-        for (int i = 0; i < BS; ++i) vb[i] = pb[i] ? __ldg(pb[i] + (eb[i] ? oe : ot)) : 0.f;
+          for (int i = 0; i < BS; ++i) vb[i] = pb[i] ? __ldg(pb[i] + (eb[i] ? oe : ot)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) acc[i][j] = fmaf(va[i], vb[j], acc[i][j]);
       }
-#pragma unroll
-      for (int i = 0; i < BS; ++i)
-#pragma unroll
-        for (int j = 0; j < BS; ++j) acc[i][j] = fmaf(va[i], vb[j], acc[i][j]);
     }
 #pragma unroll
     for (int i = 0; i < BS; ++i)
@@ -157,40 +164,40 @@ dc_backward_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
     coef[idx] = (float)v;
   }
   __syncthreads();
-  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  // work item = (tile of 64 points, output block); warps stride over items
-  const int64_t tiles = ceil_div(q1 - q0, 64);
-  for (int64_t item = warp; item < tiles * eblocks; item += nwarps) {
-    const int64_t tile = item / eblocks;
-    const int eb = (int)(item - tile * eblocks);
-    const int64_t qa = q0 + tile * 64 + lane, qb = qa + 32;
-    const bool oka = qa < q1, okb = qb < q1;
-    const int64_t ta = qa / F, fa = qa - ta * F, tb = qb / F, fb = qb - tb * F;
+  // work units = (frame, block of 64 bins); this CTA owns [u0, u1); a warp item = (unit, output block)
+  const int64_t fblocks = ceil_div(F, (int64_t)64);
+  const int64_t units = T * fblocks;
+  const int64_t u0 = units * chunk / nchunks, u1 = units * (chunk + 1) / nchunks;
+  for (int64_t item = (u1 - u0) * 0 + warp; item < (u1 - u0) * eblocks; item += nwarps) {
+    const int64_t u = u0 + item / eblocks;
+    const int eb = (int)(item % eblocks);
+    const int64_t t = u / fblocks;
+    const int64_t fa = (u - t * fblocks) * 64 + lane, fb = fa + 32;
+    const bool oka = fa < F, okb = fb < F;
+    const float* ea_ = e_ + t * se.t + fa * se.f;
+    const float* ta_ = t_ + t * st.t + fa * st.f;
     float ga[BS], gb[BS];
 #pragma unroll
     for (int j = 0; j < BS; ++j) { ga[j] = 0.f; gb[j] = 0.f; }
     for (int c = 0; c < C; ++c) {
-      float za, zb;
-      if (c < E) {
-        za = oka ? __ldg(e_ + ta * se.t + c * se.c + fa * se.f) : 0.f;
-        zb = okb ? __ldg(e_ + tb * se.t + c * se.c + fb * se.f) : 0.f;
-      } else {
-        za = oka ? __ldg(t_ + ta * st.t + (c - E) * st.c + fa * st.f) : 0.f;
-        zb = okb ? __ldg(t_ + tb * st.t + (c - E) * st.c + fb * st.f) : 0.f;
-      }
+      const float* src = c < E ? ea_ + c * se.c : ta_ + (c - E) * st.c;
+      const int64_t step = 32 * (c < E ? se.f : st.f);
+      const float za = oka ? __ldg(src) : 0.f;
+      const float zb = okb ? __ldg(src + step) : 0.f;
       const float4 c0 = *reinterpret_cast<const float4*>(coef + c * Ep + eb * BS);
       const float4 c1 = *reinterpret_cast<const float4*>(coef + c * Ep + eb * BS + 4);
       const float cf[BS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
       for (int j = 0; j < BS; ++j) { ga[j] = fmaf(za, cf[j], ga[j]); gb[j] = fmaf(zb, cf[j], gb[j]); }
     }
+    float* dst = g_ + t * se.t + fa * se.f;
 #pragma unroll
     for (int j = 0; j < BS; ++j) {
       const int e = eb * BS + j;
       if (e < E) {
-        if (oka) g_[ta * se.t + e * se.c + fa * se.f] = ga[j];
-        if (okb) g_[tb * se.t + e * se.c + fb * se.f] = gb[j];
+        if (oka) dst[e * se.c] = ga[j];
+        if (okb) dst[e * se.c + 32 * se.f] = gb[j];
       }
     }
   }
@@ -243,7 +250,7 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
   const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
   const Strides st{target_strides[0], target_strides[1], target_strides[2]};
   const int64_t points = std::max<int64_t>(1, max_frames * bins);
-  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 4096, 256));
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 4096, 128));
   const int Ep = (embedding_dim + BS - 1) / BS * BS;
   const size_t smem = sizeof(float) * C * Ep;
   dc_backward_kernel<<<dim3((unsigned)batch, nchunks), 256, smem, (cudaStream_t)stream>>>(

@@ -16,29 +16,33 @@ using namespace b2s;
 
 namespace {
 
+constexpr int kPitWarps = 8;
+constexpr int kPitThreads = 32 * kPitWarps;
+constexpr int kPitUnroll = 4;          // bin groups of 32 in flight per lane
+constexpr int kPitCtasPerSm = 3;
+
 struct PitGrid {
-  int bx, by, tchunks, fchunks;
+  int tchunks, fchunks;
   int nchunks() const { return tchunks * fchunks; }
-  int threads() const { return bx * by; }
 };
 
-constexpr int64_t kBinsPerChunk = 8192;
+constexpr int64_t kBinsPerChunk = 16384;
 
 PitGrid pit_grid(int64_t batch, int64_t max_frames, int64_t bins) {
   PitGrid g;
-  g.bx = (int)std::min<int64_t>((bins + 31) / 32 * 32, 576);
-  g.by = std::max(1, 512 / g.bx);
   g.fchunks = (int)ceil_div(std::max<int64_t>(bins, 1), kBinsPerChunk);
-  const int per_sm = std::max(1, 2048 / g.threads());
-  const int64_t capacity = (int64_t)kNumSMs * per_sm;
+  // when there are few frames but very long rows (pit_loss on [K, T] signals) split the rows instead
+  if (max_frames < 4 * kPitWarps && bins > 4096)
+    g.fchunks = (int)std::min<int64_t>(ceil_div(bins, 2048), 1024);
+  const int64_t capacity = (int64_t)kNumSMs * kPitCtasPerSm;
   int64_t t = capacity / std::max<int64_t>(1, batch * g.fchunks);
-  const int64_t most = std::max<int64_t>(1, max_frames / (2 * g.by));
+  const int64_t most = std::max<int64_t>(1, max_frames / kPitWarps);
   g.tchunks = (int)std::max<int64_t>(1, std::min<int64_t>(t, most));
   return g;
 }
 
 template <int K, bool DUAL>
-__global__ void __launch_bounds__(576)
+__global__ void __launch_bounds__(kPitThreads, kPitCtasPerSm)
 pit_sse_forward_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
                        const float* __restrict__ tgt, const float* __restrict__ scale,
                        const int64_t* __restrict__ meta, int tchunks, int fchunks, int64_t F,
@@ -57,49 +61,59 @@ pit_sse_forward_kernel(const float* __restrict__ mask, const float* __restrict__
   const float* s_ = scale ? scale + meta[b * B2S_PIT_META + 4] : nullptr;
   const int64_t t0 = T * tc / tchunks, t1 = T * (tc + 1) / tchunks;
   const int64_t f0 = F * fc / fchunks, f1 = F * (fc + 1) / fchunks;
-  const int by = blockDim.y;
+  const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
 
   float acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.f;
 
-  auto body = [&](int64_t t, int64_t f) {
-    float e[K], x[K], xs[K];
-    const float o = o_ ? __ldg(o_ + t * F + f) : 1.f;
+  // a warp owns frames t0 + warp, t0 + warp + 8, ...; its lanes sweep the bins, kPitUnroll groups of 32
+  // bins (= kPitUnroll * (1 + 2K [+K]) independent coalesced loads) in flight
+  for (int64_t t = t0 + warp_; t < t1; t += kPitWarps) {
+    const float* mrow = m_ + t * K * F;
+    const float* xrow = x_ + t * K * F;
+    const float* srow = s_ ? s_ + t * K * F : nullptr;
+    const float* orow = o_ ? o_ + t * F : nullptr;
+    for (int64_t fb = f0 + lane_; fb < f1; fb += 32 * kPitUnroll) {
+      float o[kPitUnroll], e[kPitUnroll][K], x[kPitUnroll][K], sc[kPitUnroll][K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      e[i] = __ldg(m_ + (t * K + i) * F + f) * o;
-      x[i] = __ldg(x_ + (t * K + i) * F + f);
-      xs[i] = s_ ? x[i] * __ldg(s_ + (t * K + i) * F + f) : x[i];
-    }
+      for (int u = 0; u < kPitUnroll; ++u) {
+        const int64_t f = fb + 32 * u;
+        const bool on = f < f1;
+        o[u] = (on && orow) ? __ldg(orow + f) : (on ? 1.f : 0.f);
 #pragma unroll
-    for (int i = 0; i < K; ++i)
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        if (DUAL) {
-          const float d0 = e[i] - x[j], d1 = e[i] - xs[j];
-          acc[i * K + j] = fmaf(d0, d0, acc[i * K + j]);
-          acc[K * K + i * K + j] = fmaf(d1, d1, acc[K * K + i * K + j]);
-        } else {
-          const float d = e[i] - xs[j];
-          acc[i * K + j] = fmaf(d, d, acc[i * K + j]);
+        for (int i = 0; i < K; ++i) {
+          e[u][i] = on ? __ldg(mrow + i * F + f) : 0.f;
+          x[u][i] = on ? __ldg(xrow + i * F + f) : 0.f;
+          sc[u][i] = (on && srow) ? __ldg(srow + i * F + f) : 1.f;
         }
       }
-  };
-
-  for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
-    int64_t t = t0 + threadIdx.y;
-    for (; t + by < t1; t += 2 * by) {  // two frames in flight
-      body(t, f);
-      body(t + by, f);
+#pragma unroll
+      for (int u = 0; u < kPitUnroll; ++u) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float ei = e[u][i] * o[u];
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (DUAL) {
+              const float d0 = ei - x[u][j], d1 = ei - x[u][j] * sc[u][j];
+              acc[i * K + j] = fmaf(d0, d0, acc[i * K + j]);
+              acc[K * K + i * K + j] = fmaf(d1, d1, acc[K * K + i * K + j]);
+            } else {
+              const float d = ei - x[u][j] * sc[u][j];
+              acc[i * K + j] = fmaf(d, d, acc[i * K + j]);
+            }
+          }
+        }
+      }
     }
-    if (t < t1) body(t, f);
   }
 
   // ---- CTA reduction (fixed tree) -> partial[b][chunk][NV]
-  const int tid = threadIdx.x + blockDim.x * threadIdx.y;
-  const int nthreads = blockDim.x * blockDim.y;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  const int tid = threadIdx.x;
+  constexpr int nthreads = kPitThreads;
+  const int lane = lane_, warp = warp_;
+  constexpr int nwarps = kPitWarps;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float s = warp_sum(acc[i]);
@@ -147,7 +161,7 @@ pit_sse_forward_kernel(const float* __restrict__ mask, const float* __restrict__
 
 // grad_mask[t,i,f] = sum_slot c_slot * o * (m*o - x_slot[inv_slot[i]]),  c = grad_loss * 2 / (T K F)
 template <int K, bool DUAL>
-__global__ void __launch_bounds__(576)
+__global__ void __launch_bounds__(kPitThreads, kPitCtasPerSm)
 pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
                         const float* __restrict__ tgt, const float* __restrict__ scale,
                         const int64_t* __restrict__ meta, int tchunks, int fchunks, int64_t F,
@@ -166,6 +180,7 @@ pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict_
   const int64_t t0 = T * tc / tchunks, t1 = T * (tc + 1) / tchunks;
   const int64_t f0 = F * fc / fchunks, f1 = F * (fc + 1) / fchunks;
   const double count = (double)T * (double)K * (double)F;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inv0[K], inv1[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -180,36 +195,52 @@ pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict_
   }
   const float c0 = (float)(2.0 * (double)grad_loss[b] / count);
   const float c1 = DUAL ? (float)(2.0 * (double)grad_loss[batch + b] / count) : 0.f;
-  for (int64_t f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
-    for (int64_t t = t0 + threadIdx.y; t < t1; t += blockDim.y) {
-      const float o = o_ ? __ldg(o_ + t * F + f) : 1.f;
-      float e[K], x[K], xs[K], sc[K];
+  constexpr int U = 2;
+  for (int64_t t = t0 + warp; t < t1; t += kPitWarps) {
+    const float* mrow = m_ + t * K * F;
+    const float* xrow = x_ + t * K * F;
+    const float* srow = s_ ? s_ + t * K * F : nullptr;
+    const float* orow = o_ ? o_ + t * F : nullptr;
+    float* grow = gm_ + t * K * F;
+    float* gtrow = gt_ ? gt_ + t * K * F : nullptr;
+    for (int64_t fb = f0 + lane; fb < f1; fb += 32 * U) {
+      float o[U], e[U][K], x[U][K], sc[U][K];
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        e[i] = __ldg(m_ + (t * K + i) * F + f) * o;
-        x[i] = __ldg(x_ + (t * K + i) * F + f);
-        sc[i] = s_ ? __ldg(s_ + (t * K + i) * F + f) : 1.f;
-        xs[i] = x[i] * sc[i];
-      }
+      for (int u = 0; u < U; ++u) {
+        const int64_t f = fb + 32 * u;
+        const bool on = f < f1;
+        o[u] = (on && orow) ? __ldg(orow + f) : 1.f;
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        float xa = 0.f, xb = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (inv0[i] == k) xa = DUAL ? x[k] : xs[k];
-          if (DUAL && inv1[i] == k) xb = xs[k];
+        for (int i = 0; i < K; ++i) {
+          e[u][i] = on ? __ldg(mrow + i * F + f) * o[u] : 0.f;
+          x[u][i] = on ? __ldg(xrow + i * F + f) : 0.f;
+          sc[u][i] = (on && srow) ? __ldg(srow + i * F + f) : 1.f;
         }
-        float g = c0 * (e[i] - xa);
-        if (DUAL) g = fmaf(c1, e[i] - xb, g);
-        gm_[(t * K + i) * F + f] = g * o;
       }
-      if (gt_) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float ek = 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int64_t f = fb + 32 * u;
+        if (f >= f1) continue;
 #pragma unroll
-          for (int i = 0; i < K; ++i) if (inv0[i] == k) ek = e[i];
-          gt_[(t * K + k) * F + f] = -c0 * (ek - xs[k]) * sc[k];
+        for (int i = 0; i < K; ++i) {
+          float xa = 0.f, xb = 0.f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (inv0[i] == k) xa = DUAL ? x[u][k] : x[u][k] * sc[u][k];
+            if (DUAL && inv1[i] == k) xb = x[u][k] * sc[u][k];
+          }
+          float g = c0 * (e[u][i] - xa);
+          if (DUAL) g = fmaf(c1, e[u][i] - xb, g);
+          grow[i * F + f] = g * o[u];
+        }
+        if (gtrow) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float ek = 0.f;
+#pragma unroll
+            for (int i = 0; i < K; ++i) if (inv0[i] == k) ek = e[u][i];
+            gtrow[k * F + f] = -c0 * (ek - x[u][k] * sc[u][k]) * sc[u][k];
+          }
         }
       }
     }
@@ -225,8 +256,8 @@ int launch_forward_k(const float* mask, const float* obs, const float* tgt, cons
   (void)nv;
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
-  const dim3 grid((unsigned)batch, g.nchunks()), block(g.bx, g.by);
-  const size_t smem = sizeof(double) * nv * (g.threads() / 32 + 1);
+  const dim3 grid((unsigned)batch, g.nchunks()), block(kPitThreads);
+  const size_t smem = sizeof(double) * nv * (kPitWarps + 1);
   if (dual)
     pit_sse_forward_kernel<K, true><<<grid, block, smem, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
         g.fchunks, F, partial, counters, loss, perm, sse, batch);
@@ -244,8 +275,8 @@ int launch_backward_k(const float* mask, const float* obs, const float* tgt, con
                       float* grad_target, cudaStream_t stream) {
   PitGrid g = pit_grid(batch, max_frames, F);
   // elementwise: more CTAs than the reduction wants are fine
-  g.tchunks = (int)std::max<int64_t>(g.tchunks, std::min<int64_t>(max_frames / (4 * g.by) + 1, 64));
-  const dim3 grid((unsigned)batch, g.nchunks()), block(g.bx, g.by);
+  g.tchunks = (int)std::max<int64_t>(g.tchunks, std::min<int64_t>(max_frames / (2 * kPitWarps) + 1, 64));
+  const dim3 grid((unsigned)batch, g.nchunks()), block(kPitThreads);
   if (dual)
     pit_sse_backward_kernel<K, true><<<grid, block, 0, stream>>>(mask, obs, tgt, scale, meta, g.tchunks,
         g.fchunks, F, perm, grad_loss, grad_mask, grad_target, batch);

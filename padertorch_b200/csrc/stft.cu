@@ -236,10 +236,12 @@ dft_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, i
 // CTA = (row, chunk of `hops` output hops).  Phase 1: the frames overlapping the chunk are inverse
 // transformed, windowed and parked in shared memory (frame slot == the warp's FFT tile).  Phase 2:
 // every output sample sums its <= ceil(wlen/shift) contributions in increasing frame order.
-constexpr int kInvSlots = 24;  // 24 x 4.25 KB = 102 KB of shared memory -> 2 CTAs per SM
+constexpr int kInvSlots = 16;   // 16 x 4.25 KB = 68 KB of shared memory -> 3 CTAs of 4 warps per SM
+constexpr int kInvWarps = 4;
 
-__global__ void __launch_bounds__(256)
-istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int layout, int shift,
+template <int LAYOUT>
+__global__ void __launch_bounds__(32 * kInvWarps, 3)
+istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int shift,
                  int wlen, int overlap /*ceil(wlen/shift)*/, int hops, int64_t chunks,
                  int64_t crop_left, int64_t samples_out, const float* __restrict__ win,
                  const float2* __restrict__ twtab, float interior_in_scale, float* __restrict__ out) {
@@ -253,29 +255,51 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
     wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
     wb[r] = reinterpret_cast<const float2*>(win)[fft::mirrored_b(lane, r)];
   }
+  const int k0 = fft::bin_a(lane, 0), k4 = fft::bin_a(lane, 4) - 256;   // slot p holds bin (p<4 ? k0 : k4) + 64 p
   for (int64_t job = blockIdx.x; job < rows * chunks; job += gridDim.x) {
     const int64_t row = job / chunks, chunk = job - row * chunks;
     const int64_t h0 = chunk * hops;                       // first hop (padded sample h0*shift)
     const int64_t m_first = max((int64_t)0, h0 - overlap + 1);
     const int64_t m_last = min(frames - 1, h0 + hops - 1);  // inclusive
-    __syncthreads();
-    for (int64_t m = m_first + warp; m <= m_last; m += 8) {
-      const int64_t fr = row * frames + m;
+    __syncthreads();                                        // the previous job's overlap-add is done
+    if (LAYOUT == B2S_SPEC_INTERLEAVED) {
+      // all spectra of this warp's frames start travelling into their slots now (8-byte cp.async)
+      for (int64_t m = m_first + warp; m <= m_last; m += kInvWarps) {
+        float2* slot = slots + (m - m_first) * fft::kTile;
+        const float2* src = reinterpret_cast<const float2*>(spec) + (row * frames + m) * fft::kBins;
+        for (int c = lane; c < fft::kBins; c += 32) fft::cp_async_8(slot + c, src + c);
+      }
+      fft::cp_async_commit();
+      fft::cp_async_wait_all();
+      __syncwarp();
+    }
+    for (int64_t m = m_first + warp; m <= m_last; m += kInvWarps) {
+      float2* tile = slots + (m - m_first) * fft::kTile;
       float2 ya[8], yb[8];
       float ydc = 0.f, ynyq = 0.f;
+      if (LAYOUT == B2S_SPEC_INTERLEAVED) {
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int kk = fft::bin_a(lane, p);
-        float2 u = load_bin(spec, fr, kk, layout, fft::kBins);
-        float2 v = load_bin(spec, fr, fft::kHalf - kk, layout, fft::kBins);
-        ya[p] = make_float2(u.x * interior_in_scale, u.y * interior_in_scale);
-        yb[p] = make_float2(v.x * interior_in_scale, v.y * interior_in_scale);
+        for (int p = 0; p < 8; ++p) {
+          const int kk = (p < 4 ? k0 : k4) + 64 * p;
+          ya[p] = tile[kk];
+          yb[p] = tile[fft::kHalf - kk];
+        }
+        if (lane == 0) { ydc = tile[0].x; ynyq = tile[fft::kHalf].x; }
+        __syncwarp();   // everyone has its bins before the tile becomes the exchange buffer
+      } else {
+        const float* re = spec + (row * frames + m) * 2 * fft::kBins;
+        const float* im = re + fft::kBins;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int kk = (p < 4 ? k0 : k4) + 64 * p;
+          ya[p] = make_float2(__ldg(re + kk), __ldg(im + kk));
+          yb[p] = make_float2(__ldg(re + fft::kHalf - kk), __ldg(im + fft::kHalf - kk));
+        }
+        if (lane == 0) { ydc = __ldg(re); ynyq = __ldg(re + fft::kHalf); }
       }
-      if (lane == 0) {
-        ydc = load_bin(spec, fr, 0, layout, fft::kBins).x;
-        ynyq = load_bin(spec, fr, fft::kHalf, layout, fft::kBins).x;
-      }
-      float2* tile = slots + (m - m_first) * fft::kTile;
+      const float2 sc = make_float2(interior_in_scale, interior_in_scale);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) { ya[p] = fft::pmul(ya[p], sc); yb[p] = fft::pmul(yb[p], sc); }
       float2 a[8], b[8];
       fft::irfft1024(ya, yb, ydc, ynyq, tile, k, a, b);
 #pragma unroll
@@ -286,17 +310,19 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
     }
     __syncthreads();
     const float* fbuf = reinterpret_cast<const float*>(slots);
-    const int64_t p_begin = h0 * shift, p_end = p_begin + (int64_t)hops * shift;
-    for (int64_t p = p_begin + threadIdx.x; p < p_end; p += blockDim.x) {
+    const int64_t p_begin = h0 * shift;
+    const int span = hops * shift;
+    for (int q = threadIdx.x; q < span; q += blockDim.x) {
+      const int64_t p = p_begin + q;
       const int64_t n = p - crop_left;
       if (n < 0 || n >= samples_out) continue;
       // frames m with m*shift <= p < m*shift + wlen
-      int64_t lo = (p - wlen + shift) / shift;  // ceil((p - wlen + 1)/shift) for p - wlen + 1 >= 0
-      if (p - wlen + 1 <= 0) lo = 0;
+      int64_t lo = (p - wlen + 1 <= 0) ? 0 : (p - wlen + shift) / shift;   // ceil((p - wlen + 1) / shift)
       lo = max(lo, m_first);
       const int64_t hi = min(p / shift, m_last);
       float acc = 0.f;
-      for (int64_t m = lo; m <= hi; ++m) acc += fbuf[(m - m_first) * (2 * fft::kTile) + (p - m * shift)];
+      for (int64_t m = lo; m <= hi; ++m)
+        acc += fbuf[(m - m_first) * (2 * fft::kTile) + (int)(p - m * shift)];
       out[row * samples_out + n] = acc;
     }
   }
@@ -438,21 +464,24 @@ int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, i
     return B2S_OK;
   }
   if (fused_inverse_ok(plan)) {
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(spec) & 7) == 0, "spectrum pointer must be 8-byte aligned");
     const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
     const int hops = kInvSlots - overlap + 1;
     // padded samples that can receive output: [crop_left, crop_left + samples_out)
     const int64_t total_hops = ceil_div(crop_left + samples_out, plan->shift);
     const int64_t chunks = ceil_div(total_hops, hops);
     const size_t smem = sizeof(float2) * fft::kTile * kInvSlots;
-    static bool configured[64] = {};
-    if (!configured[plan->device & 63]) {
-      B2S_CUDA(cudaFuncSetAttribute(istft1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[plan->device & 63] = true;
+    static bool configured[2][64] = {};
+    const int variant = layout == B2S_SPEC_INTERLEAVED ? 0 : 1;
+    auto kernel = variant == 0 ? istft1024_kernel<B2S_SPEC_INTERLEAVED> : istft1024_kernel<B2S_SPEC_CONCAT>;
+    if (!configured[variant][plan->device & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[variant][plan->device & 63] = true;
     }
-    const int grid = (int)std::min<int64_t>(rows * chunks, (int64_t)kNumSMs * 2 * 8);
+    const int grid = (int)std::min<int64_t>(rows * chunks, (int64_t)kNumSMs * 3 * 8);
     // irfft1024 yields S = edge + 2 * interior; the adjoint wants edge + 1 * interior: halve interior bins
-    istft1024_kernel<<<grid, 256, smem, stream>>>(spec, rows, frames, layout, plan->shift, plan->wlen,
-        overlap, hops, chunks, crop_left, samples_out, win, plan->tw, 0.5f * interior_scale, out);
+    kernel<<<grid, 32 * kInvWarps, smem, stream>>>(spec, rows, frames, plan->shift, plan->wlen, overlap, hops,
+        chunks, crop_left, samples_out, win, plan->tw, 0.5f * interior_scale, out);
     B2S_LAUNCH_CHECK("istft1024_kernel");
   } else {
     B2S_REQUIRE(scratch != nullptr, "inverse transform of this plan needs scratch (b2s_stft_scratch_bytes)");
