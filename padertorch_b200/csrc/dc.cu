@@ -20,10 +20,19 @@ constexpr int BS = 8;            // Gram block edge
 constexpr int kMaxWarps = 8;
 constexpr int kDcBinBlock = 2048;   // bins per work unit (long [N, E] inputs are split along the points)
 
-struct DcGrid { int blocks, pairs, warps, nchunks, cp; };
+struct DcGrid { int blocks, pairs, warps, nchunks, cp; bool tiled; };
 
-DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
+DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels, bool unit_bin_stride = true) {
   DcGrid g;
+  g.tiled = channels <= 24 && unit_bin_stride;
+  if (g.tiled) {
+    g.blocks = 3; g.cp = 24; g.pairs = 6; g.warps = 6;
+    const int64_t points = std::max<int64_t>(1, max_frames * bins);
+    int64_t c = (int64_t)kNumSMs * 2 / std::max<int64_t>(1, batch);
+    c = std::min<int64_t>(c, std::max<int64_t>(1, points / 512));
+    g.nchunks = (int)std::max<int64_t>(1, c);
+    return g;
+  }
   g.blocks = (channels + BS - 1) / BS;
   g.cp = g.blocks * BS;
   g.pairs = g.blocks * (g.blocks + 1) / 2;
@@ -38,6 +47,41 @@ DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
 }
 
 struct Strides { int64_t t, c, f; };
+
+// Ticket + fixed-order fold of the chunk partials -> gram[b][C][C] and the loss (all threads call it).
+__device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int E, int64_t N,
+                                          double* __restrict__ partial, int* __restrict__ counters,
+                                          double* __restrict__ gram, float* __restrict__ loss) {
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: fold chunks in order -> gram[b][C][C]; loss = (|A|^2 - 2|Cx|^2 + |D|^2) / N^2
+  __shared__ double red[32 * kMaxWarps];
+  double local = 0.0;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int r = idx / C, c = idx - r * C;
+    double s = 0.0;
+    const volatile double* p = partial + (int64_t)b * nchunks * cp * cp + r * cp + c;
+    for (int ch = 0; ch < nchunks; ++ch) s += p[(int64_t)ch * cp * cp];
+    gram[(int64_t)b * C * C + idx] = s;
+    const bool re = r < E, ce = c < E;
+    const double w = (re == ce) ? 1.0 : -1.0;  // the two mixed blocks together give -2 |V^T Y|^2
+    local += w * s * s;
+  }
+  red[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)blockDim.x; ++i) s += red[i];
+    loss[b] = (float)(s / ((double)N * (double)N));
+    counters[b] = 0;
+  }
+}
+
 
 __global__ void __launch_bounds__(32 * kMaxWarps)
 dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
@@ -110,34 +154,114 @@ dc_gram_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
         }
       }
   }
-  __threadfence();
-  __syncthreads();
-  __shared__ int s_last;
-  if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last CTA: fold chunks in order -> gram[b][C][C]; loss = (|A|^2 - 2|Cx|^2 + |D|^2) / N^2
-  __shared__ double red[32 * kMaxWarps];
-  double local = 0.0;
-  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
-    const int r = idx / C, c = idx - r * C;
-    double s = 0.0;
-    const volatile double* p = partial + (int64_t)b * nchunks * cp * cp + r * cp + c;
-    for (int ch = 0; ch < nchunks; ++ch) s += p[(int64_t)ch * cp * cp];
-    gram[(int64_t)b * C * C + idx] = s;
-    const bool re = r < E, ce = c < E;
-    const double w = (re == ce) ? 1.0 : -1.0;  // the two mixed blocks together give -2 |V^T Y|^2
-    local += w * s * s;
+  dc_finish(b, nchunks, cp, C, E, N, partial, counters, gram, loss);
+}
+
+// ------------------------------------------------------------------------------------------- tiled Gram
+// Fast path for E + K <= 24 channels with unit stride along the bins (the model's 't e f' layout):
+// tiles of 128 consecutive time-frequency points x 24 channels are copied into shared memory in their
+// native [channel][point] orientation (4-byte zero-filling cp.async, double buffered), and each of the
+// 6 warps owns one 8 x 8 block pair: a lane reads 4 consecutive points of a channel with ONE LDS.128, so
+// 16 shared loads feed 256 FMAs.
+constexpr int kTP = 128;             // points per tile
+constexpr int kTC = 24;              // channel rows per tile (3 blocks of 8)
+constexpr int kTiledWarps = 6;       // block pairs of a 3 x 3 upper triangle (compute warps)
+constexpr int kTiledThreads = 256;   // 8 warps load, the first 6 also compute
+
+__device__ __forceinline__ void cp_async_4_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kTiledThreads, 2)
+dc_gram_tiled_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                     const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
+                     int K, double* __restrict__ partial, int* __restrict__ counters,
+                     double* __restrict__ gram, float* __restrict__ loss) {
+  __shared__ __align__(16) float tile[2][kTC][kTP];
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = E + K;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  const int64_t N = T * F;
+  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
+
+  // loader: 256 threads = 128 point columns x 2 channel phases; thread (p, h) copies channels h, h+2, ...
+  // of its point: one division per tile, then a pointer increment per element
+  const int p = threadIdx.x & (kTP - 1), h = threadIdx.x >> 7;
+  auto issue_tile = [&](int64_t qt, int buf) {
+    const int64_t q = qt + p;
+    const bool ok = q < q1;
+    const int64_t t = q / F, f = q - t * F;
+    const float* pe = e_ + t * se.t + f + h * se.c;
+    const float* pt = t_ + t * st.t + f;
+    float* dst = &tile[buf][h][p];
+    int c = h;
+    for (; c < E; c += 2, pe += 2 * se.c, dst += 2 * kTP) cp_async_4_zfill(dst, ok ? pe : e_, ok);
+    pt += (c - E) * st.c;
+    for (; c < C; c += 2, pt += 2 * st.c, dst += 2 * kTP) cp_async_4_zfill(dst, ok ? pt : e_, ok);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // padding channel rows stay zero for the whole kernel
+  for (int e = threadIdx.x; e < 2 * kTC * kTP; e += kTiledThreads) {
+    const int c = (e >> 7) % kTC;
+    if (c >= C) (&tile[0][0][0])[e] = 0.f;
   }
-  red[threadIdx.x] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < (int)blockDim.x; ++i) s += red[i];
-    loss[b] = (float)(s / ((double)N * (double)N));
-    counters[b] = 0;
+  // this warp's block pair (ba <= bb) of the 3 x 3 upper triangle: 00 01 02 11 12 22
+  const int ba = warp < 3 ? 0 : (warp < 5 ? 1 : 2);
+  const int bb = warp < 3 ? warp : (warp < 5 ? warp - 2 : 2);
+  const bool active = warp < kTiledWarps && ba * BS < C && bb * BS < C;
+  float acc[BS][BS];
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
+
+  if (q0 < q1) issue_tile(q0, 0);
+  int cur = 0;
+  for (int64_t qt = q0; qt < q1; qt += kTP, cur ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                               // tile `cur` complete and visible; other buffer free
+    if (qt + kTP < q1) issue_tile(qt + kTP, cur ^ 1);
+    if (active) {
+      float4 va[BS];
+#pragma unroll
+      for (int i = 0; i < BS; ++i) va[i] = *reinterpret_cast<const float4*>(&tile[cur][ba * BS + i][4 * lane]);
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        // one row of the B block at a time keeps the live set at 64 accumulators + 36 operands
+        const float4 vb = ba == bb ? va[j] : *reinterpret_cast<const float4*>(&tile[cur][bb * BS + j][4 * lane]);
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          float a = acc[i][j];
+          a = fmaf(va[i].x, vb.x, a);
+          a = fmaf(va[i].y, vb.y, a);
+          a = fmaf(va[i].z, vb.z, a);
+          a = fmaf(va[i].w, vb.w, a);
+          acc[i][j] = a;
+        }
+      }
+    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * kTC * kTC;
+  if (warp < kTiledWarps) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        const float s = warp_sum(acc[i][j]);
+        if (lane == 0) {
+          mine[(ba * BS + i) * kTC + bb * BS + j] = (double)s;
+          mine[(bb * BS + j) * kTC + ba * BS + i] = (double)s;
+        }
+      }
+  }
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
 }
 
 // grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
@@ -203,14 +327,108 @@ dc_backward_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
   }
 }
 
+// ------------------------------------------------------------------------------------------- tiled backward
+// grad[p][e] = sum_c z[p][c] * coef[c][e]: the same [channel][point] tiles as the forward (cp.async, double
+// buffered); thread = 4 consecutive points x 5 output channels (E <= 20 -> 4 output groups x 32 point
+// quads = 128 threads compute), operands by LDS.128 (tile) and broadcast LDS (coefficients).
+constexpr int kBwdOut = 5;       // output channels per thread
+constexpr int kBwdGroups = 4;    // output groups (covers E <= 20)
+
+__global__ void __launch_bounds__(kTiledThreads, 2)
+dc_backward_tiled_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                         const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
+                         int K, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                         float* __restrict__ grad_emb) {
+  __shared__ __align__(16) float tile[2][kTC][kTP];
+  __shared__ float coef[kTC][kBwdGroups * kBwdOut];   // [c][e], zero padded
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int C = E + K;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
+  const int64_t N = T * F;
+  const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
+  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  for (int idx = threadIdx.x; idx < kTC * kBwdGroups * kBwdOut; idx += kTiledThreads) {
+    const int c = idx / (kBwdGroups * kBwdOut), e = idx - c * (kBwdGroups * kBwdOut);
+    double v = 0.0;
+    if (c < C && e < E) v = (c < E ? 1.0 : -1.0) * scale * gram[(int64_t)b * C * C + c * C + e];
+    coef[c][e] = (float)v;
+  }
+  for (int e = threadIdx.x; e < 2 * kTC * kTP; e += kTiledThreads) {
+    const int c = (e >> 7) % kTC;
+    if (c >= C) (&tile[0][0][0])[e] = 0.f;
+  }
+  const int p = threadIdx.x & (kTP - 1), h = threadIdx.x >> 7;
+  auto issue_tile = [&](int64_t qt, int buf) {
+    const int64_t q = qt + p;
+    const bool ok = q < q1;
+    const int64_t t = q / F, f = q - t * F;
+    const float* pe = e_ + t * se.t + f + h * se.c;
+    const float* pt = t_ + t * st.t + f;
+    float* dst = &tile[buf][h][p];
+    int c = h;
+    for (; c < E; c += 2, pe += 2 * se.c, dst += 2 * kTP) cp_async_4_zfill(dst, ok ? pe : e_, ok);
+    pt += (c - E) * st.c;
+    for (; c < C; c += 2, pt += 2 * st.c, dst += 2 * kTP) cp_async_4_zfill(dst, ok ? pt : e_, ok);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // compute threads: the first 128 -> (point quad = tid & 31, output group = tid >> 5)
+  const int quad = threadIdx.x & 31, og = threadIdx.x >> 5;
+  const bool active = og < kBwdGroups && og * kBwdOut < E;
+
+  if (q0 < q1) issue_tile(q0, 0);
+  int cur = 0;
+  for (int64_t qt = q0; qt < q1; qt += kTP, cur ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (qt + kTP < q1) issue_tile(qt + kTP, cur ^ 1);
+    if (active) {
+      float4 g[kBwdOut];
+#pragma unroll
+      for (int j = 0; j < kBwdOut; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < C; ++c) {
+        const float4 z = *reinterpret_cast<const float4*>(&tile[cur][c][4 * quad]);
+#pragma unroll
+        for (int j = 0; j < kBwdOut; ++j) {
+          const float w = coef[c][og * kBwdOut + j];
+          g[j].x = fmaf(z.x, w, g[j].x); g[j].y = fmaf(z.y, w, g[j].y);
+          g[j].z = fmaf(z.z, w, g[j].z); g[j].w = fmaf(z.w, w, g[j].w);
+        }
+      }
+      // 4 consecutive flattened points may straddle a frame boundary: store them one by one
+      const float gv[kBwdOut][4] = {{g[0].x, g[0].y, g[0].z, g[0].w}, {g[1].x, g[1].y, g[1].z, g[1].w},
+                                    {g[2].x, g[2].y, g[2].z, g[2].w}, {g[3].x, g[3].y, g[3].z, g[3].w},
+                                    {g[4].x, g[4].y, g[4].z, g[4].w}};
+      const int64_t qb = qt + 4 * quad;
+      int64_t t = qb / F, f = qb - t * F;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (qb + i < q1) {
+#pragma unroll
+          for (int j = 0; j < kBwdOut; ++j) {
+            const int e = og * kBwdOut + j;
+            if (e < E) g_[t * se.t + e * se.c + f] = gv[j][i];
+          }
+        }
+        if (++f == F) { f = 0; ++t; }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t b2s_dc_workspace_bytes(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
   if (batch <= 0 || channels <= 0) return 16;
-  const DcGrid g = dc_grid(batch, max_frames, bins, channels);
-  return kTicketBytes + (int64_t)sizeof(double) * batch * g.nchunks * g.cp * g.cp + 16;
+  const DcGrid g = dc_grid(batch, max_frames, bins, channels, true);
+  const DcGrid h = dc_grid(batch, max_frames, bins, channels, false);
+  const int64_t cells = std::max<int64_t>((int64_t)g.nchunks * g.cp * g.cp, (int64_t)h.nchunks * h.cp * h.cp);
+  return kTicketBytes + (int64_t)sizeof(double) * batch * cells + 16;
 }
 
 int b2s_dc_forward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
@@ -224,14 +442,19 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
   if (batch == 0) return B2S_OK;
   B2S_REQUIRE(embedding && target && meta && embedding_strides && target_strides && loss && gram &&
               workspace, "NULL pointer");
-  const DcGrid g = dc_grid(batch, max_frames, bins, C);
+  const DcGrid g = dc_grid(batch, max_frames, bins, C, embedding_strides[2] == 1 && target_strides[2] == 1);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
   const Strides st{target_strides[0], target_strides[1], target_strides[2]};
-  dc_gram_kernel<<<dim3((unsigned)batch, g.nchunks), 32 * g.warps, 0, (cudaStream_t)stream>>>(
-      embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, g.blocks, g.pairs, partial,
-      counters, gram, loss);
+  if (g.tiled) {
+    dc_gram_tiled_kernel<<<dim3((unsigned)batch, g.nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
+        embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, partial, counters, gram, loss);
+  } else {
+    dc_gram_kernel<<<dim3((unsigned)batch, g.nchunks), 32 * g.warps, 0, (cudaStream_t)stream>>>(
+        embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, g.blocks, g.pairs, partial,
+        counters, gram, loss);
+  }
   B2S_LAUNCH_CHECK("dc_gram_kernel");
   return B2S_OK;
 }
@@ -250,6 +473,14 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
   const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
   const Strides st{target_strides[0], target_strides[1], target_strides[2]};
   const int64_t points = std::max<int64_t>(1, max_frames * bins);
+  if (C <= kTC && embedding_dim <= kBwdGroups * kBwdOut && se.f == 1 && st.f == 1) {
+    const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 1024,
+                                               std::max<int64_t>(1, (int64_t)kNumSMs * 2 * 4 / batch)));
+    dc_backward_tiled_kernel<<<dim3((unsigned)batch, nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
+        embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss, grad_embedding);
+    B2S_LAUNCH_CHECK("dc_backward_tiled_kernel");
+    return B2S_OK;
+  }
   const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 4096, 128));
   const int Ep = (embedding_dim + BS - 1) / BS * BS;
   const size_t smem = sizeof(float) * C * Ep;

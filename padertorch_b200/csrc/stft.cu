@@ -309,21 +309,24 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
       }
     }
     __syncthreads();
+    // overlap-add: output sample p = (h0 + hq) * shift + i sums frame m = h0 + hq - j at index i + j * shift,
+    // j = overlap-1 .. 0 (increasing frame order); all index arithmetic relative to the chunk, in 32 bits
     const float* fbuf = reinterpret_cast<const float*>(slots);
-    const int64_t p_begin = h0 * shift;
     const int span = hops * shift;
+    const int rel0 = (int)(h0 - m_first);            // slot of frame h0 (0 .. overlap-1)
+    const int last_rel = (int)(m_last - m_first);    // last valid slot
+    const int64_t n0 = h0 * shift - crop_left;       // output index of the chunk's first sample
+    float* orow = out + row * samples_out;
     for (int q = threadIdx.x; q < span; q += blockDim.x) {
-      const int64_t p = p_begin + q;
-      const int64_t n = p - crop_left;
+      const int64_t n = n0 + q;
       if (n < 0 || n >= samples_out) continue;
-      // frames m with m*shift <= p < m*shift + wlen
-      int64_t lo = (p - wlen + 1 <= 0) ? 0 : (p - wlen + shift) / shift;   // ceil((p - wlen + 1) / shift)
-      lo = max(lo, m_first);
-      const int64_t hi = min(p / shift, m_last);
+      const int hq = q / shift, i = q - hq * shift;
       float acc = 0.f;
-      for (int64_t m = lo; m <= hi; ++m)
-        acc += fbuf[(m - m_first) * (2 * fft::kTile) + (int)(p - m * shift)];
-      out[row * samples_out + n] = acc;
+      for (int j = overlap - 1; j >= 0; --j) {
+        const int rel = rel0 + hq - j, idx = i + j * shift;
+        if (rel >= 0 && rel <= last_rel && idx < wlen) acc += fbuf[rel * (2 * fft::kTile) + idx];
+      }
+      orow[n] = acc;
     }
   }
 }

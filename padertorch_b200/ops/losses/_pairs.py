@@ -14,10 +14,12 @@ class PairProblem:
     """Geometry of one call: `groups` groups of K estimate rows / K target rows of length
     `lengths[g]`, `inner` consecutive groups per example."""
 
-    def __init__(self, estimate, target, meta, groups, inner, k, max_length, est_stride, tgt_stride):
+    def __init__(self, estimate, target, meta, groups, inner, k, max_length, est_stride, tgt_stride,
+                 covers_all=False):
         self.estimate, self.target, self.meta = estimate, target, meta
         self.groups, self.inner, self.k = groups, inner, k
         self.max_length, self.est_stride, self.tgt_stride = max_length, est_stride, tgt_stride
+        self.covers_all = covers_all     # every estimate element lies inside some group's length
 
     def stats(self):
         lib = _lib.load()
@@ -55,7 +57,8 @@ class PairProblem:
     def backward(self, stats, kind, flags, tau, reduction, pit, perm, grad_loss):
         lib = _lib.load()
         device = self.estimate.device
-        grad = torch.zeros_like(self.estimate)   # padding beyond each length stays zero
+        # padding beyond each length must stay zero; dense problems are overwritten completely
+        grad = torch.empty_like(self.estimate) if self.covers_all and self.groups else torch.zeros_like(self.estimate)
         if self.groups:
             grad_loss = grad_loss.to(torch.float32).contiguous()
             with torch.cuda.device(device):
@@ -97,7 +100,7 @@ def rowwise_problem(estimate, target):
     t = target.reshape(-1, length).contiguous()
     rows = e.shape[0]
     meta = dense_meta(rows, length, length, e.device)
-    return e, PairProblem(e, t, meta, rows, 1, 1, length, length, length)
+    return e, PairProblem(e, t, meta, rows, 1, 1, length, length, length, covers_all=True)
 
 
 def dense_meta(groups, length, group_stride, device):

@@ -10,13 +10,14 @@ class SseProblem:
     scale tensors expressed as offsets (in floats) from base tensors; see include/b200sep.h."""
 
     def __init__(self, mask_base, obs_base, target_base, scale_base, meta, batch, max_frames,
-                 sources, bins, dual, grad_numel, grad_splits, keep_alive=()):
+                 sources, bins, dual, grad_numel, grad_splits, keep_alive=(), covers_all=True):
         self.mask_base, self.obs_base = mask_base, obs_base
         self.target_base, self.scale_base = target_base, scale_base
         self.meta, self.batch, self.max_frames = meta, batch, max_frames
         self.sources, self.bins, self.dual = sources, bins, dual
         self.grad_numel, self.grad_splits = grad_numel, grad_splits
         self.keep_alive = keep_alive
+        self.covers_all = covers_all     # every element of the gradient buffer belongs to some example
 
     @property
     def device(self):
@@ -43,8 +44,9 @@ class SseProblem:
 
     def backward(self, perm, grad_loss, want_target_grad=False):
         lib = _lib.load()
-        grad_mask = torch.zeros(self.grad_numel, dtype=torch.float32, device=self.device)
-        grad_target = torch.zeros_like(grad_mask) if want_target_grad else None
+        alloc = torch.empty if self.covers_all and self.batch else torch.zeros
+        grad_mask = alloc(self.grad_numel, dtype=torch.float32, device=self.device)
+        grad_target = alloc(self.grad_numel, dtype=torch.float32, device=self.device) if want_target_grad else None
         if self.batch:
             grad_loss = grad_loss.to(torch.float32).contiguous()
             with torch.cuda.device(self.device):
@@ -149,4 +151,5 @@ def padded_problem(mask, observation, target, scale, lengths, dual=False):
             for b in range(batch)]
     meta = meta_tensor(rows, mask.device, cache_key=('sse-padded', frames, k, bins, tuple(lengths)))
     return SseProblem(mask, observation, target, scale, meta, batch, frames, k, bins, dual,
-                      mask.numel(), [(0, mask.numel(), mask.shape)]), mask
+                      mask.numel(), [(0, mask.numel(), mask.shape)],
+                      covers_all=all(n == frames for n in lengths)), mask

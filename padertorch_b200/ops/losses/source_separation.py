@@ -20,11 +20,12 @@ __all__ = [
 # ------------------------------------------------------------------------------------------ deep clustering
 class DcProblem:
     def __init__(self, emb_base, tgt_base, meta, batch, max_frames, bins, e_dim, k, emb_strides,
-                 tgt_strides, grad_numel, grad_splits, keep_alive=()):
+                 tgt_strides, grad_numel, grad_splits, keep_alive=(), covers_all=True):
         self.emb_base, self.tgt_base, self.meta = emb_base, tgt_base, meta
         self.batch, self.max_frames, self.bins, self.e_dim, self.k = batch, max_frames, bins, e_dim, k
         self.emb_strides, self.tgt_strides = emb_strides, tgt_strides
         self.grad_numel, self.grad_splits, self.keep_alive = grad_numel, grad_splits, keep_alive
+        self.covers_all = covers_all
 
     def _strides(self):
         import ctypes
@@ -53,7 +54,8 @@ class DcProblem:
     def backward(self, gram, grad_loss):
         lib = _lib.load()
         device = self.emb_base.device
-        grad = torch.zeros(self.grad_numel, dtype=torch.float32, device=device)
+        alloc = torch.empty if self.covers_all and self.batch else torch.zeros
+        grad = alloc(self.grad_numel, dtype=torch.float32, device=device)
         if self.batch:
             es, ts = self._strides()
             grad_loss = grad_loss.to(torch.float32).contiguous()
@@ -136,7 +138,8 @@ def _pair_pit_problem(estimate, target):
     t = target.reshape(k, -1, length).contiguous()
     inner = e.shape[1]
     meta = _pairs.dense_meta(inner, length, length, e.device)
-    return e, _pairs.PairProblem(e, t, meta, inner, inner, k, length, inner * length, inner * length)
+    return e, _pairs.PairProblem(e, t, meta, inner, inner, k, length, inner * length, inner * length,
+                                 covers_all=True)
 
 
 def pit_loss(

@@ -97,7 +97,8 @@ def dc_losses_per_example(embeddings, target_masks, lengths=None):
             for b in range(batch)]
     meta = meta_tensor(rows, emb.device, cache_key=('dc-padded', frames, e_dim, k, bins, tuple(lengths)))
     problem = DcProblem(emb, tgt, meta, batch, frames, bins, e_dim, k, (e_dim * bins, bins, 1),
-                        (k * bins, bins, 1), emb.numel(), [(0, emb.numel(), emb.shape)])
+                        (k * bins, bins, 1), emb.numel(), [(0, emb.numel(), emb.shape)],
+                        covers_all=all(n == frames for n in lengths))
     return DcFunction.apply(problem, emb)
 
 
@@ -153,7 +154,8 @@ def tasnet_losses(estimates, targets, num_samples, names=('si-sdr', 'log-mse', '
     assert len(num_samples) == batch and max(num_samples) <= length, (num_samples, e.shape)
     rows = [[num_samples[b], b * k * length, b * k * length] for b in range(batch)]
     meta = meta_tensor(rows, e.device, cache_key=('tasnet', k, length, tuple(num_samples)))
-    problem = _pairs.PairProblem(e, t, meta, batch, 1, k, max(num_samples), length, length)
+    problem = _pairs.PairProblem(e, t, meta, batch, 1, k, max(num_samples), length, length,
+                                 covers_all=all(n == length for n in num_samples))
     values = _TasnetFunction.apply(e, problem, tuple(names))
     return {name: v.mean() for name, v in zip(names, values)}
 
