@@ -228,6 +228,7 @@ def run_ours(args, rank, world, local_rank):
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
+        os.environ['NCCL_DEBUG'] = os.environ.get('B2S_NCCL_DEBUG', 'ERROR')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=device)
 
     stft = b2s.ops.STFT(SIZE, SHIFT)
