@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "fft1024.cuh"
+#include "rfft_packed.cuh"
 #include "stft_plan.cuh"
 #include "perm.cuh"
 
@@ -54,8 +55,22 @@ __device__ __forceinline__ int64_t owner_of(int64_t x, int64_t total, int64_t gr
   return ((x + 1) * grid + total - 1) / total - 1;
 }
 
-template <int K, bool VEC16, bool MASK8>
-__global__ void __launch_bounds__(32 * kFusedWarps, kFusedCtasPerSm)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// magnitudes of one slot pair (A side, B side)
+__device__ __forceinline__ float2 mag2(float2 ya, float2 yb) {
+  return make_float2(fft::sqrt_approx(fmaf(ya.x, ya.x, ya.y * ya.y)),
+                     fft::sqrt_approx(fmaf(yb.x, yb.x, yb.y * yb.y)));
+}
+
+// One frame position = (K [+1]) transforms (rfft_packed.cuh) whose magnitudes stay in registers as packed
+// (A side, B side) pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in
+// lane 0 only); mask and |Y| values are read straight from global memory at their point of use (the rows
+// were prefetched into L2 one group earlier), each exactly once.
+template <int K, bool VEC16, bool RECOMPUTE_Y>
+__global__ void __launch_bounds__(32 * kFusedWarps, K <= 2 ? kFusedCtasPerSm : 2)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
                       const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames,
@@ -64,30 +79,21 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
                       double* __restrict__ partial, int* __restrict__ counters, float* __restrict__ loss,
                       int32_t* __restrict__ perm, double* __restrict__ sse) {
   constexpr int NV = K * K;
-  constexpr int F = fft::kBins;
-  extern __shared__ __align__(16) float stage[];   // [2][rows][span] signal rows (rows = K, +1 when |Y| is
-                                                   // recomputed), then the warps' mask / |Y| areas
-  __shared__ float2 tiles[kFusedWarps][fft::kTile];
-  constexpr int kYOffset = ((K * F + 3) / 4) * 4;            // |Y| row after the K mask rows
-  constexpr int kWarpArea = ((kYOffset + F + 3) / 4) * 4;    // floats per warp
+  constexpr int F = rf::kBins;
+  extern __shared__ __align__(16) float smem[];   // [2][rows][span] signal rows (rows = K, +1 when |Y| is
+                                                  // recomputed), then the warps' exchange tiles
   __shared__ double sm[NV * kFusedWarps + NV];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int span = (kFusedWarps - 1) * shift + fft::kSize;
-  const int nrows = yabs ? K : K + 1;              // staged signal rows per group
+  const int span = (kFusedWarps - 1) * shift + rf::kSize;
+  constexpr int nrows = RECOMPUTE_Y ? K + 1 : K;   // staged signal rows per group
   const int buf_floats = nrows * span;
-  float* wmask = stage + 2 * buf_floats;            // [kFusedWarps][kWarpArea] (span is a multiple of 4)
-  float2* tile = tiles[warp];
-  fft::LaneConsts<false> k;
-  k.init(twtab, lane);
-  float2 wa[8], wb[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
-    wb[r] = reinterpret_cast<const float2*>(win)[fft::natural_b(lane, r)];
-  }
-  const int k0 = fft::bin_a(lane, 0), k4 = fft::bin_a(lane, 4) - 256;   // bin of slot p = (p<4 ? k0 : k4) + 64 p
-  const bool dup = lane == 0;   // lane 0: slot 15 duplicates bin 256, slots 16/17 = DC/Nyquist are live
+  float2* tile = reinterpret_cast<float2*>(smem + 2 * buf_floats) + warp * rf::kTile;
+  rf::LaneConsts k;
+  k.init(twtab, win, lane);
+  // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
+  const int k0 = rf::bin_a(lane, 0), k4 = rf::bin_a(lane, 4) - 256;
+  const bool first = lane == 0;
 
   const int64_t total = batch * gpe;
   const int64_t g_begin = range_start(blockIdx.x, total, gridDim.x);
@@ -98,10 +104,14 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     const int64_t b = g / gpe, m0 = (g - b * gpe) * kFusedWarps;
     const int64_t Tb = meta ? meta[2 * b] : samples;
     const int64_t s0 = m0 * shift - pad_left;
-    float* buf = stage + which * buf_floats;
+    float* buf = smem + which * buf_floats;
+    const bool interior = VEC16 && s0 >= 0 && s0 + span <= Tb;
     for (int j = 0; j < nrows; ++j) {
       const float* xr = (j < K) ? sources + (b * K + j) * samples : mixture + b * samples;
-      if (VEC16) {
+      if (interior) {
+        for (int c = threadIdx.x; c < (span >> 2); c += blockDim.x)
+          fft::cp_async_16(buf + j * span + 4 * c, xr + s0 + 4 * c, 16);
+      } else if (VEC16) {
         fft::stage_group(buf + j * span, xr, s0, span, Tb);
       } else {
         for (int c = threadIdx.x; c < span; c += blockDim.x) {   // unaligned rows: plain loads
@@ -111,23 +121,35 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       }
     }
   };
+  // pull the mask rows [K][F] (contiguous) and the |Y| row of this warp's frame of group g into L2
+  auto prefetch_rows = [&](int64_t g) {
+    const int64_t b = g / gpe, m = (g - b * gpe) * kFusedWarps + warp;
+    const int64_t Mb = meta ? meta[2 * b + 1] : frames;
+    if (m >= Mb) return;
+    const char* mrow = reinterpret_cast<const char*>(mask + ((b * frames + m) * K) * F);
+    for (int c = lane * 128; c < K * F * 4 + 127; c += 32 * 128) prefetch_l2(mrow + min(c, K * F * 4 - 4));
+    if (!RECOMPUTE_Y) {
+      const char* row = reinterpret_cast<const char*>(yabs + (b * frames + m) * F);
+      if (lane * 128 < F * 4 + 127) prefetch_l2(row + min(lane * 128, F * 4 - 4));
+    }
+  };
 
-  float acc[NV];
+  float2 acc[NV];   // (A-side sum, B-side sum)
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NV; ++i) acc[i] = make_float2(0.f, 0.f);
 
   // flush the CTA's partial sums of example b (all threads call it)
   auto flush = [&](int64_t b) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float s = warp_sum(acc[i]);
+      const float s = warp_sum(acc[i].x + acc[i].y);
       if (lane == 0) sm[i * kFusedWarps + warp] = (double)s;
-      acc[i] = 0.f;
+      acc[i] = make_float2(0.f, 0.f);
     }
     __syncthreads();
-    const int64_t first = owner_of(b * gpe, total, gridDim.x);
-    const int64_t last = owner_of((b + 1) * gpe - 1, total, gridDim.x);
-    const int slot = (int)(blockIdx.x - first), nparts = (int)(last - first + 1);
+    const int64_t first_owner = owner_of(b * gpe, total, gridDim.x);
+    const int64_t last_owner = owner_of((b + 1) * gpe - 1, total, gridDim.x);
+    const int slot = (int)(blockIdx.x - first_owner), nparts = (int)(last_owner - first_owner + 1);
     double* mine = partial + (b * slots + slot) * NV;
     if (threadIdx.x < NV) {
       double s = 0.0;
@@ -162,7 +184,10 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     __syncthreads();
   };
 
-  if (g_begin < g_end) stage_rows(g_begin, 0);
+  if (g_begin < g_end) {
+    stage_rows(g_begin, 0);
+    prefetch_rows(g_begin);
+  }
   fft::cp_async_commit();
   int cur = 0;
   int64_t b_cur = g_begin < g_end ? g_begin / gpe : -1;
@@ -174,93 +199,60 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     }
     fft::cp_async_wait_all();
     __syncthreads();   // group g staged and visible; the other buffer is free
-    if (g + 1 < g_end) stage_rows(g + 1, cur ^ 1);
+    if (g + 1 < g_end) {
+      stage_rows(g + 1, cur ^ 1);
+      prefetch_rows(g + 1);
+    }
     fft::cp_async_commit();
 
     const int64_t Mb = meta ? meta[2 * b + 1] : frames;
     const int64_t m = m0 + warp;
     if (m < Mb) {
-      // this warp's mask rows [K][F] and |Y| row [F] travel to its private shared-memory area while the
-      // transforms run (mask rows of a frame are contiguous and 8-byte aligned; |Y| rows only 4-byte)
-      float* wm = wmask + warp * kWarpArea;          // [K * F] masks, then [F] |Y| at kYOffset
-      {
-        const float* mrow = mask + ((b * frames + m) * K) * F;
-        if (MASK8) {
-          for (int c = lane; c < (K * F) / 2; c += 32) fft::cp_async_8(wm + 2 * c, mrow + 2 * c);
-          if ((K * F) & 1) { if (lane == 0) fft::cp_async_4(wm + K * F - 1, mrow + K * F - 1); }
-        } else {
-          for (int c = lane; c < K * F; c += 32) fft::cp_async_4(wm + c, mrow + c);
-        }
-        if (yabs) {
-          const float* row = yabs + (b * frames + m) * F;
-          for (int c = lane; c < F; c += 32) fft::cp_async_4(wm + kYOffset + c, row + c);
-        }
-        fft::cp_async_commit();
-      }
-      const float* gbuf = stage + cur * buf_floats + warp * shift;
-      float xs[K > 1 ? K - 1 : 1][18];   // magnitudes of the sources already transformed
-      float x[18];
-#pragma unroll 1
-      for (int j = yabs ? 0 : -1; j < K; ++j) {
-        const float2* src = reinterpret_cast<const float2*>(gbuf + (j < 0 ? K : j) * span);
-        float2 a[8], bb[8], ya[8], yb[8];
+      const float* gbuf = smem + cur * buf_floats + warp * shift;
+      // one transform: magnitudes as (A side, B side) pairs; slot 8 = (|DC|, |Nyquist|), zero outside lane 0;
+      // lane 0's slot 7 holds bin 256 on both sides: its B copy is zeroed (and so is the matching mask load)
+      auto transform = [&](const float* frame, float2 (&x)[9]) {
+        float2 ya[8], yb[8];
         float ydc, ynyq;
+        rf::pass1(frame, tile, k);
+        __syncwarp();
+        rf::pass2(tile, k);
+        __syncwarp();
+        rf::pass3(tile, k, ya, yb, ydc, ynyq);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float2 va = src[fft::natural_a(lane, r)], vb = src[fft::natural_b(lane, r)];
-          a[r] = fft::pmul(va, wa[r]);
-          bb[r] = fft::pmul(vb, wb[r]);
-        }
-        fft::rfft1024(a, bb, tile, k, ya, yb, ydc, ynyq);
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          x[p] = fft::sqrt_approx(fmaf(ya[p].x, ya[p].x, ya[p].y * ya[p].y));
-          x[8 + p] = fft::sqrt_approx(fmaf(yb[p].x, yb[p].x, yb[p].y * yb[p].y));
-        }
-        x[16] = fabsf(ydc); x[17] = fabsf(ynyq);
-        if (j < 0) {
-          // recomputed |Y|: park it in the warp's |Y| row so that the epilogue below is the same
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int kk = (p < 4 ? k0 : k4) + 64 * p;
-            wm[kYOffset + kk] = x[p];
-            if (p < 7 || !dup) wm[kYOffset + fft::kHalf - kk] = x[8 + p];
-          }
-          if (dup) { wm[kYOffset] = x[16]; wm[kYOffset + fft::kHalf] = x[17]; }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj + 1 < K; ++jj)
-            if (j == jj) {
-#pragma unroll
-              for (int q = 0; q < 18; ++q) xs[jj][q] = x[q];
-            }
-        }
-      }
+        for (int p = 0; p < 8; ++p) x[p] = mag2(ya[p], yb[p]);
+        if (first) x[7].y = 0.f;
+        x[8] = first ? make_float2(fabsf(ydc), fabsf(ynyq)) : make_float2(0.f, 0.f);
+      };
+      float2 o[RECOMPUTE_Y ? 9 : 1];       // |Y| pairs when recomputed from the mixture
+      if (RECOMPUTE_Y) transform(gbuf + K * span, reinterpret_cast<float2(&)[9]>(o));
+      float2 x[K][9];
+#pragma unroll(K <= 2 ? K : 1)
+      for (int j = 0; j < K; ++j) transform(gbuf + j * span, x[j]);
+
       // ---- SSE of this frame: e_i = mask_i * |Y| against every source magnitude
-      fft::cp_async_wait_all();
-      __syncwarp();
+      const float* mrow = mask + ((b * frames + m) * K) * F;
+      const float* yrow = RECOMPUTE_Y ? nullptr : yabs + (b * frames + m) * F;
 #pragma unroll
-      for (int q = 0; q < 18; ++q) {
-        // bin of slot q; lanes >= 1 have no DC/Nyquist slots, lane 0 no second copy of bin 256
-        int kk;
-        bool live = true;
-        if (q < 8) kk = (q < 4 ? k0 : k4) + 64 * q;
-        else if (q < 16) { kk = fft::kHalf - ((q - 8 < 4 ? k0 : k4) + 64 * (q - 8)); live = q < 15 || !dup; }
-        else { kk = q == 16 ? 0 : fft::kHalf; live = dup; }
-        if (live) {
-          const float o = wm[kYOffset + kk];
+      for (int p = 0; p < 9; ++p) {
+        const int ka = p < 8 ? (p < 4 ? k0 : k4) + 64 * p : 0;
+        const int kb = rf::kHalf - ka;
+        const bool live_a = p < 8 || first, live_b = p < 7 || (p == 7 ? !first : first);
+        float2 ov;
+        if (!RECOMPUTE_Y) ov = make_float2(live_a ? __ldg(yrow + ka) : 0.f, live_b ? __ldg(yrow + kb) : 0.f);
+        else ov = o[RECOMPUTE_Y ? p : 0];
 #pragma unroll
-          for (int i = 0; i < K; ++i) {
-            const float e = wm[i * F + kk] * o;
+        for (int i = 0; i < K; ++i) {
+          const float2 mv = make_float2(live_a ? __ldg(mrow + i * F + ka) : 0.f,
+                                        live_b ? __ldg(mrow + i * F + kb) : 0.f);
+          const float2 e = rf::mul2(mv, ov);
 #pragma unroll
-            for (int jj = 0; jj < K; ++jj) {
-              const float d = e - (jj + 1 < K ? xs[jj < K - 1 ? jj : 0][q] : x[q]);
-              acc[i * K + jj] = fmaf(d, d, acc[i * K + jj]);
-            }
+          for (int j = 0; j < K; ++j) {
+            const float2 d = rf::sub2(e, x[j][p]);
+            acc[i * K + j] = rf::fma2(d, d, acc[i * K + j]);
           }
         }
       }
-      __syncwarp();   // the area is rewritten by the next frame's copies
     }
   }
   fft::cp_async_wait_all();
@@ -272,26 +264,25 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
                  int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
                  cudaStream_t stream) {
-  constexpr int sources_k_ = K;
   const FusedGrid g = fused_grid(batch, frames);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = al16(sources) && (mixture == nullptr || al16(mixture)) && samples % 4 == 0 &&
                    plan->shift % 4 == 0 && pad_left % 4 == 0;
-  const int span = (kFusedWarps - 1) * plan->shift + fft::kSize;
+  // the transform reads its frame with 16-byte shared-memory loads: frames must start 16-byte aligned
+  B2S_REQUIRE(plan->shift % 4 == 0, "the fused STFT->PIT kernel needs a shift that is a multiple of 4 (got %d)",
+              plan->shift);
+  const int span = (kFusedWarps - 1) * plan->shift + rf::kSize;
   const int nrows = yabs ? K : K + 1;
-  const int warp_area = (((sources_k_ * fft::kBins + 3) / 4) * 4 + fft::kBins + 3) / 4 * 4;
-  const size_t smem = sizeof(float) * (2 * nrows * span + kFusedWarps * warp_area);
-  // mask rows [K][513] of a frame start at multiples of 8 * 513 * K / 2 bytes: 8-byte aligned with the base
-  const bool mask8 = (reinterpret_cast<uintptr_t>(mask) & 7) == 0 && (K % 2 == 0);
-  auto kernel = vec ? (mask8 ? stft_pit_fused_kernel<K, true, true> : stft_pit_fused_kernel<K, true, false>)
-                    : (mask8 ? stft_pit_fused_kernel<K, false, true> : stft_pit_fused_kernel<K, false, false>);
-  B2S_REQUIRE(smem <= 160 * 1024, "shift %d needs %zu bytes of staging: too large", plan->shift, smem);
+  const size_t smem = sizeof(float) * 2 * nrows * span + sizeof(float2) * rf::kTile * kFusedWarps;
+  auto kernel = yabs ? (vec ? stft_pit_fused_kernel<K, true, false> : stft_pit_fused_kernel<K, false, false>)
+                     : (vec ? stft_pit_fused_kernel<K, true, true> : stft_pit_fused_kernel<K, false, true>);
+  B2S_REQUIRE(smem <= 200 * 1024, "shift %d needs %zu bytes of staging: too large", plan->shift, smem);
   static bool configured[4][64] = {};   // per (variant, device)
-  const int variant = (vec ? 2 : 0) + (mask8 ? 1 : 0);
+  const int variant = (vec ? 1 : 0) + (yabs ? 0 : 2);
   if (!configured[variant][plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[variant][plan->device & 63] = true;
   }
   kernel<<<g.grid, 32 * kFusedWarps, smem, stream>>>(mixture, yabs, sources, mask, meta, batch, samples,

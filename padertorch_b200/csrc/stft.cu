@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "fft1024.cuh"
+#include "rfft_packed.cuh"
 #include "stft_plan.cuh"
 
 using namespace b2s;
@@ -116,81 +117,77 @@ stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t sampl
 }
 
 // ------------------------------------------------------------------------------------------- staged forward
-// Same transform, different feeding: a CTA of 4 warps takes 4 consecutive frames of one signal row per
-// iteration.  The 3*shift + 1024 samples they cover are brought into shared memory ONCE (frames overlap
-// 4x at shift 256) by 16-byte cp.async with zero fill outside the signal (the fading and tail pads), double
-// buffered so the copy of group i+1 is in flight while group i is transformed.  Needs 16-byte aligned rows.
+// The packed-fp32x2 transform of rfft_packed.cuh behind a staged feed: a CTA of 4 warps takes 4 consecutive
+// frames of one signal row per iteration.  The 3*shift + 1024 samples they cover are brought into shared
+// memory ONCE (frames overlap 4x at shift 256) by 16-byte cp.async -- with zero fill outside the signal for
+// the groups that touch the fading / tail pads, which therefore never exist in memory -- double buffered so
+// the copy of group i+1 is in flight while group i is transformed.  Needs 16-byte aligned rows.
+// DOUBLE_INTERIOR (adjoint of the iSTFT): interior bins times two, done by not halving the window.
+__device__ __forceinline__ void stage_interior(float* buf, const float* __restrict__ src, int span) {
+  for (int c = threadIdx.x; c < (span >> 2); c += blockDim.x) fft::cp_async_16(buf + 4 * c, src + 4 * c, 16);
+}
+
 template <int LAYOUT, bool DOUBLE_INTERIOR>
 __global__ void __launch_bounds__(32 * kFwdWarps, kFwdCtasPerSm)
 stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                        int64_t pad_left, int64_t frames, int shift, const float* __restrict__ win,
                        const float2* __restrict__ twtab, float* __restrict__ out) {
-  extern __shared__ __align__(16) float stage[];   // [2][span]
-  __shared__ float2 tiles[kFwdWarps][fft::kTile];
+  extern __shared__ __align__(16) float smem[];   // [2][span] staged samples, then the warps' exchange tiles
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int span = (kFwdWarps - 1) * shift + fft::kSize;
-  float2* tile = tiles[warp];
-  fft::LaneConsts<false> k;
-  k.init(twtab, lane);
-  float2 wa[8], wb[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
-    wb[r] = reinterpret_cast<const float2*>(win)[fft::natural_b(lane, r)];
-  }
-  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins;
+  const int span = (kFwdWarps - 1) * shift + rf::kSize;
+  float2* tile = reinterpret_cast<float2*>(smem + 2 * span) + warp * rf::kTile;
+  rf::LaneConsts k;
+  k.init(twtab, win, lane, DOUBLE_INTERIOR ? 1.f : 0.5f);
+  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
+  constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
+  // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
+  const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
+  const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
   // group indices fit 32 bits (checked by the launcher)
   const unsigned groups_per_row = (unsigned)ceil_div(frames, kFwdWarps);
   const unsigned total_groups = (unsigned)rows * groups_per_row;
+  const unsigned step_row = gridDim.x / groups_per_row, step_grp = gridDim.x - step_row * groups_per_row;
+
+  auto stage = [&](float* buf, unsigned row, unsigned grp) {
+    const int64_t s0 = (int64_t)grp * kFwdWarps * shift - pad_left;
+    const float* xr = x + (int64_t)row * row_stride;
+    if (s0 >= 0 && s0 + span <= samples) stage_interior(buf, xr + s0, span);
+    else fft::stage_group(buf, xr, s0, span, samples);
+  };
+
   unsigned g = blockIdx.x;
-  if (g < total_groups) {
-    const unsigned row = g / groups_per_row, m0 = (g - row * groups_per_row) * kFwdWarps;
-    fft::stage_group(stage, x + (int64_t)row * row_stride, (int64_t)m0 * shift - pad_left, span, samples);
-  }
+  unsigned row = g / groups_per_row, grp = g - row * groups_per_row;
+  if (g < total_groups) stage(smem, row, grp);
   fft::cp_async_commit();
   int cur = 0;
   for (; g < total_groups; g += gridDim.x, cur ^= 1) {
-    const unsigned row = g / groups_per_row, m0 = (g - row * groups_per_row) * kFwdWarps;
     fft::cp_async_wait_all();
     __syncthreads();   // group g is visible to every warp; everyone is done with the other buffer
-    const unsigned gn = g + gridDim.x;
-    if (gn < total_groups) {
-      const unsigned rown = gn / groups_per_row, mn = (gn - rown * groups_per_row) * kFwdWarps;
-      fft::stage_group(stage + (cur ^ 1) * span, x + (int64_t)rown * row_stride, (int64_t)mn * shift - pad_left,
-                  span, samples);
-    }
+    unsigned rown = row + step_row, grpn = grp + step_grp;
+    if (grpn >= groups_per_row) { grpn -= groups_per_row; ++rown; }
+    if (g + gridDim.x < total_groups) stage(smem + (cur ^ 1) * span, rown, grpn);
     fft::cp_async_commit();
-    const int64_t m = m0 + warp;
+    const unsigned m = grp * kFwdWarps + warp;
     if (m < frames) {
-      const float2* src = reinterpret_cast<const float2*>(stage + cur * span + warp * shift);
-      float2 a[8], b[8], ya[8], yb[8];
+      float2 ya[8], yb[8];
       float ydc, ynyq;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float2 va = src[fft::natural_a(lane, r)], vb = src[fft::natural_b(lane, r)];
-        a[r] = fft::pmul(va, wa[r]);
-        b[r] = fft::pmul(vb, wb[r]);
-      }
-      fft::rfft1024(a, b, tile, k, ya, yb, ydc, ynyq);
-      float* o = out + (row * frames + m) * kOutPerFrame;
-      // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
-      float* oa0 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * fft::bin_a(lane, 0);
-      float* oa4 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::bin_a(lane, 4) - 256);
-      float* ob0 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::kHalf - fft::bin_a(lane, 0));
-      float* ob4 = o + (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * (fft::kHalf + 256 - fft::bin_a(lane, 4));
-      constexpr int kStep = (LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1) * 64;
+      rf::pass1(smem + cur * span + warp * shift, tile, k);
+      __syncwarp();
+      rf::pass2(tile, k);
+      __syncwarp();
+      rf::pass3<DOUBLE_INTERIOR>(tile, k, ya, yb, ydc, ynyq);
+      float* o = out + ((int64_t)row * frames + m) * kOutPerFrame;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        float2 u = ya[p], v = yb[p];
-        if (DOUBLE_INTERIOR) { u.x *= 2.f; u.y *= 2.f; v.x *= 2.f; v.y *= 2.f; }
-        store_bin_t<LAYOUT>((p < 4 ? oa0 : oa4) + kStep * p, 0, u);
-        if (p < 7 || lane != 0) store_bin_t<LAYOUT>((p < 4 ? ob0 : ob4) - kStep * p, 0, v);
+        store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[p]);
+        store_bin_t<LAYOUT>(o + (p < 4 ? offb0 : offb4) - kS * 64 * p, 0, rf::conj(yb[p]));
       }
       if (lane == 0) {
         store_bin_t<LAYOUT>(o, 0, make_float2(ydc, 0.f));
-        store_bin_t<LAYOUT>(o, fft::kHalf, make_float2(ynyq, 0.f));
+        store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq, 0.f));
       }
     }
+    row = rown; grp = grpn;
   }
   fft::cp_async_wait_all();
 }
@@ -409,10 +406,18 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
     const int64_t groups = rows * ceil_div(frames, kFwdWarps);
     const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * kFwdCtasPerSm);
     const int span = (kFwdWarps - 1) * plan->shift + fft::kSize;
-    const size_t smem = sizeof(float) * 2 * span;
+    const size_t smem = sizeof(float) * 2 * span + sizeof(float2) * rf::kTile * kFwdWarps;
 #define B2S_STAGED(L, D)                                                                                \
-    stft1024_staged_kernel<L, D><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows, samples, row_stride,  \
-        pad_left, frames, plan->shift, win, plan->tw, out)
+    do {                                                                                                \
+      static bool configured[64] = {};                                                                  \
+      if (!configured[plan->device & 63]) {                                                             \
+        B2S_CUDA(cudaFuncSetAttribute(stft1024_staged_kernel<L, D>,                                     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));         \
+        configured[plan->device & 63] = true;                                                           \
+      }                                                                                                 \
+      stft1024_staged_kernel<L, D><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows, samples, row_stride, \
+          pad_left, frames, plan->shift, win, plan->tw, out);                                           \
+    } while (0)
     const bool twice = interior_scale == 2.f;
     switch (layout) {
       case B2S_SPEC_INTERLEAVED: if (twice) B2S_STAGED(B2S_SPEC_INTERLEAVED, true); else B2S_STAGED(B2S_SPEC_INTERLEAVED, false); break;

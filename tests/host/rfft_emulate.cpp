@@ -1,0 +1,64 @@
+// Host emulation of padertorch_b200/csrc/rfft_packed.cuh: the 32 lanes of a warp run pass by pass on the
+// CPU (shared memory = a plain array) and the 513 bins are compared with a double-precision DFT.
+// Checks the index algebra (lane <-> butterfly maps, exchange layouts, twiddles, lane-0 re-pairing,
+// real split) without a GPU.  Prints "max_rel_err <value>" and exits 0 when it is below 1e-5.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../padertorch_b200/csrc/rfft_packed.cuh"
+
+using namespace b2s::rf;
+
+int main(int argc, char** argv) {
+  const int trials = argc > 1 ? atoi(argv[1]) : 4;
+  std::vector<float2> tab(1024);
+  for (int q = 0; q < 1024; ++q) {
+    const double ang = -2.0 * M_PI * q / 1024.0;
+    tab[q] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  double worst = 0.0;
+  srand(1234);
+  for (int trial = 0; trial < trials; ++trial) {
+    alignas(16) static float win[1024];
+    alignas(16) static float frame[1024];
+    for (int i = 0; i < 1024; ++i) {
+      win[i] = trial == 0 ? 1.f : (float)(0.42 - 0.5 * cos(2 * M_PI * i / 1024.0) + 0.08 * cos(4 * M_PI * i / 1024.0));
+      frame[i] = (float)rand() / RAND_MAX - 0.5f;
+    }
+    if (trial == 1) for (int i = 0; i < 1024; ++i) frame[i] = i == 3 ? 1.f : 0.f;   // impulse
+    LaneConsts k[32];
+    for (int l = 0; l < 32; ++l) k[l].init(tab.data(), win, l);
+    alignas(16) static float2 tile[kTile];
+    for (int l = 0; l < 32; ++l) pass1(frame, tile, k[l]);
+    for (int l = 0; l < 32; ++l) pass2(tile, k[l]);
+    std::vector<double> re(513, 1e300), im(513, 1e300);
+    std::vector<int> seen(513, 0);
+    for (int l = 0; l < 32; ++l) {
+      float2 ya[8], yb[8];
+      float ydc, ynyq;
+      pass3(tile, k[l], ya, yb, ydc, ynyq);
+      for (int p = 0; p < 8; ++p) {
+        const int kk = bin_a(l, p);
+        re[kk] = ya[p].x; im[kk] = ya[p].y; seen[kk]++;
+        re[512 - kk] = yb[p].x; im[512 - kk] = -yb[p].y; seen[512 - kk]++;
+      }
+      if (l == 0) { re[0] = ydc; im[0] = 0; seen[0]++; re[512] = ynyq; im[512] = 0; seen[512]++; }
+    }
+    double maxref = 0.0, maxerr = 0.0;
+    for (int f = 0; f <= 512; ++f) {
+      if (!seen[f]) { printf("bin %d never produced\n", f); return 1; }
+      double sr = 0, si = 0;
+      for (int n = 0; n < 1024; ++n) {
+        const double v = (double)frame[n] * (double)win[n], ang = -2.0 * M_PI * (double)((f * n) % 1024) / 1024.0;
+        sr += v * cos(ang); si += v * sin(ang);
+      }
+      maxref = fmax(maxref, hypot(sr, si));
+      maxerr = fmax(maxerr, hypot(sr - re[f], si - im[f]));
+    }
+    worst = fmax(worst, maxerr / maxref);
+  }
+  printf("max_rel_err %.3e\n", worst);
+  return worst < 1e-5 ? 0 : 1;
+}
