@@ -1,12 +1,16 @@
 // Forward 1024-point real FFT, one warp per frame, written for Blackwell's packed fp32x2 pipe (sm_100a).
 //
-// Every complex value lives in an aligned register pair (re, im) and every arithmetic instruction of the
-// transform is an FADD2 / FMUL2 / FFMA2.  What makes that possible are the operand modifiers of the packed
-// instructions, which ptxas folds from plain component shuffles / negations in the source:
-//     R.F32x2.LO_HI      swapped halves          (multiplication by +-i costs nothing)
-//     R.F32x2.HI_LO.NP   per-half negation       (conjugation costs nothing; add operands and FFMA2's addend)
-//     R.F32              32-bit register broadcast (complex * complex = FMUL2 + FFMA2, twiddles stay (re, im))
-// A radix-8 butterfly is 26 packed instructions, a twiddle multiplication 2, one bin pair of the real split 6.
+// Every complex value lives in an aligned register pair (re, im).  Complex additions, conjugations and real
+// scalings are single FADD2 / FMUL2 / FFMA2 instructions; ptxas folds plain component negations in the source
+// into the operand modifiers of the packed instructions (R.F32x2.HI_LO.NP = per-half negation, R.F32 = 32-bit
+// broadcast).  Measured on B200 (tools/ubench/pipe_rate.cu, cycles per warp instruction per SM sub-partition):
+//     FADD2 / FFMA2, plain, negated or per-half negated operands      2.0
+//     FFMA2 with a broadcast (.F32) operand                            2.4
+//     any packed instruction with a SWAPPED operand (R.F32x2.LO_HI)    4.2   <- twice the price
+//     scalar FADD / FFMA                                               0.9 - 1.1
+// i.e. packed arithmetic has the FLOP rate of scalar arithmetic at half the issue slots, and the swap modifier
+// is not free.  Everything that needs swapped halves -- multiplication by +-i folded into an addition, complex
+// times complex -- is therefore written with scalar instructions, the rest packed.
 //
 // Decomposition of the 512-point complex transform of z[n] = (x[2n], x[2n+1]), n = n0 + 8 n1 + 64 n2,
 // k = k0 + 8 k1 + 64 k2  (k n = 64 n2 k0 + 8 n1 (k0 + 8 k1) + n0 k  mod 512):
@@ -76,23 +80,20 @@ B2S_HD float2 fma2(float2 a, float2 b, float2 c) {
 B2S_HD float2 neg(float2 a) { return make_float2(-a.x, -a.y); }
 B2S_HD float2 sub2(float2 a, float2 b) { return add2(a, neg(b)); }
 B2S_HD float2 bcast(float s) { return make_float2(s, s); }
-// -i a  (operand modifier LO_HI + per-half negation)
-B2S_HD float2 rotm(float2 a) { return make_float2(a.y, -a.x); }
-B2S_HD float2 swap(float2 a) { return make_float2(a.y, a.x); }
 B2S_HD float2 conj(float2 a) { return make_float2(a.x, -a.y); }
-// a * w: FMUL2 + FFMA2
+// a - i b and a + i b: scalar on purpose (a packed add with a swapped operand costs twice as much)
+B2S_HD float2 add_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+B2S_HD float2 add_pi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
+// a * w and a * conj(w): four scalar instructions
 B2S_HD float2 cmul(float2 a, float2 w) {
-  const float2 t = mul2(bcast(w.y), swap(a));                 // (w.y a.y, w.y a.x)
-  return fma2(bcast(w.x), a, make_float2(-t.x, t.y));
+  return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
 }
-// a * conj(w)
 B2S_HD float2 cmulc(float2 a, float2 w) {
-  const float2 t = mul2(bcast(w.y), swap(a));
-  return fma2(bcast(w.x), a, make_float2(t.x, -t.y));
+  return make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y));
 }
 
 // Levels 2 and 3 of a forward radix-8 butterfly: a_r = v_r + v_{r+4}, d_r = v_r - v_{r+4} (r < 4) in,
-// v[q] = sum_r v_r exp(-2 pi i r q / 8) out (natural order).  18 packed instructions.
+// v[q] = sum_r v_r exp(-2 pi i r q / 8) out (natural order).  10 packed + 16 scalar instructions.
 B2S_HD void radix8_tail(float2 a0, float2 a1, float2 a2, float2 a3, float2 d0, float2 d1, float2 d2,
                         float2 d3, float2 (&v)[8]) {
   constexpr float c = 0.70710678118654752440f;
@@ -101,18 +102,18 @@ B2S_HD void radix8_tail(float2 a0, float2 a1, float2 a2, float2 a3, float2 d0, f
     const float2 e0 = add2(a0, a2), e1 = sub2(a0, a2), o0 = add2(a1, a3), o1 = sub2(a1, a3);
     v[0] = add2(e0, o0);
     v[4] = sub2(e0, o0);
-    v[2] = add2(e1, rotm(o1));
-    v[6] = sub2(e1, rotm(o1));
+    v[2] = add_mi(e1, o1);
+    v[6] = add_pi(e1, o1);
   }
   // odd outputs: 4-point DFT of (d0, c u1, -i d2, -c g3), u1 = (1 - i) d1, g3 = (1 + i) d3
   {
-    const float2 u1 = add2(d1, rotm(d1)), g3 = sub2(d3, rotm(d3));
-    const float2 e0 = add2(d0, rotm(d2)), e1 = sub2(d0, rotm(d2));
+    const float2 u1 = add_mi(d1, d1), g3 = add_pi(d3, d3);
+    const float2 e0 = add_mi(d0, d2), e1 = add_pi(d0, d2);
     const float2 p = sub2(u1, g3), q = add2(u1, g3);
     v[1] = fma2(p, bcast(c), e0);
     v[5] = fma2(p, bcast(-c), e0);
-    v[3] = fma2(swap(q), make_float2(c, -c), e1);    // e1 - i c q
-    v[7] = fma2(swap(q), make_float2(-c, c), e1);    // e1 + i c q
+    v[3] = make_float2(fmaf(c, q.y, e1.x), fmaf(-c, q.x, e1.y));    // e1 - i c q
+    v[7] = make_float2(fmaf(-c, q.y, e1.x), fmaf(c, q.x, e1.y));    // e1 + i c q
   }
 }
 
@@ -127,6 +128,8 @@ B2S_HD void radix8(float2 (&v)[8]) {
 B2S_HD int bin_a(int lane, int p) {
   return lane ? lane + 64 * p : (p < 4 ? 32 + 64 * p : 64 * (p - 3));
 }
+
+constexpr int kConstFloat4 = 19;   // float4 per lane of a precomputed constant table (LaneConsts::pack / load)
 
 // Per-lane constants, kept in registers across frames.  `tab` = exp(-2 pi i q / 1024), `win` = the
 // (zero-extended) 1024-sample window.
@@ -156,53 +159,149 @@ struct LaneConsts {
       ts[p] = make_float2(t.y, -t.x);
     }
   }
+  // The same constants as a table [kConstFloat4][32 lanes] of float4 (built once per plan on the host): a kernel
+  // prologue is 19 coalesced LDG.128 instead of ~60 indexed loads.
+  void pack(float4* table) const {
+    float4* t = table + lane;
+    for (int i = 0; i < 8; ++i) t[32 * i] = w[i];
+    const float2 tw[14] = {t2[0], t2[1], t2[2], t2[3], t2[4], t2[5], t2[6], t3[0], t3[1], t3[2], t3[3], t3[4], t3[5], t3[6]};
+    for (int i = 0; i < 7; ++i) t[32 * (8 + i)] = make_float4(tw[2 * i].x, tw[2 * i].y, tw[2 * i + 1].x, tw[2 * i + 1].y);
+    for (int i = 0; i < 4; ++i) t[32 * (15 + i)] = make_float4(ts[2 * i].x, ts[2 * i].y, ts[2 * i + 1].x, ts[2 * i + 1].y);
+  }
+  B2S_HD void load(const float4* table, int lane_) {
+    lane = lane_;
+    const float4* t = table + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = t[32 * i];
+    float2 tw[14];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float4 v = t[32 * (8 + i)];
+      tw[2 * i] = make_float2(v.x, v.y);
+      tw[2 * i + 1] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { t2[i] = tw[i]; t3[i] = tw[7 + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = t[32 * (15 + i)];
+      ts[2 * i] = make_float2(v.x, v.y);
+      ts[2 * i + 1] = make_float2(v.z, v.w);
+    }
+  }
 };
 
-// ---- the three passes ---------------------------------------------------------------------------------
-// `frame` = the frame's first sample in (16-byte aligned) staged memory; `tile` = the warp's kTile float2.
-// Pass 1: load, window, radix-8 over n2, write exchange 1.
-B2S_HD void pass1(const float* frame, float2* tile, const LaneConsts& k) {
-  const float4* src = reinterpret_cast<const float4*>(frame) + k.lane;
-  float4 x[8];
+// The same constants in 48 instead of 76 registers: the window, three powers (w, w^2, w^4) of the pass-2 and
+// pass-3 twiddle bases and the two bases of the split twiddles; the other powers are rebuilt when a pass needs
+// them (4 + 4 + 6 complex multiplications per call, shared by all streams of the call).
+struct CompactConsts {
+  float4 w[8];
+  float2 p2[3], p3[3];   // t2[0], t2[1], t2[3] / t3[0], t3[1], t3[3]
+  float2 tsl, tsh;       // ts[p] = tsl W16^p (p < 4), tsh W16^p (p >= 4)
+  int lane;
+  B2S_HD void from_full(const LaneConsts& k) {
+    lane = k.lane;
 #pragma unroll
-  for (int n2 = 0; n2 < 8; ++n2) x[n2] = src[32 * n2];
-  float2 va[8], vb[8];
-  {
-    float2 a[4], d[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float2 lo = make_float2(x[r].x, x[r].y), wl = make_float2(k.w[r].x, k.w[r].y);
-      const float2 hi = mul2(make_float2(x[r + 4].x, x[r + 4].y), make_float2(k.w[r + 4].x, k.w[r + 4].y));
-      a[r] = fma2(lo, wl, hi);
-      d[r] = fma2(lo, wl, neg(hi));
-    }
-    radix8_tail(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3], va);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float2 lo = make_float2(x[r].z, x[r].w), wl = make_float2(k.w[r].z, k.w[r].w);
-      const float2 hi = mul2(make_float2(x[r + 4].z, x[r + 4].w), make_float2(k.w[r + 4].z, k.w[r + 4].w));
-      a[r] = fma2(lo, wl, hi);
-      d[r] = fma2(lo, wl, neg(hi));
-    }
-    radix8_tail(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3], vb);
+    for (int i = 0; i < 8; ++i) w[i] = k.w[i];
+    p2[0] = k.t2[0]; p2[1] = k.t2[1]; p2[2] = k.t2[3];
+    p3[0] = k.t3[0]; p3[1] = k.t3[1]; p3[2] = k.t3[3];
+    tsl = k.ts[0];
+    tsh = make_float2(-k.ts[4].y, k.ts[4].x);   // ts[4] = tsh W16^4 = -i tsh
   }
-  // element (n0 = 2 (l & 3) + e, n1 = l >> 2, k0) at n0 + 8 n1 + 72 k0 = 2 l + e + 72 k0
-  float4* dst = reinterpret_cast<float4*>(tile) + k.lane;
+  B2S_HD void load(const float4* table, int lane_) {
+    LaneConsts k;
+    k.load(table, lane_);   // the loads of unused entries are dead code
+    from_full(k);
+  }
+};
+B2S_HD void expand_powers(const float2 (&p)[3], float2 (&t)[7]) {
+  t[0] = p[0]; t[1] = p[1]; t[3] = p[2];
+  t[2] = cmul(p[0], p[1]);
+  t[4] = cmul(p[0], p[2]);
+  t[5] = cmul(p[1], p[2]);
+  t[6] = cmul(t[2], p[2]);
+}
+// what a pass needs, materialised into a LaneConsts whose other fields stay dead
+B2S_HD void stage_w(const LaneConsts& c, LaneConsts& k) {
+  k.lane = c.lane;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.w[i] = c.w[i];
+}
+B2S_HD void stage_w(const CompactConsts& c, LaneConsts& k) {
+  k.lane = c.lane;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.w[i] = c.w[i];
+}
+B2S_HD void stage_t2(const LaneConsts& c, LaneConsts& k) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i) k.t2[i] = c.t2[i];
+}
+B2S_HD void stage_t2(const CompactConsts& c, LaneConsts& k) { expand_powers(c.p2, k.t2); }
+B2S_HD void stage_t3(const LaneConsts& c, LaneConsts& k) {
+#pragma unroll
+  for (int i = 0; i < 7; ++i) k.t3[i] = c.t3[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.ts[i] = c.ts[i];
+}
+B2S_HD void stage_t3(const CompactConsts& c, LaneConsts& k) {
+  expand_powers(c.p3, k.t3);
+  // W16^p = exp(-2 pi i p / 16)
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  k.ts[0] = c.tsl;
+  k.ts[1] = cmul(c.tsl, make_float2(c1, -s1));
+  k.ts[2] = cmul(c.tsl, make_float2(h, -h));
+  k.ts[3] = cmul(c.tsl, make_float2(s1, -c1));
+  k.ts[4] = make_float2(c.tsh.y, -c.tsh.x);
+  k.ts[5] = cmul(c.tsh, make_float2(-s1, -c1));
+  k.ts[6] = cmul(c.tsh, make_float2(-h, -h));
+  k.ts[7] = cmul(c.tsh, make_float2(-c1, -s1));
+}
+
+// ---- building blocks of the three passes (one frame = one "stream") -----------------------------------
+// Two tile layouts: separate regions for the two exchanges (kTile float2 per stream, exchange 2 at kTile1,
+// two __syncwarp() per frame) or one shared region (kTile1 float2 per stream, exchange 2 at 0, four).
+B2S_HD void load_frame(const float* frame, int lane, float4* x, int count = 8) {
+  const float4* src = reinterpret_cast<const float4*>(frame) + lane;
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2)
+    if (n2 < count) x[n2] = src[32 * n2];
+}
+// window + radix-8 over n2 of the lane's two neighbouring butterflies (x[n2] = z[2l + 64 n2], z[2l + 1 + 64 n2])
+B2S_HD void pass1_regs(const float4* x, const LaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
+  float2 a[4], d[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float2 lo = make_float2(x[r].x, x[r].y), wl = make_float2(k.w[r].x, k.w[r].y);
+    const float2 hi = mul2(make_float2(x[r + 4].x, x[r + 4].y), make_float2(k.w[r + 4].x, k.w[r + 4].y));
+    a[r] = fma2(lo, wl, hi);
+    d[r] = fma2(lo, wl, neg(hi));
+  }
+  radix8_tail(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3], va);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float2 lo = make_float2(x[r].z, x[r].w), wl = make_float2(k.w[r].z, k.w[r].w);
+    const float2 hi = mul2(make_float2(x[r + 4].z, x[r + 4].w), make_float2(k.w[r + 4].z, k.w[r + 4].w));
+    a[r] = fma2(lo, wl, hi);
+    d[r] = fma2(lo, wl, neg(hi));
+  }
+  radix8_tail(a[0], a[1], a[2], a[3], d[0], d[1], d[2], d[3], vb);
+}
+// element (n0 = 2 (l & 3) + e, n1 = l >> 2, k0) at n0 + 8 n1 + 72 k0 = 2 l + e + 72 k0
+B2S_HD void store_ex1(float2* tile, int lane, const float2 (&va)[8], const float2 (&vb)[8]) {
+  float4* dst = reinterpret_cast<float4*>(tile) + lane;
 #pragma unroll
   for (int k0 = 0; k0 < 8; ++k0) dst[36 * k0] = make_float4(va[k0].x, va[k0].y, vb[k0].x, vb[k0].y);
 }
-
-// Pass 2: read exchange 1, twiddle, radix-8 over n1, twiddle-free write of exchange 2.
-B2S_HD void pass2(float2* tile, const LaneConsts& k) {
-  const int a2 = k.lane & 3, k0 = k.lane >> 2;
-  const float4* src = reinterpret_cast<const float4*>(tile) + a2 + 36 * k0;
-  float2 va[8], vb[8];
+B2S_HD void load_ex1(const float2* tile, int lane, float2 (&va)[8], float2 (&vb)[8]) {
+  const float4* src = reinterpret_cast<const float4*>(tile) + (lane & 3) + 36 * (lane >> 2);
 #pragma unroll
   for (int n1 = 0; n1 < 8; ++n1) {
     const float4 x = src[4 * n1];
     va[n1] = make_float2(x.x, x.y);
     vb[n1] = make_float2(x.z, x.w);
   }
+}
+B2S_HD void pass2_regs(const LaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
 #pragma unroll
   for (int n1 = 1; n1 < 8; ++n1) {
     va[n1] = cmul(va[n1], k.t2[n1 - 1]);
@@ -210,13 +309,34 @@ B2S_HD void pass2(float2* tile, const LaneConsts& k) {
   }
   radix8(va);
   radix8(vb);
-  // element (n0 = 2 a2 + e, k0, k1) at k0 + 8 k1 + 66 n0
-  float2* dst = tile + kTile1 + k0 + 132 * a2;
+}
+// element (n0 = 2 (l & 3) + e, k0 = l >> 2, k1) at k0 + 8 k1 + 66 n0; `ex2` = start of the exchange-2 region
+B2S_HD void store_ex2(float2* ex2, int lane, const float2 (&va)[8], const float2 (&vb)[8]) {
+  float2* dst = ex2 + (lane >> 2) + 132 * (lane & 3);
 #pragma unroll
   for (int k1 = 0; k1 < 8; ++k1) {
     dst[8 * k1] = va[k1];
     dst[8 * k1 + 66] = vb[k1];
   }
+}
+B2S_HD void load_ex2(const float2* ex2, int lane, float2 (&a)[8], float2 (&b)[8]) {
+  const float2* sa = ex2 + lane;
+  const float2* sb = ex2 + (lane ? 64 - lane : 32);
+#pragma unroll
+  for (int n0 = 0; n0 < 8; ++n0) {
+    a[n0] = sa[66 * n0];
+    b[n0] = sb[66 * n0];
+  }
+}
+B2S_HD void pass3_twiddle_a(const LaneConsts& k, float2 (&a)[8]) {   // lanes >= 1 only (butterfly 0 has none)
+#pragma unroll
+  for (int n0 = 1; n0 < 8; ++n0) a[n0] = cmul(a[n0], k.t3[n0 - 1]);
+}
+// butterfly 64 - l: twiddles W8^n0 conj(w^n0); the W8^n0 factor shifts the outputs by one slot:
+// b[q] = Z[(64 - l) + 64 ((q - 1) & 7)], the mirror of a[p] = Z[l + 64 p] is b[(8 - p) & 7]
+B2S_HD void pass3_twiddle_b(const LaneConsts& k, float2 (&b)[8]) {
+#pragma unroll
+  for (int n0 = 1; n0 < 8; ++n0) b[n0] = cmulc(b[n0], k.t3[n0 - 1]);
 }
 
 // dst <- src in lane 0 only, in place
@@ -228,6 +348,10 @@ B2S_HD void pmov(float2& dst, float2 src, bool pred) {
   if (pred) dst = src;
 #endif
 }
+// Lane 0: a[p] = Z[64 p], b[q] = Z[32 + 64 ((q - 1) & 7)].  Slots 0..3 <- butterfly 32: (Z[32 + 64 p], Z[480 - 64 p])
+// = (b[p + 1], b[(8 - p) & 7]); slots 4..7 <- butterfly 0: (Z[64 (p - 3)], Z[512 - 64 (p - 3)]) = (a[p - 3], a[11 - p]).
+// As a parallel move: a0 <- b1 <- a4 and the cycle (a1 b2 a5 a2 b3 a6 a3 b4 a7 a4): 13 in-place moves,
+// predicated so that the other lanes keep their registers where they are (no merge copies).
 B2S_HD void repair_lane0(float2 (&a)[8], float2 (&b)[8], bool first) {
   pmov(a[0], b[1], first);
   pmov(b[1], a[4], first);
@@ -237,28 +361,11 @@ B2S_HD void repair_lane0(float2 (&a)[8], float2 (&b)[8], bool first) {
   pmov(a[7], a[4], first); pmov(a[4], t, first);
 }
 
-// Pass 3 + real split.  On return slot p holds ya[p] = Y[bin_a(lane, p)] and yb[p] = conj(Y[512 - bin_a]);
-// y_dc / y_nyq = Y[0], Y[512] (meaningful in lane 0 only).
+// radix-8 over n0 + real split.  On return slot p holds ya[p] = Y[bin_a(lane, p)] and yb[p] =
+// conj(Y[512 - bin_a]); y_dc / y_nyq = Y[0], Y[512] (meaningful in lane 0 only).
 template <bool DOUBLE_INTERIOR = false>
-B2S_HD void pass3(const float2* tile, const LaneConsts& k, float2 (&ya)[8], float2 (&yb)[8], float& y_dc,
-                  float& y_nyq) {
-  const int lane = k.lane;
-  const float2* sa = tile + kTile1 + lane;
-  const float2* sb = tile + kTile1 + (lane ? 64 - lane : 32);
-  float2 a[8], b[8];
-#pragma unroll
-  for (int n0 = 0; n0 < 8; ++n0) {
-    a[n0] = sa[66 * n0];
-    b[n0] = sb[66 * n0];
-  }
-  if (lane != 0) {
-#pragma unroll
-    for (int n0 = 1; n0 < 8; ++n0) a[n0] = cmul(a[n0], k.t3[n0 - 1]);
-  }
-  // butterfly 64 - l: twiddles W8^n0 conj(w^n0); the W8^n0 factor shifts the outputs by one slot:
-  // b[q] = Z[(64 - l) + 64 ((q - 1) & 7)], the mirror of a[p] = Z[l + 64 p] is b[(8 - p) & 7]
-#pragma unroll
-  for (int n0 = 1; n0 < 8; ++n0) b[n0] = cmulc(b[n0], k.t3[n0 - 1]);
+B2S_HD void pass3_regs(const LaneConsts& k, float2 (&a)[8], float2 (&b)[8], float2 (&ya)[8], float2 (&yb)[8],
+                       float& y_dc, float& y_nyq) {
   radix8(a);
   radix8(b);
   // Z carries the factor 1/2 (window): Y[0] = 2 (Re + Im), Y[512] = 2 (Re - Im); with the un-halved window of
@@ -268,11 +375,7 @@ B2S_HD void pass3(const float2* tile, const LaneConsts& k, float2 (&ya)[8], floa
     y_dc = DOUBLE_INTERIOR ? s : s + s;
     y_nyq = DOUBLE_INTERIOR ? d : d + d;
   }
-  // Lane 0: a[p] = Z[64 p], b[q] = Z[32 + 64 ((q - 1) & 7)].  Slots 0..3 <- butterfly 32: (Z[32 + 64 p], Z[480 - 64 p])
-  // = (b[p + 1], b[(8 - p) & 7]); slots 4..7 <- butterfly 0: (Z[64 (p - 3)], Z[512 - 64 (p - 3)]) = (a[p - 3], a[11 - p]).
-  // As a parallel move: a0 <- b1 <- a4 and the cycle (a1 b2 a5 a2 b3 a6 a3 b4 a7 a4): 13 in-place moves,
-  // predicated so that the other lanes keep their registers where they are (no merge copies).
-  repair_lane0(a, b, lane == 0);
+  repair_lane0(a, b, k.lane == 0);
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     const float2 A = a[p], B = b[(8 - p) & 7];
@@ -283,6 +386,125 @@ B2S_HD void pass3(const float2* tile, const LaneConsts& k, float2 (&ya)[8], floa
     yb[p] = sub2(s, t);
   }
 }
+
+// ---- single-stream passes (separate exchange regions): what the host emulation drives ----------------------
+B2S_HD void pass1(const float* frame, float2* tile, const LaneConsts& k) {
+  float4 x[8];
+  float2 va[8], vb[8];
+  load_frame(frame, k.lane, x);
+  pass1_regs(x, k, va, vb);
+  store_ex1(tile, k.lane, va, vb);
+}
+B2S_HD void pass2(float2* tile, const LaneConsts& k) {
+  float2 va[8], vb[8];
+  load_ex1(tile, k.lane, va, vb);
+  pass2_regs(k, va, vb);
+  store_ex2(tile + kTile1, k.lane, va, vb);
+}
+template <bool DOUBLE_INTERIOR = false>
+B2S_HD void pass3(const float2* tile, const LaneConsts& k, float2 (&ya)[8], float2 (&yb)[8], float& y_dc,
+                  float& y_nyq) {
+  float2 a[8], b[8];
+  load_ex2(tile + kTile1, k.lane, a, b);
+  if (k.lane != 0) pass3_twiddle_a(k, a);
+  pass3_twiddle_b(k, b);
+  pass3_regs<DOUBLE_INTERIOR>(k, a, b, ya, yb, y_dc, y_nyq);
+}
+
+#ifdef __CUDACC__
+// ---- NS frames per warp, interleaved for instruction-level parallelism -------------------------------------
+// The per-lane constants (76 registers) are shared by the streams, so two frames per warp cost ~50 registers
+// more, not twice as many, and every latency (LDS, the 4-deep packed pipe) is covered by the other stream.
+// `tile` = NS regions of kTile1 float2 (both exchanges share a region: four __syncwarp() per call).
+// CONSECUTIVE: the frames are 256 samples apart in the same staged row (shift 256): their 75 % overlap is
+// loaded once (8 + 2 (NS - 1) LDS.128 instead of 8 NS).  Otherwise frame s starts at frame0 + s * stride.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `input_consumed()` is called (by the whole warp) once every lane holds its input samples in registers: the
+// staged frames may be overwritten from then on (a single-slot pipeline starts its next copy there).
+template <int NS, bool CONSECUTIVE, bool DOUBLE_INTERIOR, class Consts, class Hook = NoHook>
+__device__ __forceinline__ void rfft_streams(const float* frame0, int stride, float2* tile, const Consts& consts,
+                                             float2 (&ya)[NS][8], float2 (&yb)[NS][8], float (&y_dc)[NS],
+                                             float (&y_nyq)[NS], int ablate = 0, Hook input_consumed = Hook()) {
+  // ablate (kernel-tuning experiments only): 2 = skip the shared-memory exchanges, 4 = skip the arithmetic
+  const int lane = consts.lane;
+  LaneConsts k;   // fields are materialised right before the pass that uses them
+  stage_w(consts, k);
+  float2 va[NS][8], vb[NS][8];
+  if (CONSECUTIVE) {
+    float4 x[8 + 2 * (NS - 1)];
+    const float4* src = reinterpret_cast<const float4*>(frame0) + lane;
+#pragma unroll
+    for (int n2 = 0; n2 < 8 + 2 * (NS - 1); ++n2) x[n2] = src[32 * n2];
+    if (!(ablate & 4)) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) pass1_regs(x + 2 * s, k, va[s], vb[s]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { va[s][i] = make_float2(x[i + 2 * s].x, x[i + 2 * s].y); vb[s][i] = make_float2(x[i + 2 * s].z, x[i + 2 * s].w); }
+    }
+  } else {
+    float4 x[NS][8];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_frame(frame0 + s * stride, lane, x[s]);
+    if (!(ablate & 4)) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) pass1_regs(x[s], k, va[s], vb[s]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { va[s][i] = make_float2(x[s][i].x, x[s][i].y); vb[s][i] = make_float2(x[s][i].z, x[s][i].w); }
+    }
+  }
+  __syncwarp();   // the previous call's exchange-2 reads are done
+  input_consumed();
+  if (!(ablate & 2)) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) store_ex1(tile + s * kTile1, lane, va[s], vb[s]);
+  }
+  __syncwarp();
+  if (!(ablate & 2)) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_ex1(tile + s * kTile1, lane, va[s], vb[s]);
+  }
+  __syncwarp();   // exchange 2 overwrites the region
+  if (!(ablate & 4)) {
+    stage_t2(consts, k);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pass2_regs(k, va[s], vb[s]);
+  }
+  if (!(ablate & 2)) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) store_ex2(tile + s * kTile1, lane, va[s], vb[s]);
+  }
+  __syncwarp();
+  if (!(ablate & 2)) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_ex2(tile + s * kTile1, lane, va[s], vb[s]);
+  }
+  if (!(ablate & 4)) {
+    stage_t3(consts, k);
+    if (lane != 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) pass3_twiddle_a(k, va[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pass3_twiddle_b(k, vb[s]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pass3_regs<DOUBLE_INTERIOR>(k, va[s], vb[s], ya[s], yb[s], y_dc[s], y_nyq[s]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ya[s][i] = va[s][i]; yb[s][i] = vb[s][i]; }
+      y_dc[s] = va[s][0].x; y_nyq[s] = vb[s][0].y;
+    }
+  }
+}
+#endif
 
 }  // namespace rf
 }  // namespace b2s

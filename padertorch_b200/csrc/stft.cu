@@ -11,12 +11,16 @@
 //     non-power-of-two sizes.
 // Reference arithmetic: padertorch/ops/_stft.py:103-263.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
 #include "fft1024.cuh"
 #include "rfft_packed.cuh"
 #include "stft_plan.cuh"
+#include "tma.cuh"
 
 using namespace b2s;
 
@@ -127,29 +131,33 @@ __device__ __forceinline__ void stage_interior(float* buf, const float* __restri
   for (int c = threadIdx.x; c < (span >> 2); c += blockDim.x) fft::cp_async_16(buf + 4 * c, src + 4 * c, 16);
 }
 
-template <int LAYOUT, bool DOUBLE_INTERIOR>
-__global__ void __launch_bounds__(32 * kFwdWarps, kFwdCtasPerSm)
+// NS = frames per warp and iteration (rfft_streams), CTAS = resident CTAs per SM the registers are budgeted
+// for, COMPACT = 48-register constants (rfft_packed.cuh).  Default (2, 2, false); the others are selectable
+// with B2S_FWD_CFG=NS,CTAS,COMPACT for the |Y| layout at shift 256 (kernel tuning experiments).
+template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int kFwdStreams, int CTAS, bool COMPACT>
+__global__ void __launch_bounds__(32 * kFwdWarps, CTAS)
 stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
-                       int64_t pad_left, int64_t frames, int shift, const float* __restrict__ win,
-                       const float2* __restrict__ twtab, float* __restrict__ out) {
+                       int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
+                       float* __restrict__ out, int ablate) {
   extern __shared__ __align__(16) float smem[];   // [2][span] staged samples, then the warps' exchange tiles
+  constexpr int kFwdGroup = kFwdWarps * kFwdStreams;          // frames per CTA and iteration
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int span = (kFwdWarps - 1) * shift + rf::kSize;
-  float2* tile = reinterpret_cast<float2*>(smem + 2 * span) + warp * rf::kTile;
-  rf::LaneConsts k;
-  k.init(twtab, win, lane, DOUBLE_INTERIOR ? 1.f : 0.5f);
+  const int span = (kFwdGroup - 1) * shift + rf::kSize;
+  float2* tile = reinterpret_cast<float2*>(smem + 2 * span) + warp * (kFwdStreams * rf::kTile1);
+  typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
+  k.load(lane_table, lane);
   constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
   constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
   // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
   const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
   const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
   // group indices fit 32 bits (checked by the launcher)
-  const unsigned groups_per_row = (unsigned)ceil_div(frames, kFwdWarps);
+  const unsigned groups_per_row = (unsigned)ceil_div(frames, kFwdGroup);
   const unsigned total_groups = (unsigned)rows * groups_per_row;
   const unsigned step_row = gridDim.x / groups_per_row, step_grp = gridDim.x - step_row * groups_per_row;
 
   auto stage = [&](float* buf, unsigned row, unsigned grp) {
-    const int64_t s0 = (int64_t)grp * kFwdWarps * shift - pad_left;
+    const int64_t s0 = (int64_t)grp * kFwdGroup * shift - pad_left;
     const float* xr = x + (int64_t)row * row_stride;
     if (s0 >= 0 && s0 + span <= samples) stage_interior(buf, xr + s0, span);
     else fft::stage_group(buf, xr, s0, span, samples);
@@ -167,29 +175,163 @@ stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t sample
     if (grpn >= groups_per_row) { grpn -= groups_per_row; ++rown; }
     if (g + gridDim.x < total_groups) stage(smem + (cur ^ 1) * span, rown, grpn);
     fft::cp_async_commit();
-    const unsigned m = grp * kFwdWarps + warp;
-    if (m < frames) {
-      float2 ya[8], yb[8];
-      float ydc, ynyq;
-      rf::pass1(smem + cur * span + warp * shift, tile, k);
-      __syncwarp();
-      rf::pass2(tile, k);
-      __syncwarp();
-      rf::pass3<DOUBLE_INTERIOR>(tile, k, ya, yb, ydc, ynyq);
-      float* o = out + ((int64_t)row * frames + m) * kOutPerFrame;
+    const unsigned m0 = grp * kFwdGroup + warp * kFwdStreams;
+    if (m0 < frames) {
+      float2 ya[kFwdStreams][8], yb[kFwdStreams][8];
+      float ydc[kFwdStreams], ynyq[kFwdStreams];
+      rf::rfft_streams<kFwdStreams, SHIFT256 && (kFwdStreams > 1), DOUBLE_INTERIOR>(
+          smem + cur * span + warp * kFwdStreams * shift, shift, tile, k, ya, yb, ydc, ynyq, ablate);
+      if (ablate & 1) {   // experiments: no global stores (one dependent dummy store keeps the work alive)
+        float acc = 0.f;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[p]);
-        store_bin_t<LAYOUT>(o + (p < 4 ? offb0 : offb4) - kS * 64 * p, 0, rf::conj(yb[p]));
+        for (int s = 0; s < kFwdStreams; ++s)
+#pragma unroll
+          for (int p = 0; p < 8; ++p) acc += ya[s][p].x + ya[s][p].y + yb[s][p].x + yb[s][p].y;
+        if (acc == 1.2345f) out[0] = acc;
+      } else {
+#pragma unroll
+      for (int s = 0; s < kFwdStreams; ++s) {
+        if (m0 + s < frames) {
+          float* o = out + ((int64_t)row * frames + m0 + s) * kOutPerFrame;
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[s][p]);
+            store_bin_t<LAYOUT>(o + (p < 4 ? offb0 : offb4) - kS * 64 * p, 0, rf::conj(yb[s][p]));
+          }
+          if (lane == 0) {
+            store_bin_t<LAYOUT>(o, 0, make_float2(ydc[s], 0.f));
+            store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq[s], 0.f));
+          }
+        }
       }
-      if (lane == 0) {
-        store_bin_t<LAYOUT>(o, 0, make_float2(ydc, 0.f));
-        store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq, 0.f));
       }
     }
     row = rown; grp = grpn;
   }
   fft::cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------- warp pipelines
+// The default fast forward path.  Every warp is an independent pipeline: it owns units of two consecutive
+// frames of one row, a TMA bulk copy (one instruction of one lane) brings the unit's shift + 1024 samples into
+// the warp's own ring slot and signals an mbarrier, the copy of the next unit is started as soon as pass 1 has
+// read the current one.  No block-wide barrier, no per-thread staging code: warps drift apart, so the copies,
+// the shared-memory exchanges, the arithmetic and the spectrum stores of different warps overlap instead of
+// marching through the same phase together (the block-synchronous staged kernel above measures T = T_copy +
+// T_fft + T_store on B200, tools/ubench and B2S_ABLATE).  Units that touch the zero padding (fading, tail) or
+// are not 16-byte aligned are filled by the warp itself.
+constexpr int kPipeWarps = 4;
+
+// NS frames per unit, CTAS resident CTAs per SM the registers are budgeted for, COMPACT 48-register constants,
+// STAGES ring slots per warp (1: the next copy starts as soon as pass 1 holds the current samples in registers).
+template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int NS, int CTAS, bool COMPACT, int STAGES>
+__global__ void __launch_bounds__(32 * kPipeWarps, CTAS)
+stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
+                     int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
+                     float* __restrict__ out, int ablate) {
+  extern __shared__ __align__(16) float smem[];   // per warp: [STAGES][span] samples, NS exchange tiles, output rows
+  __shared__ __align__(8) uint64_t bars[kPipeWarps][STAGES];
+  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
+  constexpr int kOutArea = (NS * kOutPerFrame + 8 + 3) / 4 * 4;   // NS rows + alignment slack, multiple of 4 floats
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int span = (NS - 1) * shift + rf::kSize;    // NS frames, `shift` apart
+  const int warp_floats = STAGES * span + 2 * NS * rf::kTile1 + kOutArea;
+  float* ring = smem + warp * warp_floats;
+  float2* tile = reinterpret_cast<float2*>(ring + STAGES * span);
+  float* obuf = ring + STAGES * span + 2 * NS * rf::kTile1;
+  uint64_t* bar = bars[warp];
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) tma::mbar_init(bar + i, 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+  typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
+  k.load(lane_table, lane);
+  constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
+  const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
+  const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
+
+  const int64_t units_per_row = ceil_div(frames, NS);
+  const int64_t total = rows * units_per_row;
+  const int64_t nwarps = (int64_t)gridDim.x * kPipeWarps;
+  unsigned parity = 0;      // bit i: phase of slot i's barrier the warp waits for next
+  unsigned by_tma = 0;      // bit i: slot i is being filled by a bulk copy
+
+  // start filling `slot` with unit u (or remember that the warp has to fill it itself)
+  auto issue = [&](int64_t u, int slot) {
+    if (u >= total) return;
+    const int64_t row = u / units_per_row, m0 = (u - row * units_per_row) * NS;
+    const int64_t s0 = m0 * shift - pad_left;
+    const float* src = x + row * row_stride + s0;
+    const bool bulk = s0 >= 0 && s0 + span <= samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    by_tma = bulk ? (by_tma | (1u << slot)) : (by_tma & ~(1u << slot));
+    if (bulk && lane == 0) {
+      tma::fence_proxy_async();   // the slot was last read through the generic proxy
+      tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
+      tma::bulk_g2s(ring + slot * span, src, (unsigned)span * 4u, bar + slot);
+    }
+  };
+
+  int64_t u = (int64_t)blockIdx.x * kPipeWarps + warp;
+#pragma unroll
+  for (int i = 0; i < (STAGES > 1 ? STAGES - 1 : 1); ++i) issue(u + i * nwarps, i);
+  for (int it = 0; u < total; u += nwarps, ++it) {
+    const int slot = it % STAGES;
+    if (STAGES > 1) issue(u + (STAGES - 1) * nwarps, (it + STAGES - 1) % STAGES);
+    const int64_t row = u / units_per_row, m0 = (u - row * units_per_row) * NS;
+    float* buf = ring + slot * span;
+    if (by_tma & (1u << slot)) {
+      tma::mbar_wait(bar + slot, (parity >> slot) & 1u);
+      parity ^= 1u << slot;
+    } else {
+      const int64_t s0 = m0 * shift - pad_left;
+      const float* xr = x + row * row_stride;
+      for (int i = lane; i < span; i += 32) {
+        const int64_t n = s0 + i;
+        buf[i] = (n >= 0 && n < samples) ? __ldg(xr + n) : 0.f;
+      }
+      __syncwarp();
+    }
+    float2 ya[NS][8], yb[NS][8];
+    float ydc[NS], ynyq[NS];
+    auto next_copy = [&]() { if (STAGES == 1) issue(u + nwarps, 0); };
+    rf::rfft_streams<NS, SHIFT256 && (NS > 1), DOUBLE_INTERIOR>(buf, shift, tile, k, ya, yb, ydc, ynyq, ablate, next_copy);
+    if (ablate & 1) continue;   // experiments: no output at all
+    // The spectrum rows of the unit are adjacent in global memory.  They are assembled in shared memory at
+    // the global address's phase within 16 bytes and leave as ONE asynchronous TMA bulk store (plus at most 3
+    // floats at either end from lanes): per-lane STG of rows that are only 4-byte aligned costs several LSU
+    // cycles per touched line and blocks the shared-memory traffic of the whole SM behind it.
+    const int nrows = (int)min((int64_t)NS, frames - m0);
+    float* g = out + (row * frames + m0) * kOutPerFrame;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
+    if (lane == 0) tma::bulk_wait_read<0>();   // the previous unit's store has read the staging rows
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      float* o = obuf + phase + s * kOutPerFrame;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[s][p]);
+        store_bin_t<LAYOUT>(o + (p < 4 ? offb0 : offb4) - kS * 64 * p, 0, rf::conj(yb[s][p]));
+      }
+      if (lane == 0) {
+        store_bin_t<LAYOUT>(o, 0, make_float2(ydc[s], 0.f));
+        store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq[s], 0.f));
+      }
+    }
+    tma::fence_proxy_async();   // the rows were written through the generic proxy
+    __syncwarp();
+    const int n = nrows * kOutPerFrame;
+    const int head = (4 - phase) & 3, mid = (n - head) & ~3, tail = n - head - mid;
+    if (lane == 0) {
+      tma::bulk_s2g(g + head, obuf + phase + head, (unsigned)mid * 4u);
+      tma::bulk_commit();
+    }
+    if (lane < head) g[lane] = obuf[phase + lane];
+    if (lane < tail) g[head + mid + lane] = obuf[phase + head + mid + lane];
+  }
+  if (lane == 0) tma::bulk_wait<0>();   // shared memory must outlive the last store
 }
 
 // ------------------------------------------------------------------------------------------- generic forward
@@ -401,30 +543,113 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
   if (total == 0) return B2S_OK;
   const bool aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && row_stride % 4 == 0 &&
                          plan->shift % 4 == 0 && pad_left % 4 == 0;
-  if (plan->fast && plan->wlen == fft::kSize && aligned16 && plan->shift <= fft::kSize &&
-      rows * ceil_div(frames, kFwdWarps) < (int64_t)1 << 30) {
-    const int64_t groups = rows * ceil_div(frames, kFwdWarps);
-    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * kFwdCtasPerSm);
-    const int span = (kFwdWarps - 1) * plan->shift + fft::kSize;
-    const size_t smem = sizeof(float) * 2 * span + sizeof(float2) * rf::kTile * kFwdWarps;
-#define B2S_STAGED(L, D)                                                                                \
+  static const int use_staged = [] { const char* e = getenv("B2S_FWD_STAGED"); return e ? atoi(e) : 0; }();
+  if (plan->fast && plan->wlen == fft::kSize && plan->shift % 4 == 0 && plan->shift <= fft::kSize && !use_staged) {
+    // warp pipelines (TMA-fed); any row alignment (unaligned units are filled by the warp itself)
+    // configuration NS,CTAS,COMPACT,STAGES: default 2,2,0,2; others (|Y| layout, shift 256) via B2S_PIPE_CFG
+    static const int cfg = [] {
+      const char* e = getenv("B2S_PIPE_CFG");
+      int ns = 2, ctas = 2, compact = 0, stages = 2;
+      if (e) sscanf(e, "%d,%d,%d,%d", &ns, &ctas, &compact, &stages);
+      return ns * 1000 + ctas * 100 + compact * 10 + stages;
+    }();
+    static const int ablate = [] { const char* e = getenv("B2S_ABLATE"); return e ? atoi(e) : 0; }();
+    const bool twice = interior_scale == 2.f;
+    const bool experimental = cfg != 2202 && layout == B2S_SPEC_ABS && !twice && plan->shift == 256;
+    const int ns = experimental ? cfg / 1000 : 2, ctas = experimental ? (cfg / 100) % 10 : 2;
+    const int stages = experimental ? cfg % 10 : 2;
+    const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
+    B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
+    const int64_t units = rows * ceil_div(frames, ns);
+    const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * ctas);
+    const int span = (ns - 1) * plan->shift + fft::kSize;
+    const int out_area = (ns * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
+    const size_t smem = kPipeWarps * (sizeof(float) * (stages * span + out_area) + sizeof(float2) * ns * rf::kTile1);
+#define B2S_PIPE(L, D, S, NS, C, CP, ST)                                                                \
     do {                                                                                                \
       static bool configured[64] = {};                                                                  \
       if (!configured[plan->device & 63]) {                                                             \
-        B2S_CUDA(cudaFuncSetAttribute(stft1024_staged_kernel<L, D>,                                     \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));         \
+        B2S_CUDA(cudaFuncSetAttribute(stft1024_warp_kernel<L, D, S, NS, C, CP, ST>,                     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));        \
         configured[plan->device & 63] = true;                                                           \
       }                                                                                                 \
-      stft1024_staged_kernel<L, D><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows, samples, row_stride, \
-          pad_left, frames, plan->shift, win, plan->tw, out);                                           \
+      stft1024_warp_kernel<L, D, S, NS, C, CP, ST><<<grid, 32 * kPipeWarps, smem, stream>>>(x, rows,    \
+          samples, row_stride, pad_left, frames, plan->shift, table, out, ablate);                      \
     } while (0)
-    const bool twice = interior_scale == 2.f;
-    switch (layout) {
-      case B2S_SPEC_INTERLEAVED: if (twice) B2S_STAGED(B2S_SPEC_INTERLEAVED, true); else B2S_STAGED(B2S_SPEC_INTERLEAVED, false); break;
-      case B2S_SPEC_CONCAT: if (twice) B2S_STAGED(B2S_SPEC_CONCAT, true); else B2S_STAGED(B2S_SPEC_CONCAT, false); break;
-      case B2S_SPEC_ABS: B2S_STAGED(B2S_SPEC_ABS, false); break;
-      default: B2S_STAGED(B2S_SPEC_LOG1P_ABS, false); break;
+#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) B2S_PIPE(L, D, true, 2, 2, false, 2); else B2S_PIPE(L, D, false, 2, 2, false, 2); } while (0)
+    if (experimental) {
+      switch (cfg) {
+        case 2201: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 2, false, 1); break;
+        case 2311: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 3, true, 1); break;
+        case 2312: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 3, true, 2); break;
+        case 1411: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 4, true, 1); break;
+        case 1412: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 4, true, 2); break;
+        case 1302: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 3, false, 2); break;
+        default: B2S_REQUIRE(false, "unknown B2S_PIPE_CFG %d", cfg);
+      }
+    } else {
+      switch (layout) {
+        case B2S_SPEC_INTERLEAVED: if (twice) B2S_PIPE_S(B2S_SPEC_INTERLEAVED, true); else B2S_PIPE_S(B2S_SPEC_INTERLEAVED, false); break;
+        case B2S_SPEC_CONCAT: if (twice) B2S_PIPE_S(B2S_SPEC_CONCAT, true); else B2S_PIPE_S(B2S_SPEC_CONCAT, false); break;
+        case B2S_SPEC_ABS: B2S_PIPE_S(B2S_SPEC_ABS, false); break;
+        default: B2S_PIPE_S(B2S_SPEC_LOG1P_ABS, false); break;
+      }
     }
+#undef B2S_PIPE_S
+#undef B2S_PIPE
+    B2S_LAUNCH_CHECK("stft1024_warp_kernel");
+  } else
+  if (plan->fast && plan->wlen == fft::kSize && aligned16 && plan->shift <= fft::kSize &&
+      rows * frames < (int64_t)1 << 30) {
+    // kernel configuration (NS, CTAS, COMPACT): see stft1024_staged_kernel
+    static const int cfg = [] {
+      const char* e = getenv("B2S_FWD_CFG");
+      int ns = 2, ctas = 2, compact = 0;
+      if (e) sscanf(e, "%d,%d,%d", &ns, &ctas, &compact);
+      return ns * 100 + ctas * 10 + compact;
+    }();
+    static const int ablate = [] { const char* e = getenv("B2S_ABLATE"); return e ? atoi(e) : 0; }();
+    const bool twice = interior_scale == 2.f;
+    const bool experimental = cfg != 220 && layout == B2S_SPEC_ABS && !twice && plan->shift == 256;
+    const int ns = experimental ? cfg / 100 : 2, ctas = experimental ? (cfg / 10) % 10 : 2;
+    const int group = kFwdWarps * ns;
+    const int64_t groups = rows * ceil_div(frames, group);
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * ctas);
+    const int span = (group - 1) * plan->shift + fft::kSize;
+    const size_t smem = sizeof(float) * 2 * span + sizeof(float2) * rf::kTile1 * ns * kFwdWarps;
+    const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
+    B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
+#define B2S_STAGED(L, D, S, NS, C, CP)                                                                  \
+    do {                                                                                                \
+      static bool configured[64] = {};                                                                  \
+      if (!configured[plan->device & 63]) {                                                             \
+        B2S_CUDA(cudaFuncSetAttribute(stft1024_staged_kernel<L, D, S, NS, C, CP>,                       \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));        \
+        configured[plan->device & 63] = true;                                                           \
+      }                                                                                                 \
+      stft1024_staged_kernel<L, D, S, NS, C, CP><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows,       \
+          samples, row_stride, pad_left, frames, plan->shift, table, out, ablate);                      \
+    } while (0)
+#define B2S_STAGED_S(L, D) do { if (plan->shift == 256) B2S_STAGED(L, D, true, 2, 2, false); else B2S_STAGED(L, D, false, 2, 2, false); } while (0)
+    if (experimental) {
+      switch (cfg) {
+        case 231: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 3, true); break;
+        case 221: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 2, true); break;
+        case 230: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 3, false); break;
+        case 141: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 4, true); break;
+        case 131: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 3, true); break;
+        case 130: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 3, false); break;
+        default: B2S_REQUIRE(false, "unknown B2S_FWD_CFG %d", cfg);
+      }
+    } else {
+      switch (layout) {
+        case B2S_SPEC_INTERLEAVED: if (twice) B2S_STAGED_S(B2S_SPEC_INTERLEAVED, true); else B2S_STAGED_S(B2S_SPEC_INTERLEAVED, false); break;
+        case B2S_SPEC_CONCAT: if (twice) B2S_STAGED_S(B2S_SPEC_CONCAT, true); else B2S_STAGED_S(B2S_SPEC_CONCAT, false); break;
+        case B2S_SPEC_ABS: B2S_STAGED_S(B2S_SPEC_ABS, false); break;
+        default: B2S_STAGED_S(B2S_SPEC_LOG1P_ABS, false); break;
+      }
+    }
+#undef B2S_STAGED_S
 #undef B2S_STAGED
     B2S_LAUNCH_CHECK("stft1024_staged_kernel");
   } else if (plan->fast) {
@@ -556,12 +781,28 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
   plan->bins = size / 2 + 1;
   plan->fast = size == fft::kSize;
   plan->awin = nullptr; plan->swin = nullptr; plan->tw = nullptr;
+  plan->lane_fwd = nullptr; plan->lane_adj = nullptr;
   cudaError_t e = cudaMalloc(&plan->awin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->swin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->tw, sizeof(float2) * size);
   if (e == cudaSuccess) e = cudaMemcpy(plan->awin, aw.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->swin, sw.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(plan->tw, tw.data(), sizeof(float2) * size, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && plan->fast) {
+    const size_t bytes = sizeof(float4) * rf::kConstFloat4 * 32;
+    std::vector<float4> fwd(rf::kConstFloat4 * 32), adj(rf::kConstFloat4 * 32);
+    for (int lane = 0; lane < 32; ++lane) {
+      rf::LaneConsts k;
+      k.init(tw.data(), aw.data(), lane, 0.5f);
+      k.pack(fwd.data());
+      k.init(tw.data(), sw.data(), lane, 1.f);
+      k.pack(adj.data());
+    }
+    e = cudaMalloc(&plan->lane_fwd, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&plan->lane_adj, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->lane_fwd, fwd.data(), bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->lane_adj, adj.data(), bytes, cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     set_error("stft plan allocation failed: %s", cudaGetErrorString(e));
     b2s_stft_plan_destroy(plan);
@@ -575,6 +816,7 @@ int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
   if (!plan) return B2S_OK;
   cudaSetDevice(plan->device);
   cudaFree(plan->awin); cudaFree(plan->swin); cudaFree(plan->tw);
+  cudaFree(plan->lane_fwd); cudaFree(plan->lane_adj);
   delete plan;
   return B2S_OK;
 }

@@ -8,4 +8,7 @@ struct b2s_stft_plan {
   float* awin;   // [size] analysis window, zero beyond wlen
   float* swin;   // [size] synthesis window (biorthogonal / size), zero beyond wlen
   float2* tw;    // [size] exp(-2 pi i q / size)
+  // fast plans only: per-lane constant tables of the packed warp FFT (rfft_packed.cuh, [19][32] float4):
+  float4* lane_fwd;   // analysis window, halved        (STFT forward, fused STFT -> PIT)
+  float4* lane_adj;   // synthesis window, not halved    (adjoint of the iSTFT: interior bins doubled)
 };

@@ -29,7 +29,23 @@ int main(int argc, char** argv) {
     }
     if (trial == 1) for (int i = 0; i < 1024; ++i) frame[i] = i == 3 ? 1.f : 0.f;   // impulse
     LaneConsts k[32];
-    for (int l = 0; l < 32; ++l) k[l].init(tab.data(), win, l);
+    alignas(16) static float4 table[kConstFloat4 * 32];
+    for (int l = 0; l < 32; ++l) {
+      LaneConsts full;
+      full.init(tab.data(), win, l);
+      full.pack(table);
+    }
+    for (int l = 0; l < 32; ++l) {
+      if (trial & 1) {
+        k[l].load(table, l);                       // odd trials: through the packed table
+      } else {                                     // even trials: compact constants expanded on the fly
+        CompactConsts c;
+        c.load(table, l);
+        stage_w(c, k[l]);
+        stage_t2(c, k[l]);
+        stage_t3(c, k[l]);
+      }
+    }
     alignas(16) static float2 tile[kTile];
     for (int l = 0; l < 32; ++l) pass1(frame, tile, k[l]);
     for (int l = 0; l < 32; ++l) pass2(tile, k[l]);

@@ -41,13 +41,17 @@ def time_graph(make_fn, n_sets, iters=60):
         graphs.append(g)
     for i in range(2 * n_sets):
         graphs[i % n_sets].replay()
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for i, (e0, e1) in enumerate(pairs):
+    # CUDA event timestamps tick at ~2 us on this platform: time bursts of replays, not single ones
+    burst = 4 * n_sets
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+             for _ in range(max(5, iters // burst))]
+    for e0, e1 in pairs:
         e0.record()
-        graphs[i % n_sets].replay()
+        for i in range(burst):
+            graphs[i % n_sets].replay()
         e1.record()
     torch.cuda.synchronize()
-    return statistics.median(e0.elapsed_time(e1) for e0, e1 in pairs)
+    return statistics.median(e0.elapsed_time(e1) for e0, e1 in pairs) / burst
 
 
 def main():
