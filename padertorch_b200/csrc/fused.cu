@@ -6,13 +6,15 @@
 // Algorithmic HBM bytes per utterance: 4T(1+K) + 4MFK; reading the already
 // materialised |Y| instead of recomputing it trades 4T for 4MF bytes against one FFT per frame.
 //
-// Work decomposition: a "group" is 4 consecutive frames of one example (one frame per warp of a 4-warp
-// CTA).  The groups of the whole batch form one list; CTA c of a persistent grid owns a contiguous range
-// of it, so every SM gets the same number of frames (+-1 group) and a CTA meets at most a few example
-// boundaries, where it flushes its K x K partial sums (fixed-order reduction, ticket per example).
-// The source samples of a group are staged ONCE in shared memory by zero-filling 16-byte cp.async
-// (frames overlap 4x), double buffered against the transform of the previous group; mask and |Y| loads
-// are issued before the first transform and consumed after it.
+// Work decomposition: the frame positions of the whole batch form one list; every warp of a persistent grid
+// is an independent pipeline that owns a contiguous range of it (equal work per warp, at most a few example
+// boundaries per warp).  Per position the warp's elected lane starts TMA bulk copies (cp.async.bulk ->
+// mbarrier): the 1024-sample frames of the K sources (re-started for the next position as soon as pass 1
+// holds the current samples in registers) and the position's mask rows [K][513] and |Y| row (re-started
+// after the SSE).  The K transforms run two at a time (rfft_packed.cuh); their magnitudes never leave the
+// registers.  No block-wide barrier and no per-thread staging code exist in the steady state.
+// At an example boundary the warp flushes its K x K partial sums; the last warp of an example (ticket)
+// folds the partials in slot order and searches the K! permutations (itertools order, first minimum wins).
 #include <algorithm>
 #include <stdlib.h>
 
@@ -24,41 +26,37 @@
 #include "perm.cuh"
 
 using namespace b2s;
+using namespace b2s::tma;
 
 namespace {
 
-constexpr int kFusedWarps = 4;
+constexpr int kFusedWarps = 4;       // warps per CTA
+constexpr int kFusedCtasPerSm = 2;   // <= 255 registers: two interleaved transforms stay in registers
 
 struct FusedGrid {
   int grid;            // persistent CTAs
-  int64_t gpe;         // groups per example (dense enumeration over `frames`)
-  int64_t total;       // batch * gpe
+  int64_t warps;       // pipelines = grid * kFusedWarps
+  int64_t total;       // batch * frames positions (dense enumeration over `frames`)
   int slots;           // partial-sum slots per example
 };
 
-int sources_ctas(int K) {
-  static const int want_ctas = [] { const char* e = getenv("B2S_FUSED_CTAS"); return e ? atoi(e) : 2; }();
-  return (K <= 2 && want_ctas == 3) ? 3 : 2;
-}
-
-FusedGrid fused_grid(int64_t batch, int64_t frames, int ctas_per_sm) {
+FusedGrid fused_grid(int64_t batch, int64_t frames) {
   FusedGrid g;
-  g.gpe = std::max<int64_t>(1, ceil_div(frames, kFusedWarps));
-  g.total = batch * g.gpe;
-  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(g.total, (int64_t)kNumSMs * ctas_per_sm));
-  g.slots = (int)(ceil_div(g.gpe * g.grid, std::max<int64_t>(1, g.total)) + 2);
+  g.total = batch * std::max<int64_t>(1, frames);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, kFusedWarps),
+                                                       (int64_t)kNumSMs * kFusedCtasPerSm));
+  g.warps = std::min<int64_t>((int64_t)g.grid * kFusedWarps, g.total);   // surplus warps of the last CTA idle
+  g.slots = (int)(ceil_div(std::max<int64_t>(1, frames) * g.warps, g.total) + 2);
   return g;
 }
 
-// first group of CTA c: floor(c * total / grid); CTA owning group x: ceil((x + 1) * grid / total) - 1
-__device__ __forceinline__ int64_t range_start(int64_t c, int64_t total, int64_t grid) {
-  return c * total / grid;
+// first position of warp w: floor(w * total / warps); warp owning position x: ceil((x + 1) * warps / total) - 1
+__device__ __forceinline__ int64_t range_start(int64_t w, int64_t total, int64_t warps) {
+  return w * total / warps;
 }
-__device__ __forceinline__ int64_t owner_of(int64_t x, int64_t total, int64_t grid) {
-  return ((x + 1) * grid + total - 1) / total - 1;
+__device__ __forceinline__ int64_t owner_of(int64_t x, int64_t total, int64_t warps) {
+  return ((x + 1) * warps + total - 1) / total - 1;
 }
-
-using namespace b2s::tma;
 
 // floats of a warp's mask / |Y| landing area: [mask rows K * F + 8 | |Y| row F + 8], both 16-byte aligned
 __host__ __device__ constexpr int mask_area_floats(int K) { return ((K * 513 + 8 + 3) / 4) * 4; }
@@ -70,80 +68,121 @@ __device__ __forceinline__ float2 mag2(float2 ya, float2 yb) {
                      fft::sqrt_approx(fmaf(yb.x, yb.x, yb.y * yb.y)));
 }
 
-// One frame position = (K [+1]) transforms (rfft_packed.cuh) whose magnitudes stay in registers as packed
-// (A side, B side) pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in
-// lane 0 only); mask and |Y| values are read straight from global memory at their point of use (the rows
-// were prefetched into L2 one group earlier), each exactly once.
-template <int K, bool VEC16, bool RECOMPUTE_Y, int CTAS>
-__global__ void __launch_bounds__(32 * kFusedWarps, CTAS)
+// All K! (K <= 4: at most 24) assignments evaluated by the lanes of ONE warp; lane 0 receives the winner.
+__device__ __forceinline__ void warp_search_permutations(const double* cost, int K, int lane, double& best_value,
+                                                         int* best_perm) {
+  const int total = factorial(K);
+  double val = 0.0;
+  int idx = 0x7fffffff;
+  if (lane < total) {
+    int p[B2S_MAX_SOURCES];
+    unrank_permutation(lane, K, p);
+    for (int k = 0; k < K; ++k) val += cost[p[k] * K + k];
+    idx = lane;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oi != 0x7fffffff && (idx == 0x7fffffff || candidate_better(ov, oi, val, idx))) { val = ov; idx = oi; }
+  }
+  best_value = val;
+  if (lane == 0) unrank_permutation(idx, K, best_perm);
+}
+
+// One frame position = (K [+1]) transforms whose magnitudes stay in registers as packed (A side, B side)
+// pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in lane 0 only).
+template <int K, bool RECOMPUTE_Y>
+__global__ void __launch_bounds__(32 * kFusedWarps, kFusedCtasPerSm)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
                       const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames,
-                      int shift, int64_t pad_left, const float4* __restrict__ lane_table, int64_t gpe, int slots,
+                      int shift, int64_t pad_left, const float4* __restrict__ lane_table, int slots,
                       double* __restrict__ partial, int* __restrict__ counters, float* __restrict__ loss,
                       int32_t* __restrict__ perm, double* __restrict__ sse) {
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
-  extern __shared__ __align__(16) float smem[];   // [2][rows][span] signal rows (rows = K, +1 when |Y| is
-                                                  // recomputed), then the warps' exchange tiles
-  __shared__ double sm[NV * kFusedWarps + NV];
-  __shared__ int s_last;
+  constexpr int NT = RECOMPUTE_Y ? K + 1 : K;   // transforms per position; with RECOMPUTE_Y the mixture is first
+  constexpr int kWarpFloats = NT * rf::kSize + 4 * rf::kTile1 + row_area_floats(K);
+  extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, 2 exchange tiles, mask / |Y| rows
+  __shared__ __align__(8) uint64_t bars[kFusedWarps][2];
+  __shared__ double totals_sm[kFusedWarps][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int span = (kFusedWarps - 1) * shift + rf::kSize;
-  constexpr int nrows = RECOMPUTE_Y ? K + 1 : K;   // staged signal rows per group
-  const int buf_floats = nrows * span;
-  float2* tile = reinterpret_cast<float2*>(smem + 2 * buf_floats) + warp * (2 * rf::kTile1);
-  // per warp: the mask rows [K][F] (+ |Y| row) of its current frame, copied by TMA while the transforms run
-  float* rows_area = smem + 2 * buf_floats + kFusedWarps * 4 * rf::kTile1 + warp * row_area_floats(K);
-  __shared__ __align__(8) uint64_t bars[kFusedWarps];
-  uint64_t* bar = &bars[warp];
-  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  float* sig = smem + warp * kWarpFloats;                          // frame of transform t at sig + t * 1024
+  float2* tile = reinterpret_cast<float2*>(sig + NT * rf::kSize);
+  float* rows_area = sig + NT * rf::kSize + 4 * rf::kTile1;
+  uint64_t* bar_sig = &bars[warp][0];
+  uint64_t* bar_rows = &bars[warp][1];
+  if (lane == 0) {
+    mbar_init(bar_sig, 1);
+    mbar_init(bar_rows, 1);
+    fence_mbar_init();
+  }
   __syncwarp();
-  unsigned bar_phase = 0;       // parity of the copy the warp waits for next
-  int off_m = 0, off_y = 0;     // float offset of the row inside its landing area (source misalignment / 4)
-  bool copy_pending = false;
   rf::LaneConsts k;
   k.load(lane_table, lane);
   // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
   const int k0 = rf::bin_a(lane, 0), k4 = rf::bin_a(lane, 4) - 256;
   const bool first = lane == 0;
 
-  const int64_t total = batch * gpe;
-  const int64_t g_begin = range_start(blockIdx.x, total, gridDim.x);
-  const int64_t g_end = range_start(blockIdx.x + 1, total, gridDim.x);
+  const int64_t total = batch * frames;
+  const int64_t nwarps = min((int64_t)gridDim.x * kFusedWarps, total);   // every pipeline owns >= 1 position
+  const int64_t gw = (int64_t)blockIdx.x * kFusedWarps + warp;
+  if (gw >= nwarps) return;
+  const int64_t p_begin = range_start(gw, total, nwarps), p_end = range_start(gw + 1, total, nwarps);
 
-  // stage the signal rows of group g into buffer `which`
-  auto stage_rows = [&](int64_t g, int which) {
-    const int64_t b = g / gpe, m0 = (g - b * gpe) * kFusedWarps;
+  unsigned sig_phase = 0, rows_phase = 0;
+  bool sig_by_tma = false;
+  int off_m = 0, off_y = 0;     // float offset of a row inside its landing area (source misalignment / 4)
+
+  auto frames_of = [&](int64_t b) { return meta ? meta[2 * b + 1] : frames; };
+  // row t of a position: t < K source t, t == K the mixture; order of the transforms: (mixture,) sources
+  auto signal_row = [&](int64_t b, int t) -> const float* {
+    const int r = RECOMPUTE_Y ? (t == 0 ? K : t - 1) : t;
+    return r < K ? sources + (b * K + r) * samples : mixture + b * samples;
+  };
+  // start the copy of the NT frames of position q (or note that the warp must fill them itself: zero padding
+  // at the signal's ends, rows that are not 16-byte aligned)
+  auto start_signals = [&](int64_t q) {
+    if (q >= p_end) return;
+    const int64_t b = q / frames, m = q - b * frames;
+    if (m >= frames_of(b)) { sig_by_tma = false; return; }
     const int64_t Tb = meta ? meta[2 * b] : samples;
-    const int64_t s0 = m0 * shift - pad_left;
-    float* buf = smem + which * buf_floats;
-    const bool interior = VEC16 && s0 >= 0 && s0 + span <= Tb;
-    for (int j = 0; j < nrows; ++j) {
-      const float* xr = (j < K) ? sources + (b * K + j) * samples : mixture + b * samples;
-      if (interior) {
-        for (int c = threadIdx.x; c < (span >> 2); c += blockDim.x)
-          fft::cp_async_16(buf + j * span + 4 * c, xr + s0 + 4 * c, 16);
-      } else if (VEC16) {
-        fft::stage_group(buf + j * span, xr, s0, span, Tb);
-      } else {
-        for (int c = threadIdx.x; c < span; c += blockDim.x) {   // unaligned rows: plain loads
-          const int64_t i = s0 + c;
-          buf[j * span + c] = (i >= 0 && i < Tb) ? __ldg(xr + i) : 0.f;
+    const int64_t s0 = m * shift - pad_left;
+    bool bulk = s0 >= 0 && s0 + rf::kSize <= Tb;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) bulk = bulk && (reinterpret_cast<uintptr_t>(signal_row(b, t) + s0) & 15) == 0;
+    sig_by_tma = bulk;
+    if (bulk) {
+      if (lane == 0) {
+        fence_proxy_async();   // the frames were last read through the generic proxy
+        mbar_expect_tx(bar_sig, NT * rf::kSize * 4u);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, signal_row(b, t) + s0, rf::kSize * 4u, bar_sig);
+      }
+    } else {
+      // frames that touch the zero padding or are not 16-byte aligned: 4-byte cp.async with zero fill, just as
+      // asynchronous as the bulk copy (waited for with cp.async.wait_group before pass 1)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const float* xr = signal_row(b, t);
+        for (int i = lane; i < rf::kSize; i += 32) {
+          const int64_t n = s0 + i;
+          const bool ok = n >= 0 && n < Tb;
+          fft::cp_async_4_zfill(sig + t * rf::kSize + i, ok ? xr + n : xr, ok ? 4 : 0);
         }
       }
+      fft::cp_async_commit();
     }
   };
-  // Start the copy of the mask rows [K][F] (contiguous) and the |Y| row of this warp's frame of group g.  A bulk
-  // copy needs 16-byte aligned addresses and sizes while rows start at multiples of 4 bytes: the enclosing
-  // aligned range is copied and the row found at the source's misalignment inside the landing area.  The at
-  // most 12 bytes before / after a row belong to the neighbouring rows or, at the very ends of the tensor, to
-  // the same (>= 256-byte granular) allocation -- an address that is not 16-byte aligned is never at its edge.
-  auto start_copy = [&](int64_t g) {
-    const int64_t b = g / gpe, m = (g - b * gpe) * kFusedWarps + warp;
-    const int64_t Mb = meta ? meta[2 * b + 1] : frames;
-    copy_pending = m < Mb;
-    if (!copy_pending) return;
+  // Start the copy of the mask rows [K][F] (contiguous) and the |Y| row of position q.  A bulk copy needs
+  // 16-byte aligned addresses and sizes while rows start at multiples of 4 bytes: the enclosing aligned range is
+  // copied and the row found at the source's misalignment inside the landing area.  The at most 12 bytes before
+  // / after a row belong to the neighbouring rows or, at the very ends of the tensor, to the same (>= 256-byte
+  // granular) allocation -- an address that is not 16-byte aligned is never at its edge.
+  auto start_rows = [&](int64_t q) {
+    if (q >= p_end) return;
+    const int64_t b = q / frames, m = q - b * frames;
+    if (m >= frames_of(b)) return;
     const uintptr_t am = reinterpret_cast<uintptr_t>(mask + ((b * frames + m) * K) * F);
     const uintptr_t ay = RECOMPUTE_Y ? 0 : reinterpret_cast<uintptr_t>(yabs + (b * frames + m) * F);
     off_m = (int)(am & 15) >> 2;
@@ -151,11 +190,11 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (lane == 0) {
       const unsigned bytes_m = (unsigned)(((am & 15) + K * F * 4 + 15) & ~15u);
       const unsigned bytes_y = RECOMPUTE_Y ? 0u : (unsigned)(((ay & 15) + F * 4 + 15) & ~15u);
-      fence_proxy_async();   // the area's previous contents were read through the generic proxy
-      mbar_expect_tx(bar, bytes_m + bytes_y);
-      bulk_g2s(rows_area, reinterpret_cast<const void*>(am & ~(uintptr_t)15), bytes_m, bar);
+      fence_proxy_async();
+      mbar_expect_tx(bar_rows, bytes_m + bytes_y);
+      bulk_g2s(rows_area, reinterpret_cast<const void*>(am & ~(uintptr_t)15), bytes_m, bar_rows);
       if (!RECOMPUTE_Y)
-        bulk_g2s(rows_area + mask_area_floats(K), reinterpret_cast<const void*>(ay & ~(uintptr_t)15), bytes_y, bar);
+        bulk_g2s(rows_area + mask_area_floats(K), reinterpret_cast<const void*>(ay & ~(uintptr_t)15), bytes_y, bar_rows);
     }
   };
 
@@ -163,136 +202,125 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float2(0.f, 0.f);
 
-  // flush the CTA's partial sums of example b (all threads call it)
+  // flush the warp's partial sums of example b (whole warp)
   auto flush = [&](int64_t b) {
+    double mine[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float s = warp_sum(acc[i].x + acc[i].y);
-      if (lane == 0) sm[i * kFusedWarps + warp] = (double)s;
+      mine[i] = (double)warp_sum(acc[i].x + acc[i].y);
       acc[i] = make_float2(0.f, 0.f);
     }
-    __syncthreads();
-    const int64_t first_owner = owner_of(b * gpe, total, gridDim.x);
-    const int64_t last_owner = owner_of((b + 1) * gpe - 1, total, gridDim.x);
-    const int slot = (int)(blockIdx.x - first_owner), nparts = (int)(last_owner - first_owner + 1);
-    double* mine = partial + (b * slots + slot) * NV;
-    if (threadIdx.x < NV) {
-      double s = 0.0;
-      for (int w = 0; w < kFusedWarps; ++w) s += sm[threadIdx.x * kFusedWarps + w];
-      mine[threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == nparts - 1;
-    __syncthreads();
-    if (s_last) {   // block-uniform
+    const int64_t first_owner = owner_of(b * frames, total, nwarps);
+    const int64_t last_owner = owner_of((b + 1) * frames - 1, total, nwarps);
+    const int slot = (int)(gw - first_owner), nparts = (int)(last_owner - first_owner + 1);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) partial[(b * slots + slot) * NV + i] = mine[i];
       __threadfence();
-      double* totals = sm + NV * kFusedWarps;
-      if (threadIdx.x < NV) {
+    }
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(counters + b, 1) == nparts - 1;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {   // warp-uniform
+      __threadfence();
+      double* totals = totals_sm[warp];
+      if (lane < NV) {
         double s = 0.0;
-        const volatile double* p = partial + b * slots * NV + threadIdx.x;
+        const volatile double* p = partial + b * slots * NV + lane;
         for (int c = 0; c < nparts; ++c) s += p[(int64_t)c * NV];
-        totals[threadIdx.x] = s;
-        sse[b * NV + threadIdx.x] = s;
+        totals[lane] = s;
+        sse[b * NV + lane] = s;
       }
-      __syncthreads();
+      __syncwarp();
       double best;
       int bp[B2S_MAX_SOURCES];
-      search_permutations(totals, K, best, bp);
-      if (threadIdx.x == 0) {
-        const int64_t Mb = meta ? meta[2 * b + 1] : frames;
-        loss[b] = (float)(best / ((double)Mb * (double)K * (double)F));
+      warp_search_permutations(totals, K, lane, best, bp);
+      if (lane == 0) {
+        loss[b] = (float)(best / ((double)frames_of(b) * (double)K * (double)F));
         for (int kk = 0; kk < K; ++kk) perm[b * K + kk] = bp[kk];
         counters[b] = 0;
       }
+      __syncwarp();
     }
-    __syncthreads();
   };
 
-  if (g_begin < g_end) {
-    stage_rows(g_begin, 0);
-    start_copy(g_begin);
-  }
-  fft::cp_async_commit();
-  int cur = 0;
-  int64_t b_cur = g_begin < g_end ? g_begin / gpe : -1;
-  for (int64_t g = g_begin; g < g_end; ++g, cur ^= 1) {
-    const int64_t b = g / gpe, m0 = (g - b * gpe) * kFusedWarps;
-    if (b != b_cur) {   // CTA-uniform
+  start_signals(p_begin);
+  start_rows(p_begin);
+  int64_t b_cur = p_begin < p_end ? p_begin / frames : -1;
+  for (int64_t q = p_begin; q < p_end; ++q) {
+    const int64_t b = q / frames, m = q - b * frames;
+    if (b != b_cur) {   // warp-uniform
       flush(b_cur);
       b_cur = b;
     }
-    fft::cp_async_wait_all();
-    __syncthreads();   // group g staged and visible; the other buffer is free
-    if (g + 1 < g_end) {
-      stage_rows(g + 1, cur ^ 1);
+    if (m >= frames_of(b)) {   // position beyond this example's length (ragged batch): nothing to do
+      start_signals(q + 1);
+      start_rows(q + 1);
+      continue;
     }
-    fft::cp_async_commit();
-
-    const int64_t Mb = meta ? meta[2 * b + 1] : frames;
-    const int64_t m = m0 + warp;
-    if (m < Mb) {
-      const float* gbuf = smem + cur * buf_floats + warp * shift;
-      // transforms run two at a time (rfft_streams: the sources of a frame position are independent streams);
-      // magnitudes stay in registers as (A side, B side) pairs; slot 8 = (|DC|, |Nyquist|), zero outside lane 0;
-      // lane 0's slot 7 holds bin 256 on both sides: its B copy is zeroed (and so is the matching mask load)
-      auto magnitudes = [&](const float2 (&ya)[8], const float2 (&yb)[8], float ydc, float ynyq, float2 (&x)[9]) {
+    if (sig_by_tma) {
+      mbar_wait(bar_sig, sig_phase);
+      sig_phase ^= 1;
+    } else {
+      fft::cp_async_wait_all();
+      __syncwarp();
+    }
+    // magnitudes as (A side, B side) pairs; slot 8 = (|DC|, |Nyquist|), zero outside lane 0; lane 0's slot 7
+    // holds bin 256 on both sides: its B copy is zeroed (and so is the matching mask load)
+    auto magnitudes = [&](const float2 (&ya)[8], const float2 (&yb)[8], float ydc, float ynyq, float2 (&x)[9]) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) x[p] = mag2(ya[p], yb[p]);
-        if (first) x[7].y = 0.f;
-        x[8] = first ? make_float2(fabsf(ydc), fabsf(ynyq)) : make_float2(0.f, 0.f);
-      };
-      // signal row r of the staged group: r < K sources, r == K the mixture; row order of the transforms:
-      // (mixture,) source 0, source 1, ...
-      constexpr int NT = RECOMPUTE_Y ? K + 1 : K;
-      float2 x[NT][9];   // with RECOMPUTE_Y x[0] = |Y|, sources follow
-      auto row_of = [&](int t) { return RECOMPUTE_Y ? (t == 0 ? K : t - 1) : t; };
+      for (int p = 0; p < 8; ++p) x[p] = mag2(ya[p], yb[p]);
+      if (first) x[7].y = 0.f;
+      x[8] = first ? make_float2(fabsf(ydc), fabsf(ynyq)) : make_float2(0.f, 0.f);
+    };
+    float2 x[NT][9];   // with RECOMPUTE_Y x[0] = |Y|, sources follow
 #pragma unroll(K <= 2 ? 2 : 1)
-      for (int t = 0; t + 1 < NT; t += 2) {
-        float2 ya[2][8], yb[2][8];
-        float ydc[2], ynyq[2];
-        const int r0 = row_of(t), r1 = row_of(t + 1);
-        rf::rfft_streams<2, false, false>(gbuf + r0 * span, (r1 - r0) * span, tile, k, ya, yb, ydc, ynyq);
-        magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
-        magnitudes(ya[1], yb[1], ydc[1], ynyq[1], x[t + 1]);
-      }
-      if (NT & 1) {
-        float2 ya[1][8], yb[1][8];
-        float ydc[1], ynyq[1];
-        rf::rfft_streams<1, false, false>(gbuf + row_of(NT - 1) * span, 0, tile, k, ya, yb, ydc, ynyq);
-        magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[NT - 1]);
-      }
-      constexpr int XS = RECOMPUTE_Y ? 1 : 0;   // x[XS + j] = |STFT(s_j)|
+    for (int t = 0; t + 1 < NT; t += 2) {
+      float2 ya[2][8], yb[2][8];
+      float ydc[2], ynyq[2];
+      // the frames of the LAST transforms are in registers after pass 1: start the next position's copy
+      auto next_copy = [&]() { if (t + 2 >= NT) start_signals(q + 1); };
+      rf::rfft_streams<2, false, false>(sig + t * rf::kSize, rf::kSize, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
+      magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
+      magnitudes(ya[1], yb[1], ydc[1], ynyq[1], x[t + 1]);
+    }
+    if (NT & 1) {
+      float2 ya[1][8], yb[1][8];
+      float ydc[1], ynyq[1];
+      auto next_copy = [&]() { start_signals(q + 1); };
+      rf::rfft_streams<1, false, false>(sig + (NT - 1) * rf::kSize, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
+      magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[NT - 1]);
+    }
+    constexpr int XS = RECOMPUTE_Y ? 1 : 0;   // x[XS + j] = |STFT(s_j)|
 
-      // ---- SSE of this frame: e_i = mask_i * |Y| against every source magnitude
-      mbar_wait(bar, bar_phase);   // the rows of this frame have landed
-      bar_phase ^= 1;
-      const float* mrow = rows_area + off_m;
-      const float* yrow = rows_area + mask_area_floats(K) + off_y;
+    // ---- SSE of this frame: e_i = mask_i * |Y| against every source magnitude
+    mbar_wait(bar_rows, rows_phase);   // the rows of this frame have landed
+    rows_phase ^= 1;
+    const float* mrow = rows_area + off_m;
+    const float* yrow = rows_area + mask_area_floats(K) + off_y;
 #pragma unroll
-      for (int p = 0; p < 9; ++p) {
-        const int ka = p < 8 ? (p < 4 ? k0 : k4) + 64 * p : 0;
-        const int kb = rf::kHalf - ka;
-        const bool live_a = p < 8 || first, live_b = p < 7 || (p == 7 ? !first : first);
-        float2 ov;
-        if (!RECOMPUTE_Y) ov = make_float2(live_a ? yrow[ka] : 0.f, live_b ? yrow[kb] : 0.f);
-        else ov = x[0][p];
+    for (int p = 0; p < 9; ++p) {
+      const int ka = p < 8 ? (p < 4 ? k0 : k4) + 64 * p : 0;
+      const int kb = rf::kHalf - ka;
+      const bool live_a = p < 8 || first, live_b = p < 7 || (p == 7 ? !first : first);
+      float2 ov;
+      if (!RECOMPUTE_Y) ov = make_float2(live_a ? yrow[ka] : 0.f, live_b ? yrow[kb] : 0.f);
+      else ov = x[0][p];
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          const float2 mv = make_float2(live_a ? mrow[i * F + ka] : 0.f, live_b ? mrow[i * F + kb] : 0.f);
-          const float2 e = rf::mul2(mv, ov);
+      for (int i = 0; i < K; ++i) {
+        const float2 mv = make_float2(live_a ? mrow[i * F + ka] : 0.f, live_b ? mrow[i * F + kb] : 0.f);
+        const float2 e = rf::mul2(mv, ov);
 #pragma unroll
-          for (int j = 0; j < K; ++j) {
-            const float2 d = rf::sub2(e, x[XS + j][p]);
-            acc[i * K + j] = rf::fma2(d, d, acc[i * K + j]);
-          }
+        for (int j = 0; j < K; ++j) {
+          const float2 d = rf::sub2(e, x[XS + j][p]);
+          acc[i * K + j] = rf::fma2(d, d, acc[i * K + j]);
         }
       }
-      __syncwarp();   // every lane has read its rows: the area may be overwritten
     }
-    if (g + 1 < g_end) start_copy(g + 1);
+    __syncwarp();   // every lane has read its rows: the area may be overwritten
+    start_rows(q + 1);
   }
-  fft::cp_async_wait_all();
   if (b_cur >= 0) flush(b_cur);
 }
 
@@ -301,37 +329,25 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
                  int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
                  cudaStream_t stream) {
-  const FusedGrid g = fused_grid(batch, frames, sources_ctas(K));
+  const FusedGrid g = fused_grid(batch, frames);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool vec = al16(sources) && (mixture == nullptr || al16(mixture)) && samples % 4 == 0 &&
-                   plan->shift % 4 == 0 && pad_left % 4 == 0;
-  // the transform reads its frame with 16-byte shared-memory loads: frames must start 16-byte aligned
+  // the transform reads its frame with 16-byte shared-memory loads and TMA copies 16-byte units
   B2S_REQUIRE(plan->shift % 4 == 0, "the fused STFT->PIT kernel needs a shift that is a multiple of 4 (got %d)",
               plan->shift);
-  const int span = (kFusedWarps - 1) * plan->shift + rf::kSize;
-  const int nrows = yabs ? K : K + 1;
-  const size_t smem = sizeof(float) * 2 * nrows * span + sizeof(float2) * 2 * rf::kTile1 * kFusedWarps +
-                      sizeof(float) * row_area_floats(K) * kFusedWarps;
-  // resident CTAs per SM: 2 (<= 255 registers: the two interleaved transforms keep all their values in
-  // registers); B2S_FUSED_CTAS=3 selects the 168-register build for experiments (shared memory must allow it)
-  const bool three = sources_ctas(K) == 3;
-  constexpr int C3 = K <= 2 ? 3 : 2;   // K >= 3 keeps more magnitudes live: always 2
-  auto kernel = three
-      ? (yabs ? (vec ? stft_pit_fused_kernel<K, true, false, C3> : stft_pit_fused_kernel<K, false, false, C3>)
-              : (vec ? stft_pit_fused_kernel<K, true, true, C3> : stft_pit_fused_kernel<K, false, true, C3>))
-      : (yabs ? (vec ? stft_pit_fused_kernel<K, true, false, 2> : stft_pit_fused_kernel<K, false, false, 2>)
-              : (vec ? stft_pit_fused_kernel<K, true, true, 2> : stft_pit_fused_kernel<K, false, true, 2>));
-  B2S_REQUIRE(smem <= 200 * 1024, "shift %d needs %zu bytes of staging: too large", plan->shift, smem);
-  static bool configured[8][64] = {};   // per (variant, device)
-  const int variant = (vec ? 1 : 0) + (yabs ? 0 : 2) + (three ? 4 : 0);
+  B2S_REQUIRE(frames >= 1, "the fused STFT->PIT kernel needs at least one frame");
+  const int nt = yabs ? K : K + 1;
+  const size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 4 * rf::kTile1 + row_area_floats(K));
+  auto kernel = yabs ? stft_pit_fused_kernel<K, false> : stft_pit_fused_kernel<K, true>;
+  B2S_REQUIRE(smem <= 220 * 1024, "internal: %zu bytes of shared memory", smem);
+  static bool configured[2][64] = {};   // per (variant, device)
+  const int variant = yabs ? 0 : 1;
   if (!configured[variant][plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured[variant][plan->device & 63] = true;
   }
-  kernel<<<g.grid, 32 * kFusedWarps, smem, stream>>>(mixture, yabs, sources, mask, meta, batch, samples,
-      frames, plan->shift, pad_left, plan->lane_fwd, g.gpe, g.slots, partial, counters, loss, perm, sse);
+  kernel<<<g.grid, 32 * kFusedWarps, smem, stream>>>(mixture, yabs, sources, mask, meta, batch, samples, frames,
+      plan->shift, pad_left, plan->lane_fwd, g.slots, partial, counters, loss, perm, sse);
   B2S_LAUNCH_CHECK("stft_pit_fused_kernel");
   return B2S_OK;
 }
@@ -342,7 +358,7 @@ extern "C" {
 
 int64_t b2s_stft_pit_workspace_bytes(int64_t batch, int64_t frames, int sources) {
   if (batch <= 0 || sources <= 0) return kTicketBytes + 16;
-  const FusedGrid g = fused_grid(batch, frames, sources_ctas(sources));
+  const FusedGrid g = fused_grid(batch, frames);
   return kTicketBytes + (int64_t)sizeof(double) * batch * g.slots * sources * sources + 16;
 }
 

@@ -63,10 +63,6 @@ __device__ __forceinline__ void store_bin_t(float* __restrict__ out, int k, floa
 }
 
 constexpr int kFwdWarps = 4;
-#ifndef B2S_FWD_CTAS_PER_SM
-#define B2S_FWD_CTAS_PER_SM 3
-#endif
-constexpr int kFwdCtasPerSm = B2S_FWD_CTAS_PER_SM;
 
 // One warp per frame, persistent over frames.  `win` is the (zero-extended) window the samples are
 // multiplied with: the analysis window for STFT, the synthesis window for the adjoint of iSTFT, in
@@ -120,97 +116,6 @@ stft1024_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t sampl
   }
 }
 
-// ------------------------------------------------------------------------------------------- staged forward
-// The packed-fp32x2 transform of rfft_packed.cuh behind a staged feed: a CTA of 4 warps takes 4 consecutive
-// frames of one signal row per iteration.  The 3*shift + 1024 samples they cover are brought into shared
-// memory ONCE (frames overlap 4x at shift 256) by 16-byte cp.async -- with zero fill outside the signal for
-// the groups that touch the fading / tail pads, which therefore never exist in memory -- double buffered so
-// the copy of group i+1 is in flight while group i is transformed.  Needs 16-byte aligned rows.
-// DOUBLE_INTERIOR (adjoint of the iSTFT): interior bins times two, done by not halving the window.
-__device__ __forceinline__ void stage_interior(float* buf, const float* __restrict__ src, int span) {
-  for (int c = threadIdx.x; c < (span >> 2); c += blockDim.x) fft::cp_async_16(buf + 4 * c, src + 4 * c, 16);
-}
-
-// NS = frames per warp and iteration (rfft_streams), CTAS = resident CTAs per SM the registers are budgeted
-// for, COMPACT = 48-register constants (rfft_packed.cuh).  Default (2, 2, false); the others are selectable
-// with B2S_FWD_CFG=NS,CTAS,COMPACT for the |Y| layout at shift 256 (kernel tuning experiments).
-template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int kFwdStreams, int CTAS, bool COMPACT>
-__global__ void __launch_bounds__(32 * kFwdWarps, CTAS)
-stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
-                       int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
-                       float* __restrict__ out, int ablate) {
-  extern __shared__ __align__(16) float smem[];   // [2][span] staged samples, then the warps' exchange tiles
-  constexpr int kFwdGroup = kFwdWarps * kFwdStreams;          // frames per CTA and iteration
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int span = (kFwdGroup - 1) * shift + rf::kSize;
-  float2* tile = reinterpret_cast<float2*>(smem + 2 * span) + warp * (kFwdStreams * rf::kTile1);
-  typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
-  k.load(lane_table, lane);
-  constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
-  constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
-  // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
-  const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
-  const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
-  // group indices fit 32 bits (checked by the launcher)
-  const unsigned groups_per_row = (unsigned)ceil_div(frames, kFwdGroup);
-  const unsigned total_groups = (unsigned)rows * groups_per_row;
-  const unsigned step_row = gridDim.x / groups_per_row, step_grp = gridDim.x - step_row * groups_per_row;
-
-  auto stage = [&](float* buf, unsigned row, unsigned grp) {
-    const int64_t s0 = (int64_t)grp * kFwdGroup * shift - pad_left;
-    const float* xr = x + (int64_t)row * row_stride;
-    if (s0 >= 0 && s0 + span <= samples) stage_interior(buf, xr + s0, span);
-    else fft::stage_group(buf, xr, s0, span, samples);
-  };
-
-  unsigned g = blockIdx.x;
-  unsigned row = g / groups_per_row, grp = g - row * groups_per_row;
-  if (g < total_groups) stage(smem, row, grp);
-  fft::cp_async_commit();
-  int cur = 0;
-  for (; g < total_groups; g += gridDim.x, cur ^= 1) {
-    fft::cp_async_wait_all();
-    __syncthreads();   // group g is visible to every warp; everyone is done with the other buffer
-    unsigned rown = row + step_row, grpn = grp + step_grp;
-    if (grpn >= groups_per_row) { grpn -= groups_per_row; ++rown; }
-    if (g + gridDim.x < total_groups) stage(smem + (cur ^ 1) * span, rown, grpn);
-    fft::cp_async_commit();
-    const unsigned m0 = grp * kFwdGroup + warp * kFwdStreams;
-    if (m0 < frames) {
-      float2 ya[kFwdStreams][8], yb[kFwdStreams][8];
-      float ydc[kFwdStreams], ynyq[kFwdStreams];
-      rf::rfft_streams<kFwdStreams, SHIFT256 && (kFwdStreams > 1), DOUBLE_INTERIOR>(
-          smem + cur * span + warp * kFwdStreams * shift, shift, tile, k, ya, yb, ydc, ynyq, ablate);
-      if (ablate & 1) {   // experiments: no global stores (one dependent dummy store keeps the work alive)
-        float acc = 0.f;
-#pragma unroll
-        for (int s = 0; s < kFwdStreams; ++s)
-#pragma unroll
-          for (int p = 0; p < 8; ++p) acc += ya[s][p].x + ya[s][p].y + yb[s][p].x + yb[s][p].y;
-        if (acc == 1.2345f) out[0] = acc;
-      } else {
-#pragma unroll
-      for (int s = 0; s < kFwdStreams; ++s) {
-        if (m0 + s < frames) {
-          float* o = out + ((int64_t)row * frames + m0 + s) * kOutPerFrame;
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[s][p]);
-            store_bin_t<LAYOUT>(o + (p < 4 ? offb0 : offb4) - kS * 64 * p, 0, rf::conj(yb[s][p]));
-          }
-          if (lane == 0) {
-            store_bin_t<LAYOUT>(o, 0, make_float2(ydc[s], 0.f));
-            store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq[s], 0.f));
-          }
-        }
-      }
-      }
-    }
-    row = rown; grp = grpn;
-  }
-  fft::cp_async_wait_all();
-}
-
 // ------------------------------------------------------------------------------------------- warp pipelines
 // The default fast forward path.  Every warp is an independent pipeline: it owns units of two consecutive
 // frames of one row, a TMA bulk copy (one instruction of one lane) brings the unit's shift + 1024 samples into
@@ -220,11 +125,17 @@ stft1024_staged_kernel(const float* __restrict__ x, int64_t rows, int64_t sample
 // marching through the same phase together (the block-synchronous staged kernel above measures T = T_copy +
 // T_fft + T_store on B200, tools/ubench and B2S_ABLATE).  Units that touch the zero padding (fading, tail) or
 // are not 16-byte aligned are filled by the warp itself.
-constexpr int kPipeWarps = 4;
+constexpr int kPipeWarps = 4;      // warps per CTA
+constexpr int kPipeCtasPerSm = 2;  // <= 255 registers: two interleaved transforms stay in registers
+constexpr int kPipeFrames = 2;     // NS: frames per unit
+constexpr int kPipeStages = 2;     // ring slots per warp
 
-// NS frames per unit, CTAS resident CTAs per SM the registers are budgeted for, COMPACT 48-register constants,
-// STAGES ring slots per warp (1: the next copy starts as soon as pass 1 holds the current samples in registers).
-template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int NS, int CTAS, bool COMPACT, int STAGES>
+// Measured alternatives on B200 (same 22.8 us at the north-star shape for all of them, the kernel is bound by
+// shared-memory wavefronts + FP32 pipe cycles per frame): 3 CTAs/SM with 48-register
+// compact constants (rf::CompactConsts), one frame per unit at 4 CTAs/SM, a single ring slot refilled from
+// rfft_streams' input_consumed hook.
+template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm,
+          bool COMPACT = false, int STAGES = kPipeStages>
 __global__ void __launch_bounds__(32 * kPipeWarps, CTAS)
 stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                      int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
@@ -260,17 +171,30 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
 
   // start filling `slot` with unit u (or remember that the warp has to fill it itself)
   auto issue = [&](int64_t u, int slot) {
-    if (u >= total) return;
+    if (u < total) {
     const int64_t row = u / units_per_row, m0 = (u - row * units_per_row) * NS;
     const int64_t s0 = m0 * shift - pad_left;
     const float* src = x + row * row_stride + s0;
     const bool bulk = s0 >= 0 && s0 + span <= samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     by_tma = bulk ? (by_tma | (1u << slot)) : (by_tma & ~(1u << slot));
-    if (bulk && lane == 0) {
-      tma::fence_proxy_async();   // the slot was last read through the generic proxy
-      tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
-      tma::bulk_g2s(ring + slot * span, src, (unsigned)span * 4u, bar + slot);
+    if (bulk) {
+      if (lane == 0) {
+        tma::fence_proxy_async();   // the slot was last read through the generic proxy
+        tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
+        tma::bulk_g2s(ring + slot * span, src, (unsigned)span * 4u, bar + slot);
+      }
+    } else {
+      // units that touch the zero padding or are not 16-byte aligned: 4-byte cp.async with zero fill, just as
+      // asynchronous as the bulk copy (waited for with cp.async.wait_group before pass 1)
+      const float* xr = x + row * row_stride;
+      for (int i = lane; i < span; i += 32) {
+        const int64_t n = s0 + i;
+        const bool ok = n >= 0 && n < samples;
+        fft::cp_async_4_zfill(ring + slot * span + i, ok ? xr + n : xr, ok ? 4 : 0);
+      }
     }
+    }
+    fft::cp_async_commit();   // one (possibly empty) group per call keeps the wait_group counting uniform
   };
 
   int64_t u = (int64_t)blockIdx.x * kPipeWarps + warp;
@@ -285,12 +209,8 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
       tma::mbar_wait(bar + slot, (parity >> slot) & 1u);
       parity ^= 1u << slot;
     } else {
-      const int64_t s0 = m0 * shift - pad_left;
-      const float* xr = x + row * row_stride;
-      for (int i = lane; i < span; i += 32) {
-        const int64_t n = s0 + i;
-        buf[i] = (n >= 0 && n < samples) ? __ldg(xr + n) : 0.f;
-      }
+      // the unit's own cp.async group is complete once at most the groups issued after it are pending
+      if (STAGES > 1) fft::cp_async_wait_group<STAGES - 1>(); else fft::cp_async_wait_all();
       __syncwarp();
     }
     float2 ya[NS][8], yb[NS][8];
@@ -541,117 +461,39 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                    float interior_scale, float* out, cudaStream_t stream) {
   const int64_t total = rows * frames;
   if (total == 0) return B2S_OK;
-  const bool aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && row_stride % 4 == 0 &&
-                         plan->shift % 4 == 0 && pad_left % 4 == 0;
-  static const int use_staged = [] { const char* e = getenv("B2S_FWD_STAGED"); return e ? atoi(e) : 0; }();
-  if (plan->fast && plan->wlen == fft::kSize && plan->shift % 4 == 0 && plan->shift <= fft::kSize && !use_staged) {
-    // warp pipelines (TMA-fed); any row alignment (unaligned units are filled by the warp itself)
-    // configuration NS,CTAS,COMPACT,STAGES: default 2,2,0,2; others (|Y| layout, shift 256) via B2S_PIPE_CFG
-    static const int cfg = [] {
-      const char* e = getenv("B2S_PIPE_CFG");
-      int ns = 2, ctas = 2, compact = 0, stages = 2;
-      if (e) sscanf(e, "%d,%d,%d,%d", &ns, &ctas, &compact, &stages);
-      return ns * 1000 + ctas * 100 + compact * 10 + stages;
-    }();
-    static const int ablate = [] { const char* e = getenv("B2S_ABLATE"); return e ? atoi(e) : 0; }();
+  if (plan->fast && plan->wlen == fft::kSize && plan->shift % 4 == 0 && plan->shift <= fft::kSize) {
+    // warp pipelines (TMA-fed); any row alignment (units that are not 16-byte aligned are filled with cp.async)
+    static const int ablate = [] { const char* e = getenv("B2S_ABLATE"); return e ? atoi(e) : 0; }();   // tuning aid
     const bool twice = interior_scale == 2.f;
-    const bool experimental = cfg != 2202 && layout == B2S_SPEC_ABS && !twice && plan->shift == 256;
-    const int ns = experimental ? cfg / 1000 : 2, ctas = experimental ? (cfg / 100) % 10 : 2;
-    const int stages = experimental ? cfg % 10 : 2;
     const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
     B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
-    const int64_t units = rows * ceil_div(frames, ns);
-    const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * ctas);
-    const int span = (ns - 1) * plan->shift + fft::kSize;
-    const int out_area = (ns * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
-    const size_t smem = kPipeWarps * (sizeof(float) * (stages * span + out_area) + sizeof(float2) * ns * rf::kTile1);
-#define B2S_PIPE(L, D, S, NS, C, CP, ST)                                                                \
+    const int64_t units = rows * ceil_div(frames, kPipeFrames);
+    const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * kPipeCtasPerSm);
+    const int span = (kPipeFrames - 1) * plan->shift + fft::kSize;
+    const int out_area = (kPipeFrames * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
+    const size_t smem = kPipeWarps * (sizeof(float) * (kPipeStages * span + out_area) +
+                                      sizeof(float2) * kPipeFrames * rf::kTile1);
+#define B2S_PIPE(L, D, S)                                                                               \
     do {                                                                                                \
       static bool configured[64] = {};                                                                  \
       if (!configured[plan->device & 63]) {                                                             \
-        B2S_CUDA(cudaFuncSetAttribute(stft1024_warp_kernel<L, D, S, NS, C, CP, ST>,                     \
+        B2S_CUDA(cudaFuncSetAttribute(stft1024_warp_kernel<L, D, S>,                                    \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));        \
         configured[plan->device & 63] = true;                                                           \
       }                                                                                                 \
-      stft1024_warp_kernel<L, D, S, NS, C, CP, ST><<<grid, 32 * kPipeWarps, smem, stream>>>(x, rows,    \
-          samples, row_stride, pad_left, frames, plan->shift, table, out, ablate);                      \
+      stft1024_warp_kernel<L, D, S><<<grid, 32 * kPipeWarps, smem, stream>>>(x, rows, samples,          \
+          row_stride, pad_left, frames, plan->shift, table, out, ablate);                               \
     } while (0)
-#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) B2S_PIPE(L, D, true, 2, 2, false, 2); else B2S_PIPE(L, D, false, 2, 2, false, 2); } while (0)
-    if (experimental) {
-      switch (cfg) {
-        case 2201: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 2, false, 1); break;
-        case 2311: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 3, true, 1); break;
-        case 2312: B2S_PIPE(B2S_SPEC_ABS, false, true, 2, 3, true, 2); break;
-        case 1411: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 4, true, 1); break;
-        case 1412: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 4, true, 2); break;
-        case 1302: B2S_PIPE(B2S_SPEC_ABS, false, true, 1, 3, false, 2); break;
-        default: B2S_REQUIRE(false, "unknown B2S_PIPE_CFG %d", cfg);
-      }
-    } else {
-      switch (layout) {
-        case B2S_SPEC_INTERLEAVED: if (twice) B2S_PIPE_S(B2S_SPEC_INTERLEAVED, true); else B2S_PIPE_S(B2S_SPEC_INTERLEAVED, false); break;
-        case B2S_SPEC_CONCAT: if (twice) B2S_PIPE_S(B2S_SPEC_CONCAT, true); else B2S_PIPE_S(B2S_SPEC_CONCAT, false); break;
-        case B2S_SPEC_ABS: B2S_PIPE_S(B2S_SPEC_ABS, false); break;
-        default: B2S_PIPE_S(B2S_SPEC_LOG1P_ABS, false); break;
-      }
+#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) B2S_PIPE(L, D, true); else B2S_PIPE(L, D, false); } while (0)
+    switch (layout) {
+      case B2S_SPEC_INTERLEAVED: if (twice) B2S_PIPE_S(B2S_SPEC_INTERLEAVED, true); else B2S_PIPE_S(B2S_SPEC_INTERLEAVED, false); break;
+      case B2S_SPEC_CONCAT: if (twice) B2S_PIPE_S(B2S_SPEC_CONCAT, true); else B2S_PIPE_S(B2S_SPEC_CONCAT, false); break;
+      case B2S_SPEC_ABS: B2S_PIPE_S(B2S_SPEC_ABS, false); break;
+      default: B2S_PIPE_S(B2S_SPEC_LOG1P_ABS, false); break;
     }
 #undef B2S_PIPE_S
 #undef B2S_PIPE
     B2S_LAUNCH_CHECK("stft1024_warp_kernel");
-  } else
-  if (plan->fast && plan->wlen == fft::kSize && aligned16 && plan->shift <= fft::kSize &&
-      rows * frames < (int64_t)1 << 30) {
-    // kernel configuration (NS, CTAS, COMPACT): see stft1024_staged_kernel
-    static const int cfg = [] {
-      const char* e = getenv("B2S_FWD_CFG");
-      int ns = 2, ctas = 2, compact = 0;
-      if (e) sscanf(e, "%d,%d,%d", &ns, &ctas, &compact);
-      return ns * 100 + ctas * 10 + compact;
-    }();
-    static const int ablate = [] { const char* e = getenv("B2S_ABLATE"); return e ? atoi(e) : 0; }();
-    const bool twice = interior_scale == 2.f;
-    const bool experimental = cfg != 220 && layout == B2S_SPEC_ABS && !twice && plan->shift == 256;
-    const int ns = experimental ? cfg / 100 : 2, ctas = experimental ? (cfg / 10) % 10 : 2;
-    const int group = kFwdWarps * ns;
-    const int64_t groups = rows * ceil_div(frames, group);
-    const int grid = (int)std::min<int64_t>(groups, (int64_t)kNumSMs * ctas);
-    const int span = (group - 1) * plan->shift + fft::kSize;
-    const size_t smem = sizeof(float) * 2 * span + sizeof(float2) * rf::kTile1 * ns * kFwdWarps;
-    const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
-    B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
-#define B2S_STAGED(L, D, S, NS, C, CP)                                                                  \
-    do {                                                                                                \
-      static bool configured[64] = {};                                                                  \
-      if (!configured[plan->device & 63]) {                                                             \
-        B2S_CUDA(cudaFuncSetAttribute(stft1024_staged_kernel<L, D, S, NS, C, CP>,                       \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));        \
-        configured[plan->device & 63] = true;                                                           \
-      }                                                                                                 \
-      stft1024_staged_kernel<L, D, S, NS, C, CP><<<grid, 32 * kFwdWarps, smem, stream>>>(x, rows,       \
-          samples, row_stride, pad_left, frames, plan->shift, table, out, ablate);                      \
-    } while (0)
-#define B2S_STAGED_S(L, D) do { if (plan->shift == 256) B2S_STAGED(L, D, true, 2, 2, false); else B2S_STAGED(L, D, false, 2, 2, false); } while (0)
-    if (experimental) {
-      switch (cfg) {
-        case 231: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 3, true); break;
-        case 221: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 2, true); break;
-        case 230: B2S_STAGED(B2S_SPEC_ABS, false, true, 2, 3, false); break;
-        case 141: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 4, true); break;
-        case 131: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 3, true); break;
-        case 130: B2S_STAGED(B2S_SPEC_ABS, false, true, 1, 3, false); break;
-        default: B2S_REQUIRE(false, "unknown B2S_FWD_CFG %d", cfg);
-      }
-    } else {
-      switch (layout) {
-        case B2S_SPEC_INTERLEAVED: if (twice) B2S_STAGED_S(B2S_SPEC_INTERLEAVED, true); else B2S_STAGED_S(B2S_SPEC_INTERLEAVED, false); break;
-        case B2S_SPEC_CONCAT: if (twice) B2S_STAGED_S(B2S_SPEC_CONCAT, true); else B2S_STAGED_S(B2S_SPEC_CONCAT, false); break;
-        case B2S_SPEC_ABS: B2S_STAGED_S(B2S_SPEC_ABS, false); break;
-        default: B2S_STAGED_S(B2S_SPEC_LOG1P_ABS, false); break;
-      }
-    }
-#undef B2S_STAGED_S
-#undef B2S_STAGED
-    B2S_LAUNCH_CHECK("stft1024_staged_kernel");
   } else if (plan->fast) {
     const int64_t want = ceil_div(total, kFwdWarps);
     const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 3 * 4);
