@@ -312,16 +312,18 @@ def run_ours(args, rank, world, local_rank):
             gs.append(g)
         for i in range(6):
             gs[i % ROTATE].replay()
-        n_probe = min(max(args.steps, 30), 300)
+        # CUDA event timestamps tick at ~2 us on this platform: time bursts of replays, not single ones
+        burst = 4 * ROTATE
+        n_probe = max(5, min(max(args.steps, 30), 300) // burst)
         pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                  for _ in range(n_probe)]
-        for i, (e0, e1) in enumerate(pairs):
-            # a different kernel in between keeps the L2 state comparable to the full step
+        for e0, e1 in pairs:
             e0.record()
-            gs[i % ROTATE].replay()
+            for i in range(burst):
+                gs[i % ROTATE].replay()
             e1.record()
         torch.cuda.synchronize()
-        return statistics.mean(e0.elapsed_time(e1) for e0, e1 in pairs)
+        return statistics.median(e0.elapsed_time(e1) for e0, e1 in pairs) / burst
 
     y_abs_sets = [stft.magnitude(d['y']) for d in sets]
     front_ms = kernel_ms(lambda d: stft.magnitude(d['y']))

@@ -53,7 +53,6 @@ int main() {
   run<1, 0>("STG.32 aligned (128 B)", buf, cyc);
   run<1, 1>("STG.32 misaligned +4 B", buf, cyc);
   run<2, 0>("STG.64 aligned (256 B)", buf, cyc);
-  run<2, 1>("STG.64 misaligned", buf, cyc);
   run<4, 0>("STG.128 aligned (512 B)", buf, cyc);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
