@@ -16,7 +16,9 @@
 // At an example boundary the warp flushes its K x K partial sums; the last warp of an example (ticket)
 // folds the partials in slot order and searches the K! permutations (itertools order, first minimum wins).
 #include <algorithm>
+#include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 
 #include "common.cuh"
 #include "fft1024.cuh"
@@ -30,8 +32,9 @@ using namespace b2s::tma;
 
 namespace {
 
-constexpr int kFusedWarps = 4;       // warps per CTA
 constexpr int kFusedCtasPerSm = 2;   // <= 255 registers: two interleaved transforms stay in registers
+// warps per CTA: shared memory per warp grows with K (frames + mask rows); two CTAs must fit in 227 KB
+__host__ __device__ constexpr int fused_warps(int K) { return K <= 2 ? 4 : 3; }
 
 struct FusedGrid {
   int grid;            // persistent CTAs
@@ -40,12 +43,13 @@ struct FusedGrid {
   int slots;           // partial-sum slots per example
 };
 
-FusedGrid fused_grid(int64_t batch, int64_t frames) {
+FusedGrid fused_grid(int64_t batch, int64_t frames, int sources) {
   FusedGrid g;
+  const int warps = fused_warps(sources);
   g.total = batch * std::max<int64_t>(1, frames);
-  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, kFusedWarps),
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, warps),
                                                        (int64_t)kNumSMs * kFusedCtasPerSm));
-  g.warps = std::min<int64_t>((int64_t)g.grid * kFusedWarps, g.total);   // surplus warps of the last CTA idle
+  g.warps = std::min<int64_t>((int64_t)g.grid * warps, g.total);   // surplus warps of the last CTA idle
   g.slots = (int)(ceil_div(std::max<int64_t>(1, frames) * g.warps, g.total) + 2);
   return g;
 }
@@ -92,21 +96,31 @@ __device__ __forceinline__ void warp_search_permutations(const double* cost, int
 // One frame position = (K [+1]) transforms whose magnitudes stay in registers as packed (A side, B side)
 // pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in lane 0 only).
 template <int K, bool RECOMPUTE_Y>
-__global__ void __launch_bounds__(32 * kFusedWarps, kFusedCtasPerSm)
+__global__ void __launch_bounds__(32 * fused_warps(K), kFusedCtasPerSm)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
                       const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames,
                       int shift, int64_t pad_left, const float4* __restrict__ lane_table, int slots,
                       double* __restrict__ partial, int* __restrict__ counters, float* __restrict__ loss,
-                      int32_t* __restrict__ perm, double* __restrict__ sse) {
+                      int32_t* __restrict__ perm, double* __restrict__ sse, unsigned long long* __restrict__ trace) {
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
+  constexpr int kFusedWarps = fused_warps(K);
   constexpr int NT = RECOMPUTE_Y ? K + 1 : K;   // transforms per position; with RECOMPUTE_Y the mixture is first
   constexpr int kWarpFloats = NT * rf::kSize + 4 * rf::kTile1 + row_area_floats(K);
   extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, 2 exchange tiles, mask / |Y| rows
   __shared__ __align__(8) uint64_t bars[kFusedWarps][2];
   __shared__ double totals_sm[kFusedWarps][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // B2S_FUSED_TRACE (tuning aid): %globaltimer of five events per warp
+  auto stamp = [&](int what) {
+    if (trace && lane == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace[((size_t)blockIdx.x * kFusedWarps + warp) * 8 + what] = t;
+    }
+  };
+  stamp(0);
   float* sig = smem + warp * kWarpFloats;                          // frame of transform t at sig + t * 1024
   float2* tile = reinterpret_cast<float2*>(sig + NT * rf::kSize);
   float* rows_area = sig + NT * rf::kSize + 4 * rf::kTile1;
@@ -160,15 +174,26 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
         for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, signal_row(b, t) + s0, rf::kSize * 4u, bar_sig);
       }
     } else {
-      // frames that touch the zero padding or are not 16-byte aligned: 4-byte cp.async with zero fill, just as
-      // asynchronous as the bulk copy (waited for with cp.async.wait_group before pass 1)
+      // frames that touch the zero padding or are not 16-byte aligned: cp.async with zero fill (16-byte units
+      // when the rows allow it), just as asynchronous as the bulk copy (cp.async.wait_group before pass 1)
+      bool a16 = (s0 & 3) == 0;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) a16 = a16 && (reinterpret_cast<uintptr_t>(signal_row(b, t)) & 15) == 0;
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const float* xr = signal_row(b, t);
-        for (int i = lane; i < rf::kSize; i += 32) {
-          const int64_t n = s0 + i;
-          const bool ok = n >= 0 && n < Tb;
-          fft::cp_async_4_zfill(sig + t * rf::kSize + i, ok ? xr + n : xr, ok ? 4 : 0);
+        if (a16) {
+          for (int c = lane; c < rf::kSize / 4; c += 32) {
+            const int64_t n = s0 + 4 * c;
+            const int bytes = n < 0 ? 0 : (int)max((int64_t)0, min((int64_t)4, Tb - n)) * 4;
+            fft::cp_async_16(sig + t * rf::kSize + 4 * c, bytes ? xr + n : xr, bytes);
+          }
+        } else {
+          for (int i = lane; i < rf::kSize; i += 32) {
+            const int64_t n = s0 + i;
+            const bool ok = n >= 0 && n < Tb;
+            fft::cp_async_4_zfill(sig + t * rf::kSize + i, ok ? xr + n : xr, ok ? 4 : 0);
+          }
         }
       }
       fft::cp_async_commit();
@@ -225,10 +250,21 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (last) {   // warp-uniform
       __threadfence();
       double* totals = totals_sm[warp];
+      // fold the partials in a fixed order: lane (c0, i) sums slots c0, c0 + per, ... of value i (independent
+      // loads in flight instead of one dependent chain), then the `per` lanes of a value are added in lane order
+      constexpr int per = 32 / NV;
+      const int vi = lane % NV, c0 = lane / NV;
+      double s = 0.0;
+      if (c0 < per) {
+        const volatile double* p = partial + b * slots * NV + vi;
+        for (int c = c0; c < nparts; c += per) s += p[(int64_t)c * NV];
+      }
+#pragma unroll
+      for (int j = 1; j < per; ++j) {
+        const double o = __shfl_sync(0xffffffffu, s, (vi + j * NV) & 31);
+        if (lane < NV) s += o;
+      }
       if (lane < NV) {
-        double s = 0.0;
-        const volatile double* p = partial + b * slots * NV + lane;
-        for (int c = 0; c < nparts; ++c) s += p[(int64_t)c * NV];
         totals[lane] = s;
         sse[b * NV + lane] = s;
       }
@@ -247,8 +283,11 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
 
   start_signals(p_begin);
   start_rows(p_begin);
+  stamp(1);
   int64_t b_cur = p_begin < p_end ? p_begin / frames : -1;
   for (int64_t q = p_begin; q < p_end; ++q) {
+    if (q == p_begin + 1) stamp(2);
+    if (q == p_begin + 2) stamp(3);
     const int64_t b = q / frames, m = q - b * frames;
     if (b != b_cur) {   // warp-uniform
       flush(b_cur);
@@ -321,7 +360,9 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     __syncwarp();   // every lane has read its rows: the area may be overwritten
     start_rows(q + 1);
   }
+  stamp(4);
   if (b_cur >= 0) flush(b_cur);
+  stamp(5);
 }
 
 template <int K>
@@ -329,7 +370,8 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
                  int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
                  cudaStream_t stream) {
-  const FusedGrid g = fused_grid(batch, frames);
+  const FusedGrid g = fused_grid(batch, frames, K);
+  constexpr int kFusedWarps = fused_warps(K);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   // the transform reads its frame with 16-byte shared-memory loads and TMA copies 16-byte units
@@ -346,9 +388,60 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
     B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured[variant][plan->device & 63] = true;
   }
+  static const bool want_trace = getenv("B2S_FUSED_TRACE") != nullptr;
+  unsigned long long* trace = nullptr;
+  const size_t nstamps = (size_t)g.grid * kFusedWarps * 8;
+  if (want_trace) {
+    B2S_CUDA(cudaMalloc(&trace, nstamps * sizeof(unsigned long long)));
+    B2S_CUDA(cudaMemsetAsync(trace, 0, nstamps * sizeof(unsigned long long), stream));
+  }
   kernel<<<g.grid, 32 * kFusedWarps, smem, stream>>>(mixture, yabs, sources, mask, meta, batch, samples, frames,
-      plan->shift, pad_left, plan->lane_fwd, g.slots, partial, counters, loss, perm, sse);
+      plan->shift, pad_left, plan->lane_fwd, g.slots, partial, counters, loss, perm, sse, trace);
   B2S_LAUNCH_CHECK("stft_pit_fused_kernel");
+  if (want_trace) {   // tuning aid: per-warp timeline statistics on stderr
+    std::vector<unsigned long long> h(nstamps);
+    B2S_CUDA(cudaStreamSynchronize(stream));
+    B2S_CUDA(cudaMemcpy(h.data(), trace, nstamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    unsigned long long t0 = ~0ull, t_end = 0;
+    for (size_t w = 0; w < nstamps / 8; ++w) if (h[w * 8]) { t0 = std::min(t0, h[w * 8]); t_end = std::max(t_end, h[w * 8 + 5]); }
+    double sum[6] = {}, mx[6] = {}, mn[6] = {1e30, 1e30, 1e30, 1e30, 1e30, 1e30};
+    size_t n = 0;
+    for (size_t w = 0; w < nstamps / 8; ++w) {
+      if (!h[w * 8] || !h[w * 8 + 5]) continue;
+      ++n;
+      for (int i = 0; i < 6; ++i) {
+        const double v = h[w * 8 + i] ? (double)(h[w * 8 + i] - t0) * 1e-3 : 0.0;
+        sum[i] += v; mx[i] = std::max(mx[i], v); mn[i] = std::min(mn[i], v);
+      }
+    }
+    fprintf(stderr, "[fused trace] %zu warps, kernel span %.1f us; event: mean / min / max us after the first warp started\n",
+            n, (double)(t_end - t0) * 1e-3);
+    const char* names[6] = {"entry", "first copies issued", "position 1 done", "position 2 done", "loop done", "flush done"};
+    for (int i = 0; i < 6; ++i) fprintf(stderr, "  %-20s %7.2f / %7.2f / %7.2f\n", names[i], sum[i] / n, mn[i], mx[i]);
+    // loop duration (event 4 - event 1) by number of positions of the warp, and per-SM-ish (block) spread
+    std::vector<double> dur;
+    for (size_t w = 0; w < nstamps / 8; ++w) if (h[w * 8 + 4]) dur.push_back((double)(h[w * 8 + 4] - h[w * 8 + 1]) * 1e-3);
+    std::sort(dur.begin(), dur.end());
+    if (!dur.empty())
+      fprintf(stderr, "  loop duration percentiles 0/10/25/50/75/90/100: %.1f %.1f %.1f %.1f %.1f %.1f %.1f us\n", dur[0],
+              dur[dur.size() / 10], dur[dur.size() / 4], dur[dur.size() / 2], dur[dur.size() * 3 / 4],
+              dur[dur.size() * 9 / 10], dur.back());
+    std::vector<double> fl;
+    for (size_t w = 0; w < nstamps / 8; ++w) if (h[w * 8 + 5]) fl.push_back((double)(h[w * 8 + 5] - h[w * 8 + 4]) * 1e-3);
+    std::sort(fl.begin(), fl.end());
+    if (!fl.empty())
+      fprintf(stderr, "  final flush percentiles 0/50/90/99/100: %.2f %.2f %.2f %.2f %.2f us\n", fl[0], fl[fl.size() / 2],
+              fl[fl.size() * 9 / 10], fl[fl.size() * 99 / 100], fl.back());
+    // mean loop duration of the 4 warps of each block, extremes
+    double bmin = 1e30, bmax = 0;
+    for (size_t b = 0; b + kFusedWarps <= nstamps / 8; b += kFusedWarps) {
+      double s4 = 0;
+      for (int w = 0; w < kFusedWarps; ++w) s4 += (double)(h[(b + w) * 8 + 4] - h[(b + w) * 8 + 1]) * 1e-3;
+      bmin = std::min(bmin, s4 / kFusedWarps); bmax = std::max(bmax, s4 / kFusedWarps);
+    }
+    fprintf(stderr, "  per-block mean loop duration: min %.1f max %.1f us\n", bmin, bmax);
+  }
   return B2S_OK;
 }
 
@@ -358,7 +451,7 @@ extern "C" {
 
 int64_t b2s_stft_pit_workspace_bytes(int64_t batch, int64_t frames, int sources) {
   if (batch <= 0 || sources <= 0) return kTicketBytes + 16;
-  const FusedGrid g = fused_grid(batch, frames);
+  const FusedGrid g = fused_grid(batch, frames, sources);
   return kTicketBytes + (int64_t)sizeof(double) * batch * g.slots * sources * sources + 16;
 }
 

@@ -184,13 +184,21 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
         tma::bulk_g2s(ring + slot * span, src, (unsigned)span * 4u, bar + slot);
       }
     } else {
-      // units that touch the zero padding or are not 16-byte aligned: 4-byte cp.async with zero fill, just as
-      // asynchronous as the bulk copy (waited for with cp.async.wait_group before pass 1)
+      // units that touch the zero padding or are not 16-byte aligned: cp.async with zero fill (16-byte units
+      // when the row allows it), just as asynchronous as the bulk copy (cp.async.wait_group before pass 1)
       const float* xr = x + row * row_stride;
-      for (int i = lane; i < span; i += 32) {
-        const int64_t n = s0 + i;
-        const bool ok = n >= 0 && n < samples;
-        fft::cp_async_4_zfill(ring + slot * span + i, ok ? xr + n : xr, ok ? 4 : 0);
+      if ((s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
+        for (int c = lane; c < span / 4; c += 32) {
+          const int64_t n = s0 + 4 * c;
+          const int bytes = n < 0 ? 0 : (int)max((int64_t)0, min((int64_t)4, samples - n)) * 4;
+          fft::cp_async_16(ring + slot * span + 4 * c, bytes ? xr + n : xr, bytes);
+        }
+      } else {
+        for (int i = lane; i < span; i += 32) {
+          const int64_t n = s0 + i;
+          const bool ok = n >= 0 && n < samples;
+          fft::cp_async_4_zfill(ring + slot * span + i, ok ? xr + n : xr, ok ? 4 : 0);
+        }
       }
     }
     }

@@ -443,6 +443,42 @@ def test_fused_step_against_oracle(b2s, k, seconds):
         assert_loss_close(loss_r[b].cpu().numpy(), w_loss[0].numpy())
 
 
+def test_fused_step_unaligned_views_and_tiny_batches(b2s):
+    """The fused kernel's TMA pipelines fall back to zero-filling cp.async for rows that are not 16-byte
+    aligned; batches with fewer frame positions than warps leave pipelines idle.  Results must not change."""
+    from oracle import path as OP
+    rng = np.random.RandomState(5)
+    stft = b2s.ops.STFT(1024, 256)
+    for B, T in ((1, 1300), (2, 5000)):
+        k = 2
+        base = (0.1 * rng.randn(B, k, T + 3)).astype(np.float32)
+        s_np = np.ascontiguousarray(base[:, :, 1:T + 1])
+        y_np = s_np.sum(1)
+        M = stft.samples_to_frames(T)
+        masks = rng.rand(B, M, k, 513).astype(np.float32)
+        want_loss, want_perm, _ = OP.stft_mask_pit_step(torch.from_numpy(y_np), torch.from_numpy(s_np),
+                                                        torch.from_numpy(masks))
+        # aligned tensor and a contiguous tensor whose storage starts 4 bytes off a 16-byte boundary
+        flat = torch.zeros(s_np.size + 1, dtype=torch.float32, device=dev())
+        flat[1:] = cuda(s_np).reshape(-1)
+        s_off = flat[1:].view(B, k, T)
+        assert s_off.is_contiguous() and s_off.data_ptr() % 16 != 0
+        for s_dev in (cuda(s_np), s_off):
+            loss, perm = b2s.review.stft_mask_pit_step(cuda(y_np), s_dev, cuda(masks), stft=stft)
+            np.testing.assert_array_equal(perm.cpu().numpy(), np.asarray(want_perm))
+            assert_loss_close(loss.cpu().numpy(), want_loss.numpy())
+        # odd sample count: frames end inside a 16-byte unit
+        T2 = T - 1
+        s2, y2 = np.ascontiguousarray(s_np[:, :, :T2]), np.ascontiguousarray(y_np[:, :T2])
+        M2 = stft.samples_to_frames(T2)
+        w_loss, w_perm, _ = OP.stft_mask_pit_step(torch.from_numpy(y2), torch.from_numpy(s2),
+                                                  torch.from_numpy(masks[:, :M2]))
+        loss, perm = b2s.review.stft_mask_pit_step(cuda(y2), cuda(s2), cuda(np.ascontiguousarray(masks[:, :M2])),
+                                                   stft=stft)
+        np.testing.assert_array_equal(perm.cpu().numpy(), np.asarray(w_perm))
+        assert_loss_close(loss.cpu().numpy(), w_loss.numpy())
+
+
 # ------------------------------------------------------------------------------------------------ full size
 def test_full_size_properties(b2s):
     """BASELINE.json's headline shape: batch 64 x 4 s x 16 kHz, 2 speakers, STFT(1024, 256)."""
