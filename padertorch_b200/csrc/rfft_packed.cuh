@@ -301,7 +301,8 @@ B2S_HD void load_ex1(const float2* tile, int lane, float2 (&va)[8], float2 (&vb)
     vb[n1] = make_float2(x.z, x.w);
   }
 }
-B2S_HD void pass2_regs(const LaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
+template <class C>
+B2S_HD void pass2_regs(const C& k, float2 (&va)[8], float2 (&vb)[8]) {
 #pragma unroll
   for (int n1 = 1; n1 < 8; ++n1) {
     va[n1] = cmul(va[n1], k.t2[n1 - 1]);
@@ -328,13 +329,15 @@ B2S_HD void load_ex2(const float2* ex2, int lane, float2 (&a)[8], float2 (&b)[8]
     b[n0] = sb[66 * n0];
   }
 }
-B2S_HD void pass3_twiddle_a(const LaneConsts& k, float2 (&a)[8]) {   // lanes >= 1 only (butterfly 0 has none)
+template <class C>
+B2S_HD void pass3_twiddle_a(const C& k, float2 (&a)[8]) {   // lanes >= 1 only (butterfly 0 has none)
 #pragma unroll
   for (int n0 = 1; n0 < 8; ++n0) a[n0] = cmul(a[n0], k.t3[n0 - 1]);
 }
 // butterfly 64 - l: twiddles W8^n0 conj(w^n0); the W8^n0 factor shifts the outputs by one slot:
 // b[q] = Z[(64 - l) + 64 ((q - 1) & 7)], the mirror of a[p] = Z[l + 64 p] is b[(8 - p) & 7]
-B2S_HD void pass3_twiddle_b(const LaneConsts& k, float2 (&b)[8]) {
+template <class C>
+B2S_HD void pass3_twiddle_b(const C& k, float2 (&b)[8]) {
 #pragma unroll
   for (int n0 = 1; n0 < 8; ++n0) b[n0] = cmulc(b[n0], k.t3[n0 - 1]);
 }
@@ -409,6 +412,111 @@ B2S_HD void pass3(const float2* tile, const LaneConsts& k, float2 (&ya)[8], floa
   if (k.lane != 0) pass3_twiddle_a(k, a);
   pass3_twiddle_b(k, b);
   pass3_regs<DOUBLE_INTERIOR>(k, a, b, ya, yb, y_dc, y_nyq);
+}
+
+// ---- inverse real transform ----------------------------------------------------------------------------------
+// S[m] = Y0 + (-1)^m Y512 + 2 sum_{0<f<512} Re(Y_f e^{+2 pi i f m / 1024}) = 1024 irfft(Y)[m] through the SAME
+// three passes: with Z[k] = (Y[k] + conj Y[512-k]) + i e^{+2 pi i k/1024} (Y[k] - conj Y[512-k]) the 512-point
+// inverse transform z[n] = sum_k Z[k] e^{+2 pi i k n / 512} equals S[2n] + i S[2n+1], and z = conj(FFT(conj Z)).
+// The passes therefore run on u[k] = conj Z[k] = (A + B) + tin[k] (A - B),  A = conj Y[k], B = Y[512-k],
+// tin[k] = -i e^{-2 pi i k/1024}, with k in the role of the forward transform's sample index, and the output
+// lane l holds conj z[n] for n = l + 64 p (a side) and n = (64 - l) + 64 ((q - 1) & 7) (b side; lane 0: 32 + ...).
+// No real split and no lane-0 re-pairing is needed on this side.  The imaginary parts of Y[0] and Y[512]
+// are ignored like the reference's transposed convolution does (its sine rows are zero there).
+constexpr int kInvConstFloat4 = 23;
+struct InvLaneConsts {
+  float2 tin[16];   // tin[2 n2 + e] for the lane's input bins k = 2 l + e + 64 n2
+  float2 t2[7], t3[7];
+  float2 wa[8], wb[8];   // (scale w[2n], -scale w[2n+1]) of the a / b output positions (conj z -> samples)
+  float dc_fix;          // 1 / scale for the k = 0 input (DC and Nyquist are not scaled)
+  int lane;
+
+  // scale: factor applied to the interior bins' contribution (1: plain irfft * 1024; 1/2: adjoint of the STFT)
+  B2S_HD void init(const float2* tab, const float* win, int lane_, float scale) {
+    lane = lane_;
+    dc_fix = 1.f / scale;
+#pragma unroll
+    for (int n2 = 0; n2 < 8; ++n2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float2 t = tab[2 * lane + e + 64 * n2];
+        tin[2 * n2 + e] = make_float2(t.y, -t.x);
+      }
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      t2[r - 1] = tab[(16 * r * (lane >> 2)) & 1023];
+      t3[r - 1] = lane ? tab[(2 * r * lane) & 1023] : tab[64 * r];
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int na = lane + 64 * p, nb = (lane ? 64 - lane : 32) + 64 * ((p + 7) & 7);
+      wa[p] = make_float2(scale * win[2 * na], -scale * win[2 * na + 1]);
+      wb[p] = make_float2(scale * win[2 * nb], -scale * win[2 * nb + 1]);
+    }
+  }
+  void pack(float4* table) const {
+    float4* t = table + lane;
+    float2 all[46];
+    for (int i = 0; i < 16; ++i) all[i] = tin[i];
+    for (int i = 0; i < 7; ++i) { all[16 + i] = t2[i]; all[23 + i] = t3[i]; }
+    for (int i = 0; i < 8; ++i) { all[30 + i] = wa[i]; all[38 + i] = wb[i]; }
+    for (int i = 0; i < 23; ++i) t[32 * i] = make_float4(all[2 * i].x, all[2 * i].y, all[2 * i + 1].x, all[2 * i + 1].y);
+  }
+  B2S_HD void load(const float4* table, int lane_, float scale) {
+    lane = lane_;
+    dc_fix = 1.f / scale;
+    const float4* t = table + lane;
+    float2 all[46];
+#pragma unroll
+    for (int i = 0; i < 23; ++i) {
+      const float4 v = t[32 * i];
+      all[2 * i] = make_float2(v.x, v.y);
+      all[2 * i + 1] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tin[i] = all[i];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { t2[i] = all[16 + i]; t3[i] = all[23 + i]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { wa[i] = all[30 + i]; wb[i] = all[38 + i]; }
+  }
+};
+// output sample pair index of b-side slot q
+B2S_HD int inv_pos_b(int lane, int q) { return (lane ? 64 - lane : 32) + 64 * ((q + 7) & 7); }
+
+// Shared-memory position of bin k of a staged spectrum: even bins first, odd bins from 264 -- lanes read bins
+// 2 l + e + 64 n2 and their mirrors, i.e. consecutive positions (conflict free) instead of every other one.
+B2S_HD int inv_bin_pos(int k) { return (k >> 1) + (k & 1) * 264; }
+
+// inverse split + radix-8 over n2; Y = the frame's 513 bins (re, im) in shared memory at inv_bin_pos(k)
+B2S_HD void inv_pass1_regs(const float2* Y, const InvLaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
+  const int lane = k.lane;
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = 2 * lane + e + 64 * n2;
+      // kk and 512 - kk have the same parity: positions lane + 32 n2 (+264) and 256 - lane - 32 n2 - e (+264)
+      float2 A = conj(Y[lane + 32 * n2 + 264 * e]), B = Y[256 - lane - 32 * n2 - e + 264 * e];
+      if (n2 == 0 && e == 0 && lane == 0) { A.y = 0.f; B.y = 0.f; }
+      const float2 s = add2(A, B), d = sub2(A, B);
+      float2 u = add2(s, cmul(d, k.tin[2 * n2 + e]));
+      if (n2 == 0 && e == 0 && lane == 0) u = mul2(u, bcast(k.dc_fix));
+      if (e == 0) va[n2] = u; else vb[n2] = u;
+    }
+  }
+  radix8(va);
+  radix8(vb);
+}
+// windowed samples of the a / b positions: (S[2n], S[2n+1]) w
+B2S_HD void inv_finish(const InvLaneConsts& k, float2 (&a)[8], float2 (&b)[8]) {
+  radix8(a);
+  radix8(b);
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    a[p] = mul2(a[p], k.wa[p]);
+    b[p] = mul2(b[p], k.wb[p]);
+  }
 }
 
 #ifdef __CUDACC__
@@ -503,6 +611,40 @@ __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, fl
       y_dc[s] = va[s][0].x; y_nyq[s] = vb[s][0].y;
     }
   }
+}
+
+// NS inverse transforms per warp.  `tile` = NS regions of kTile1 float2; on entry region s holds the 513 bins of
+// stream s (it becomes the exchange buffer once every lane has its inputs); on return a[s][p] / b[s][q] are the
+// windowed sample pairs of positions lane + 64 p / inv_pos_b(lane, q).
+template <int NS>
+__device__ __forceinline__ void irfft_streams(float2* tile, const InvLaneConsts& k, float2 (&a)[NS][8],
+                                              float2 (&b)[NS][8]) {
+  const int lane = k.lane;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) inv_pass1_regs(tile + s * kTile1, k, a[s], b[s]);
+  __syncwarp();   // every lane holds its bins: the regions become exchange buffers
+#pragma unroll
+  for (int s = 0; s < NS; ++s) store_ex1(tile + s * kTile1, lane, a[s], b[s]);
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NS; ++s) load_ex1(tile + s * kTile1, lane, a[s], b[s]);
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NS; ++s) pass2_regs(k, a[s], b[s]);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) store_ex2(tile + s * kTile1, lane, a[s], b[s]);
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NS; ++s) load_ex2(tile + s * kTile1, lane, a[s], b[s]);
+  if (lane != 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pass3_twiddle_a(k, a[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) pass3_twiddle_b(k, b[s]);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) inv_finish(k, a[s], b[s]);
+  __syncwarp();   // all exchange-2 reads are done: the caller may overwrite the regions
 }
 #endif
 

@@ -301,78 +301,79 @@ dft_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, i
 
 // ------------------------------------------------------------------------------------------- fast inverse
 // CTA = (row, chunk of `hops` output hops).  Phase 1: the frames overlapping the chunk are inverse
-// transformed, windowed and parked in shared memory (frame slot == the warp's FFT tile).  Phase 2:
-// every output sample sums its <= ceil(wlen/shift) contributions in increasing frame order.
-constexpr int kInvSlots = 16;   // 16 x 4.25 KB = 68 KB of shared memory -> 3 CTAs of 4 warps per SM
+// transformed two at a time per warp (rf::irfft_streams: the forward passes run on conj Z), windowed and
+// parked in shared memory (frame slot == spectrum landing area == exchange tile).  Phase 2: every output
+// sample sums its <= ceil(wlen/shift) contributions in increasing frame order -- deterministic, no atomics.
 constexpr int kInvWarps = 4;
+// NS = 1: 16 slots (72 KB) and <= 168 registers -> 3 CTAs per SM; NS = 2: 24 slots (108 KB), 2 CTAs per SM
+__host__ __device__ constexpr int inv_slots(int ns) { return ns == 1 ? 16 : 24; }
 
+// stage the 513 bins of frame `fr` (global frame index) as interleaved float2 into `slot`
 template <int LAYOUT>
-__global__ void __launch_bounds__(32 * kInvWarps, 3)
+__device__ __forceinline__ void stage_spectrum(float2* slot, const float* __restrict__ spec, int64_t fr, int lane) {
+  if (LAYOUT == B2S_SPEC_INTERLEAVED) {
+    const float2* src = reinterpret_cast<const float2*>(spec) + fr * rf::kBins;
+    for (int c = lane; c < rf::kBins; c += 32) fft::cp_async_8(slot + rf::inv_bin_pos(c), src + c);
+  } else {   // 'concat': a row of real parts, then a row of imaginary parts
+    const float* re = spec + fr * 2 * rf::kBins;
+    float* dst = reinterpret_cast<float*>(slot);
+    for (int c = lane; c < rf::kBins; c += 32) {
+      fft::cp_async_4(dst + 2 * rf::inv_bin_pos(c), re + c);
+      fft::cp_async_4(dst + 2 * rf::inv_bin_pos(c) + 1, re + rf::kBins + c);
+    }
+  }
+}
+
+template <int LAYOUT, int NS>
+__global__ void __launch_bounds__(32 * kInvWarps, NS == 1 ? 3 : 2)
 istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int shift,
                  int wlen, int overlap /*ceil(wlen/shift)*/, int hops, int64_t chunks,
-                 int64_t crop_left, int64_t samples_out, const float* __restrict__ win,
-                 const float2* __restrict__ twtab, float interior_in_scale, float* __restrict__ out) {
-  extern __shared__ float2 slots[];  // [kInvSlots][kTile]
+                 int64_t crop_left, int64_t samples_out, const float4* __restrict__ lane_table,
+                 float interior_in_scale, float* __restrict__ out) {
+  extern __shared__ float2 slots[];  // [inv_slots(NS)][rf::kTile1]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  fft::LaneConsts<true> k;
-  k.init(twtab, lane);
-  float2 wa[8], wb[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    wa[r] = reinterpret_cast<const float2*>(win)[fft::natural_a(lane, r)];
-    wb[r] = reinterpret_cast<const float2*>(win)[fft::mirrored_b(lane, r)];
-  }
-  const int k0 = fft::bin_a(lane, 0), k4 = fft::bin_a(lane, 4) - 256;   // slot p holds bin (p<4 ? k0 : k4) + 64 p
+  rf::InvLaneConsts k;
+  k.load(lane_table, lane, interior_in_scale);
+  // 16-byte overlap-add: whole float4 groups stay inside one frame's window and one output alignment class
+  const bool vec4 = (shift & 3) == 0 && (wlen & 3) == 0 && (crop_left & 3) == 0 && (samples_out & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   for (int64_t job = blockIdx.x; job < rows * chunks; job += gridDim.x) {
     const int64_t row = job / chunks, chunk = job - row * chunks;
     const int64_t h0 = chunk * hops;                       // first hop (padded sample h0*shift)
     const int64_t m_first = max((int64_t)0, h0 - overlap + 1);
     const int64_t m_last = min(frames - 1, h0 + hops - 1);  // inclusive
     __syncthreads();                                        // the previous job's overlap-add is done
-    if (LAYOUT == B2S_SPEC_INTERLEAVED) {
-      // all spectra of this warp's frames start travelling into their slots now (8-byte cp.async)
-      for (int64_t m = m_first + warp; m <= m_last; m += kInvWarps) {
-        float2* slot = slots + (m - m_first) * fft::kTile;
-        const float2* src = reinterpret_cast<const float2*>(spec) + (row * frames + m) * fft::kBins;
-        for (int c = lane; c < fft::kBins; c += 32) fft::cp_async_8(slot + c, src + c);
-      }
+    // this warp's frame groups (m .. m + NS - 1), m = m_first + NS (warp + 4 i): all spectra start travelling
+    // now, one cp.async group per frame group
+    int ngroups = 0;
+    for (int64_t m = m_first + NS * warp; m <= m_last; m += NS * kInvWarps, ++ngroups) {
+      float2* slot = slots + (m - m_first) * rf::kTile1;
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (m + s <= m_last) stage_spectrum<LAYOUT>(slot + s * rf::kTile1, spec, row * frames + m + s, lane);
       fft::cp_async_commit();
-      fft::cp_async_wait_all();
-      __syncwarp();
     }
-    for (int64_t m = m_first + warp; m <= m_last; m += kInvWarps) {
-      float2* tile = slots + (m - m_first) * fft::kTile;
-      float2 ya[8], yb[8];
-      float ydc = 0.f, ynyq = 0.f;
-      if (LAYOUT == B2S_SPEC_INTERLEAVED) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int kk = (p < 4 ? k0 : k4) + 64 * p;
-          ya[p] = tile[kk];
-          yb[p] = tile[fft::kHalf - kk];
-        }
-        if (lane == 0) { ydc = tile[0].x; ynyq = tile[fft::kHalf].x; }
-        __syncwarp();   // everyone has its bins before the tile becomes the exchange buffer
-      } else {
-        const float* re = spec + (row * frames + m) * 2 * fft::kBins;
-        const float* im = re + fft::kBins;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int kk = (p < 4 ? k0 : k4) + 64 * p;
-          ya[p] = make_float2(__ldg(re + kk), __ldg(im + kk));
-          yb[p] = make_float2(__ldg(re + fft::kHalf - kk), __ldg(im + fft::kHalf - kk));
-        }
-        if (lane == 0) { ydc = __ldg(re); ynyq = __ldg(re + fft::kHalf); }
+    int grp = 0;
+    for (int64_t m = m_first + NS * warp; m <= m_last; m += NS * kInvWarps, ++grp) {
+      float2* tile = slots + (m - m_first) * rf::kTile1;
+      // groups complete in order: group `grp` has landed once at most ngroups - 1 - grp groups are pending
+      switch (ngroups - 1 - grp) {
+        case 0: fft::cp_async_wait_group<0>(); break;
+        case 1: fft::cp_async_wait_group<1>(); break;
+        case 2: fft::cp_async_wait_group<2>(); break;
+        default: fft::cp_async_wait_group<3>(); break;
       }
-      const float2 sc = make_float2(interior_in_scale, interior_in_scale);
+      __syncwarp();
+      float2 a[NS][8], b[NS][8];
+      rf::irfft_streams<NS>(tile, k, a, b);
 #pragma unroll
-      for (int p = 0; p < 8; ++p) { ya[p] = fft::pmul(ya[p], sc); yb[p] = fft::pmul(yb[p], sc); }
-      float2 a[8], b[8];
-      fft::irfft1024(ya, yb, ydc, ynyq, tile, k, a, b);
+      for (int s = 0; s < NS; ++s) {
+        float2* fr = tile + s * rf::kTile1;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        tile[fft::natural_a(lane, r)] = fft::pmul(a[r], wa[r]);
-        tile[fft::mirrored_b(lane, r)] = fft::pmul(b[r], wb[r]);
+        for (int p = 0; p < 8; ++p) {
+          fr[lane + 64 * p] = a[s][p];
+          fr[rf::inv_pos_b(lane, p)] = b[s][p];
+        }
       }
     }
     __syncthreads();
@@ -384,16 +385,41 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
     const int last_rel = (int)(m_last - m_first);    // last valid slot
     const int64_t n0 = h0 * shift - crop_left;       // output index of the chunk's first sample
     float* orow = out + row * samples_out;
-    for (int q = threadIdx.x; q < span; q += blockDim.x) {
-      const int64_t n = n0 + q;
-      if (n < 0 || n >= samples_out) continue;
-      const int hq = q / shift, i = q - hq * shift;
-      float acc = 0.f;
-      for (int j = overlap - 1; j >= 0; --j) {
-        const int rel = rel0 + hq - j, idx = i + j * shift;
-        if (rel >= 0 && rel <= last_rel && idx < wlen) acc += fbuf[rel * (2 * fft::kTile) + idx];
+    if (vec4) {
+      // four consecutive samples per thread: one LDS.128 per contributing frame, one 16-byte store
+      for (int q4 = threadIdx.x; q4 < (span >> 2); q4 += blockDim.x) {
+        const int q = q4 << 2;
+        const int64_t n = n0 + q;
+        if (n + 3 < 0 || n >= samples_out) continue;
+        const int hq = q / shift, i = q - hq * shift;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = overlap - 1; j >= 0; --j) {
+          const int rel = rel0 + hq - j, idx = i + j * shift;
+          if (rel >= 0 && rel <= last_rel && idx < wlen) {
+            const float4 v = *reinterpret_cast<const float4*>(fbuf + rel * (2 * rf::kTile1) + idx);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        }
+        if (n >= 0 && n + 3 < samples_out) {
+          *reinterpret_cast<float4*>(orow + n) = acc;
+        } else {
+          const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+          for (int c = 0; c < 4; ++c)
+            if (n + c >= 0 && n + c < samples_out) orow[n + c] = a4[c];
+        }
       }
-      orow[n] = acc;
+    } else {
+      for (int q = threadIdx.x; q < span; q += blockDim.x) {
+        const int64_t n = n0 + q;
+        if (n < 0 || n >= samples_out) continue;
+        const int hq = q / shift, i = q - hq * shift;
+        float acc = 0.f;
+        for (int j = overlap - 1; j >= 0; --j) {
+          const int rel = rel0 + hq - j, idx = i + j * shift;
+          if (rel >= 0 && rel <= last_rel && idx < wlen) acc += fbuf[rel * (2 * rf::kTile1) + idx];
+        }
+        orow[n] = acc;
+      }
     }
   }
 }
@@ -533,7 +559,7 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
 
 bool fused_inverse_ok(const b2s_stft_plan* plan) {
   const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
-  return plan->fast && overlap <= 8;
+  return plan->fast && overlap <= 8;   // hops = slots - overlap + 1 >= 9
 }
 
 // inverse-type launch shared by b2s_istft_forward and b2s_stft_backward
@@ -548,23 +574,29 @@ int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, i
   }
   if (fused_inverse_ok(plan)) {
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(spec) & 7) == 0, "spectrum pointer must be 8-byte aligned");
+    static const int ns = [] { const char* e = getenv("B2S_INV_NS"); return e && atoi(e) == 2 ? 2 : 1; }();
     const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
-    const int hops = kInvSlots - overlap + 1;
+    const int hops = inv_slots(ns) - overlap + 1;
     // padded samples that can receive output: [crop_left, crop_left + samples_out)
     const int64_t total_hops = ceil_div(crop_left + samples_out, plan->shift);
     const int64_t chunks = ceil_div(total_hops, hops);
-    const size_t smem = sizeof(float2) * fft::kTile * kInvSlots;
-    static bool configured[2][64] = {};
-    const int variant = layout == B2S_SPEC_INTERLEAVED ? 0 : 1;
-    auto kernel = variant == 0 ? istft1024_kernel<B2S_SPEC_INTERLEAVED> : istft1024_kernel<B2S_SPEC_CONCAT>;
+    const size_t smem = sizeof(float2) * rf::kTile1 * inv_slots(ns);
+    static bool configured[4][64] = {};
+    const int variant = (layout == B2S_SPEC_INTERLEAVED ? 0 : 1) + (ns == 2 ? 2 : 0);
+    auto kernel = ns == 2
+        ? (layout == B2S_SPEC_INTERLEAVED ? istft1024_kernel<B2S_SPEC_INTERLEAVED, 2> : istft1024_kernel<B2S_SPEC_CONCAT, 2>)
+        : (layout == B2S_SPEC_INTERLEAVED ? istft1024_kernel<B2S_SPEC_INTERLEAVED, 1> : istft1024_kernel<B2S_SPEC_CONCAT, 1>);
     if (!configured[variant][plan->device & 63]) {
       B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[variant][plan->device & 63] = true;
     }
-    const int grid = (int)std::min<int64_t>(rows * chunks, (int64_t)kNumSMs * 3 * 8);
-    // irfft1024 yields S = edge + 2 * interior; the adjoint wants edge + 1 * interior: halve interior bins
+    const int grid = (int)std::min<int64_t>(rows * chunks, (int64_t)kNumSMs * (ns == 1 ? 3 : 2) * 8);
+    // the inverse transform yields S = edge + 2 * interior; the adjoint of the STFT wants edge + 1 * interior
+    const bool adjoint = interior_scale == 1.f;
+    B2S_REQUIRE(win == (adjoint ? plan->awin : plan->swin), "internal: window / table mismatch");
     kernel<<<grid, 32 * kInvWarps, smem, stream>>>(spec, rows, frames, plan->shift, plan->wlen, overlap, hops,
-        chunks, crop_left, samples_out, win, plan->tw, 0.5f * interior_scale, out);
+        chunks, crop_left, samples_out, adjoint ? plan->lane_inv_ana : plan->lane_inv_syn,
+        0.5f * interior_scale, out);
     B2S_LAUNCH_CHECK("istft1024_kernel");
   } else {
     B2S_REQUIRE(scratch != nullptr, "inverse transform of this plan needs scratch (b2s_stft_scratch_bytes)");
@@ -631,7 +663,7 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
   plan->bins = size / 2 + 1;
   plan->fast = size == fft::kSize;
   plan->awin = nullptr; plan->swin = nullptr; plan->tw = nullptr;
-  plan->lane_fwd = nullptr; plan->lane_adj = nullptr;
+  plan->lane_fwd = nullptr; plan->lane_adj = nullptr; plan->lane_inv_syn = nullptr; plan->lane_inv_ana = nullptr;
   cudaError_t e = cudaMalloc(&plan->awin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->swin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->tw, sizeof(float2) * size);
@@ -652,6 +684,19 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
     if (e == cudaSuccess) e = cudaMalloc(&plan->lane_adj, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(plan->lane_fwd, fwd.data(), bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(plan->lane_adj, adj.data(), bytes, cudaMemcpyHostToDevice);
+    const size_t ibytes = sizeof(float4) * rf::kInvConstFloat4 * 32;
+    std::vector<float4> isyn(rf::kInvConstFloat4 * 32), iana(rf::kInvConstFloat4 * 32);
+    for (int lane = 0; lane < 32; ++lane) {
+      rf::InvLaneConsts ik;
+      ik.init(tw.data(), sw.data(), lane, 1.f);
+      ik.pack(isyn.data());
+      ik.init(tw.data(), aw.data(), lane, 0.5f);
+      ik.pack(iana.data());
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&plan->lane_inv_syn, ibytes);
+    if (e == cudaSuccess) e = cudaMalloc(&plan->lane_inv_ana, ibytes);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->lane_inv_syn, isyn.data(), ibytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->lane_inv_ana, iana.data(), ibytes, cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     set_error("stft plan allocation failed: %s", cudaGetErrorString(e));
@@ -667,6 +712,7 @@ int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
   cudaSetDevice(plan->device);
   cudaFree(plan->awin); cudaFree(plan->swin); cudaFree(plan->tw);
   cudaFree(plan->lane_fwd); cudaFree(plan->lane_adj);
+  cudaFree(plan->lane_inv_syn); cudaFree(plan->lane_inv_ana);
   delete plan;
   return B2S_OK;
 }

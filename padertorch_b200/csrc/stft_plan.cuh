@@ -11,4 +11,7 @@ struct b2s_stft_plan {
   // fast plans only: per-lane constant tables of the packed warp FFT (rfft_packed.cuh, [19][32] float4):
   float4* lane_fwd;   // analysis window, halved        (STFT forward, fused STFT -> PIT)
   float4* lane_adj;   // synthesis window, not halved    (adjoint of the iSTFT: interior bins doubled)
+  // inverse transform ([23][32] float4, rf::InvLaneConsts):
+  float4* lane_inv_syn;   // synthesis window, scale 1    (iSTFT)
+  float4* lane_inv_ana;   // analysis window, scale 1/2   (adjoint of the STFT)
 };
