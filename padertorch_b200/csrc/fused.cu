@@ -154,44 +154,61 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     const int r = RECOMPUTE_Y ? (t == 0 ? K : t - 1) : t;
     return r < K ? sources + (b * K + r) * samples : mixture + b * samples;
   };
-  // start the copy of the NT frames of position q (or note that the warp must fill them itself: zero padding
-  // at the signal's ends, rows that are not 16-byte aligned)
-  auto start_signals = [&](int64_t q) {
-    if (q >= p_end) return;
-    const int64_t b = q / frames, m = q - b * frames;
-    if (m >= frames_of(b)) { sig_by_tma = false; return; }
-    const int64_t Tb = meta ? meta[2 * b] : samples;
-    const int64_t s0 = m * shift - pad_left;
-    bool bulk = s0 >= 0 && s0 + rf::kSize <= Tb;
+  // Per-example context (warp uniform), recomputed only when the example changes: the steady-state loop has no
+  // 64-bit multiplications or divisions.  Sample offsets fit 32 bits (checked by the launcher).
+  int64_t ctx_b = -1;
+  int ctx_T = 0, ctx_M = 0;
+  bool ctx_a16 = false;
+  const float* ctx_row[NT];
+  const float* ctx_mask = nullptr;
+  const float* ctx_y = nullptr;
+  auto set_ctx = [&](int64_t b) {
+    if (b == ctx_b) return;
+    ctx_b = b;
+    ctx_T = (int)(meta ? meta[2 * b] : samples);
+    ctx_M = (int)frames_of(b);
+    ctx_a16 = true;
 #pragma unroll
-    for (int t = 0; t < NT; ++t) bulk = bulk && (reinterpret_cast<uintptr_t>(signal_row(b, t) + s0) & 15) == 0;
+    for (int t = 0; t < NT; ++t) {
+      ctx_row[t] = signal_row(b, t);
+      ctx_a16 = ctx_a16 && (reinterpret_cast<uintptr_t>(ctx_row[t]) & 15) == 0;
+    }
+    ctx_mask = mask + b * frames * (K * F);
+    ctx_y = RECOMPUTE_Y ? nullptr : yabs + b * frames * F;
+  };
+  const int pad = (int)pad_left;
+  // start the copy of the NT frames of position q = (b, m) (TMA, or zero-filling cp.async for frames that touch
+  // the zero padding at the signal's ends or are not 16-byte aligned)
+  auto start_signals = [&](int64_t q, int64_t b, int m) {
+    if (q >= p_end) return;
+    set_ctx(b);
+    if (m >= ctx_M) { sig_by_tma = false; return; }
+    const int s0 = m * shift - pad;
+    const bool a16 = ctx_a16 && (s0 & 3) == 0;
+    const bool bulk = a16 && s0 >= 0 && s0 + rf::kSize <= ctx_T;
     sig_by_tma = bulk;
     if (bulk) {
       if (lane == 0) {
         fence_proxy_async();   // the frames were last read through the generic proxy
         mbar_expect_tx(bar_sig, NT * rf::kSize * 4u);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, signal_row(b, t) + s0, rf::kSize * 4u, bar_sig);
+        for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, ctx_row[t] + s0, rf::kSize * 4u, bar_sig);
       }
     } else {
-      // frames that touch the zero padding or are not 16-byte aligned: cp.async with zero fill (16-byte units
-      // when the rows allow it), just as asynchronous as the bulk copy (cp.async.wait_group before pass 1)
-      bool a16 = (s0 & 3) == 0;
-#pragma unroll
-      for (int t = 0; t < NT; ++t) a16 = a16 && (reinterpret_cast<uintptr_t>(signal_row(b, t)) & 15) == 0;
+      // just as asynchronous as the bulk copy (cp.async.wait_group before pass 1); 16-byte units when possible
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const float* xr = signal_row(b, t);
+        const float* xr = ctx_row[t];
         if (a16) {
           for (int c = lane; c < rf::kSize / 4; c += 32) {
-            const int64_t n = s0 + 4 * c;
-            const int bytes = n < 0 ? 0 : (int)max((int64_t)0, min((int64_t)4, Tb - n)) * 4;
+            const int n = s0 + 4 * c;
+            const int bytes = n < 0 ? 0 : max(0, min(4, ctx_T - n)) * 4;
             fft::cp_async_16(sig + t * rf::kSize + 4 * c, bytes ? xr + n : xr, bytes);
           }
         } else {
           for (int i = lane; i < rf::kSize; i += 32) {
-            const int64_t n = s0 + i;
-            const bool ok = n >= 0 && n < Tb;
+            const int n = s0 + i;
+            const bool ok = n >= 0 && n < ctx_T;
             fft::cp_async_4_zfill(sig + t * rf::kSize + i, ok ? xr + n : xr, ok ? 4 : 0);
           }
         }
@@ -204,12 +221,12 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   // copied and the row found at the source's misalignment inside the landing area.  The at most 12 bytes before
   // / after a row belong to the neighbouring rows or, at the very ends of the tensor, to the same (>= 256-byte
   // granular) allocation -- an address that is not 16-byte aligned is never at its edge.
-  auto start_rows = [&](int64_t q) {
+  auto start_rows = [&](int64_t q, int64_t b, int m) {
     if (q >= p_end) return;
-    const int64_t b = q / frames, m = q - b * frames;
-    if (m >= frames_of(b)) return;
-    const uintptr_t am = reinterpret_cast<uintptr_t>(mask + ((b * frames + m) * K) * F);
-    const uintptr_t ay = RECOMPUTE_Y ? 0 : reinterpret_cast<uintptr_t>(yabs + (b * frames + m) * F);
+    set_ctx(b);
+    if (m >= ctx_M) return;
+    const uintptr_t am = reinterpret_cast<uintptr_t>(ctx_mask + m * (K * F));
+    const uintptr_t ay = RECOMPUTE_Y ? 0 : reinterpret_cast<uintptr_t>(ctx_y + m * F);
     off_m = (int)(am & 15) >> 2;
     off_y = (int)(ay & 15) >> 2;
     if (lane == 0) {
@@ -281,21 +298,33 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     }
   };
 
-  start_signals(p_begin);
-  start_rows(p_begin);
+  // (example, frame) of the current and of the next position are tracked incrementally: no 64-bit divisions in
+  // the loop
+  int64_t b = p_begin / frames;
+  int m = (int)(p_begin - b * frames);
+  const int frames_i = (int)frames;
+  start_signals(p_begin, b, m);
+  // everything above is independent of the preceding kernel; |Y| (and, conservatively, the masks) are not
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  start_rows(p_begin, b, m);
   stamp(1);
-  int64_t b_cur = p_begin < p_end ? p_begin / frames : -1;
+  int64_t b_cur = p_begin < p_end ? b : -1;
   for (int64_t q = p_begin; q < p_end; ++q) {
     if (q == p_begin + 1) stamp(2);
     if (q == p_begin + 2) stamp(3);
-    const int64_t b = q / frames, m = q - b * frames;
+    // next position
+    int64_t bn = b;
+    int mn = m + 1;
+    if (mn == frames_i) { mn = 0; ++bn; }
     if (b != b_cur) {   // warp-uniform
       flush(b_cur);
       b_cur = b;
     }
-    if (m >= frames_of(b)) {   // position beyond this example's length (ragged batch): nothing to do
-      start_signals(q + 1);
-      start_rows(q + 1);
+    set_ctx(b);
+    if (m >= ctx_M) {   // position beyond this example's length (ragged batch): nothing to do
+      start_signals(q + 1, bn, mn);
+      start_rows(q + 1, bn, mn);
+      b = bn; m = mn;
       continue;
     }
     if (sig_by_tma) {
@@ -319,7 +348,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       float2 ya[2][8], yb[2][8];
       float ydc[2], ynyq[2];
       // the frames of the LAST transforms are in registers after pass 1: start the next position's copy
-      auto next_copy = [&]() { if (t + 2 >= NT) start_signals(q + 1); };
+      auto next_copy = [&]() { if (t + 2 >= NT) start_signals(q + 1, bn, mn); };
       rf::rfft_streams<2, false, false>(sig + t * rf::kSize, rf::kSize, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
       magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
       magnitudes(ya[1], yb[1], ydc[1], ynyq[1], x[t + 1]);
@@ -327,7 +356,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (NT & 1) {
       float2 ya[1][8], yb[1][8];
       float ydc[1], ynyq[1];
-      auto next_copy = [&]() { start_signals(q + 1); };
+      auto next_copy = [&]() { start_signals(q + 1, bn, mn); };
       rf::rfft_streams<1, false, false>(sig + (NT - 1) * rf::kSize, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
       magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[NT - 1]);
     }
@@ -358,7 +387,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       }
     }
     __syncwarp();   // every lane has read its rows: the area may be overwritten
-    start_rows(q + 1);
+    start_rows(q + 1, bn, mn);
+    b = bn; m = mn;
   }
   stamp(4);
   if (b_cur >= 0) flush(b_cur);
@@ -378,6 +408,8 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
   B2S_REQUIRE(plan->shift % 4 == 0, "the fused STFT->PIT kernel needs a shift that is a multiple of 4 (got %d)",
               plan->shift);
   B2S_REQUIRE(frames >= 1, "the fused STFT->PIT kernel needs at least one frame");
+  B2S_REQUIRE(samples < ((int64_t)1 << 30) && frames < ((int64_t)1 << 20) && pad_left < ((int64_t)1 << 30),
+              "signal too long for the fused STFT->PIT kernel (%lld samples)", (long long)samples);
   const int nt = yabs ? K : K + 1;
   const size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 4 * rf::kTile1 + row_area_floats(K));
   auto kernel = yabs ? stft_pit_fused_kernel<K, false> : stft_pit_fused_kernel<K, true>;
@@ -395,8 +427,25 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
     B2S_CUDA(cudaMalloc(&trace, nstamps * sizeof(unsigned long long)));
     B2S_CUDA(cudaMemsetAsync(trace, 0, nstamps * sizeof(unsigned long long), stream));
   }
-  kernel<<<g.grid, 32 * kFusedWarps, smem, stream>>>(mixture, yabs, sources, mask, meta, batch, samples, frames,
-      plan->shift, pad_left, plan->lane_fwd, g.slots, partial, counters, loss, perm, sse, trace);
+  // Programmatic dependent launch: the kernel may start while its predecessor in the stream (normally the STFT
+  // front-end that produces |Y|) drains -- constants, barriers and the first source frames do not depend on it;
+  // the kernel executes griddepcontrol.wait before it touches |Y|.  B2S_PDL=0 falls back to a plain launch.
+  static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.grid);
+  cfg.blockDim = dim3(32 * kFusedWarps);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  const int shift = plan->shift;
+  const float4* table = plan->lane_fwd;
+  const int slots = g.slots;
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, mixture, yabs, sources, mask, meta, batch, samples, frames, shift,
+                              pad_left, table, slots, partial, counters, loss, perm, sse, trace));
   B2S_LAUNCH_CHECK("stft_pit_fused_kernel");
   if (want_trace) {   // tuning aid: per-warp timeline statistics on stderr
     std::vector<unsigned long long> h(nstamps);

@@ -157,61 +157,76 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     tma::fence_mbar_init();
   }
   __syncwarp();
+  // a kernel launched with programmatic stream serialization behind this one (the fused loss) may start now
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
   k.load(lane_table, lane);
   constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
   const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
   const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
 
-  const int64_t units_per_row = ceil_div(frames, NS);
-  const int64_t total = rows * units_per_row;
-  const int64_t nwarps = (int64_t)gridDim.x * kPipeWarps;
+  // Units are enumerated as (row, index in row); a warp steps through them with a fixed stride, tracked
+  // incrementally: the steady-state loop has no divisions and one 64-bit multiplication.  Unit counts and
+  // sample offsets fit 32 bits (checked by the launcher).
+  const int upr = (int)ceil_div(frames, NS);                       // units per row
+  const int nwarps = (int)gridDim.x * kPipeWarps;
+  const int step_row = nwarps / upr, step_idx = nwarps - step_row * upr;
+  const int nrows_i = (int)rows, nsamples = (int)samples, pad = (int)pad_left;
+  struct Pos { int row, idx; };
+  auto advance = [&](Pos& p) {
+    p.row += step_row;
+    p.idx += step_idx;
+    if (p.idx >= upr) { p.idx -= upr; ++p.row; }
+  };
   unsigned parity = 0;      // bit i: phase of slot i's barrier the warp waits for next
   unsigned by_tma = 0;      // bit i: slot i is being filled by a bulk copy
 
-  // start filling `slot` with unit u (or remember that the warp has to fill it itself)
-  auto issue = [&](int64_t u, int slot) {
-    if (u < total) {
-    const int64_t row = u / units_per_row, m0 = (u - row * units_per_row) * NS;
-    const int64_t s0 = m0 * shift - pad_left;
-    const float* src = x + row * row_stride + s0;
-    const bool bulk = s0 >= 0 && s0 + span <= samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    by_tma = bulk ? (by_tma | (1u << slot)) : (by_tma & ~(1u << slot));
-    if (bulk) {
-      if (lane == 0) {
-        tma::fence_proxy_async();   // the slot was last read through the generic proxy
-        tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
-        tma::bulk_g2s(ring + slot * span, src, (unsigned)span * 4u, bar + slot);
-      }
-    } else {
-      // units that touch the zero padding or are not 16-byte aligned: cp.async with zero fill (16-byte units
-      // when the row allows it), just as asynchronous as the bulk copy (cp.async.wait_group before pass 1)
-      const float* xr = x + row * row_stride;
-      if ((s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
+  // start filling `slot` with the unit at p (TMA, or zero-filling cp.async for units that touch the zero padding
+  // or are not 16-byte aligned)
+  auto issue = [&](Pos p, int slot) {
+    if (p.row < nrows_i) {
+      const int s0 = p.idx * NS * shift - pad;
+      const float* xr = x + (int64_t)p.row * row_stride;
+      const bool a16 = (s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0;
+      const bool bulk = a16 && s0 >= 0 && s0 + span <= nsamples;
+      by_tma = bulk ? (by_tma | (1u << slot)) : (by_tma & ~(1u << slot));
+      if (bulk) {
+        if (lane == 0) {
+          tma::fence_proxy_async();   // the slot was last read through the generic proxy
+          tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
+          tma::bulk_g2s(ring + slot * span, xr + s0, (unsigned)span * 4u, bar + slot);
+        }
+      } else if (a16) {   // just as asynchronous as the bulk copy (cp.async.wait_group before pass 1)
         for (int c = lane; c < span / 4; c += 32) {
-          const int64_t n = s0 + 4 * c;
-          const int bytes = n < 0 ? 0 : (int)max((int64_t)0, min((int64_t)4, samples - n)) * 4;
+          const int n = s0 + 4 * c;
+          const int bytes = n < 0 ? 0 : max(0, min(4, nsamples - n)) * 4;
           fft::cp_async_16(ring + slot * span + 4 * c, bytes ? xr + n : xr, bytes);
         }
       } else {
         for (int i = lane; i < span; i += 32) {
-          const int64_t n = s0 + i;
-          const bool ok = n >= 0 && n < samples;
+          const int n = s0 + i;
+          const bool ok = n >= 0 && n < nsamples;
           fft::cp_async_4_zfill(ring + slot * span + i, ok ? xr + n : xr, ok ? 4 : 0);
         }
       }
     }
-    }
     fft::cp_async_commit();   // one (possibly empty) group per call keeps the wait_group counting uniform
   };
 
-  int64_t u = (int64_t)blockIdx.x * kPipeWarps + warp;
-#pragma unroll
-  for (int i = 0; i < (STAGES > 1 ? STAGES - 1 : 1); ++i) issue(u + i * nwarps, i);
-  for (int it = 0; u < total; u += nwarps, ++it) {
+  Pos cur;
+  {
+    const int u0 = (int)blockIdx.x * kPipeWarps + warp;
+    cur.row = u0 / upr;
+    cur.idx = u0 - cur.row * upr;
+  }
+  Pos nxt = cur;
+  issue(cur, 0);
+  for (int it = 0; cur.row < nrows_i; ++it) {
     const int slot = it % STAGES;
-    if (STAGES > 1) issue(u + (STAGES - 1) * nwarps, (it + STAGES - 1) % STAGES);
-    const int64_t row = u / units_per_row, m0 = (u - row * units_per_row) * NS;
+    advance(nxt);
+    if (STAGES > 1) issue(nxt, (it + 1) % STAGES);
+    const int row = cur.row, m0 = cur.idx * NS;
+    cur = nxt;
     float* buf = ring + slot * span;
     if (by_tma & (1u << slot)) {
       tma::mbar_wait(bar + slot, (parity >> slot) & 1u);
@@ -223,15 +238,15 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     }
     float2 ya[NS][8], yb[NS][8];
     float ydc[NS], ynyq[NS];
-    auto next_copy = [&]() { if (STAGES == 1) issue(u + nwarps, 0); };
+    auto next_copy = [&]() { if (STAGES == 1) issue(nxt, 0); };
     rf::rfft_streams<NS, SHIFT256 && (NS > 1), DOUBLE_INTERIOR>(buf, shift, tile, k, ya, yb, ydc, ynyq, ablate, next_copy);
     if (ablate & 1) continue;   // experiments: no output at all
     // The spectrum rows of the unit are adjacent in global memory.  They are assembled in shared memory at
     // the global address's phase within 16 bytes and leave as ONE asynchronous TMA bulk store (plus at most 3
     // floats at either end from lanes): per-lane STG of rows that are only 4-byte aligned costs several LSU
     // cycles per touched line and blocks the shared-memory traffic of the whole SM behind it.
-    const int nrows = (int)min((int64_t)NS, frames - m0);
-    float* g = out + (row * frames + m0) * kOutPerFrame;
+    const int nrows = min(NS, (int)frames - m0);
+    float* g = out + ((int64_t)row * frames + m0) * kOutPerFrame;
     const int phase = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
     if (lane == 0) tma::bulk_wait_read<0>();   // the previous unit's store has read the staging rows
     __syncwarp();
@@ -502,6 +517,9 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
     const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
     B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
     const int64_t units = rows * ceil_div(frames, kPipeFrames);
+    B2S_REQUIRE(units < ((int64_t)1 << 30) && samples < ((int64_t)1 << 30) && pad_left < ((int64_t)1 << 30),
+                "signal too large for the STFT warp kernel (%lld units of %lld samples)", (long long)units,
+                (long long)samples);
     const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * kPipeCtasPerSm);
     const int span = (kPipeFrames - 1) * plan->shift + fft::kSize;
     const int out_area = (kPipeFrames * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
