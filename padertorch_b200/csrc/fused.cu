@@ -490,6 +490,18 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
       bmin = std::min(bmin, s4 / kFusedWarps); bmax = std::max(bmax, s4 / kFusedWarps);
     }
     fprintf(stderr, "  per-block mean loop duration: min %.1f max %.1f us\n", bmin, bmax);
+    // loop duration by kind of range: with / without frames that touch the zero padding (first / last 3 frames)
+    double se = 0, sn = 0; size_t ne = 0, nn = 0;
+    for (int64_t w = 0; w < g.warps; ++w) {
+      if (!h[w * 8 + 4]) continue;
+      const int64_t pb = w * g.total / g.warps, pe = (w + 1) * g.total / g.warps;
+      bool edge = false;
+      for (int64_t q = pb; q < pe; ++q) { const int64_t m = q % frames; edge = edge || m < 3 || m >= frames - 3; }
+      const double d = (double)(h[w * 8 + 4] - h[w * 8 + 1]) * 1e-3;
+      if (edge) { se += d; ++ne; } else { sn += d; ++nn; }
+    }
+    fprintf(stderr, "  mean loop duration: %zu warps with edge frames %.1f us, %zu without %.1f us\n", ne, ne ? se / ne : 0.0,
+            nn, nn ? sn / nn : 0.0);
   }
   return B2S_OK;
 }
