@@ -166,14 +166,23 @@ B2S_API int b2s_pair_stats_forward(const float* estimate, const float* target, c
 B2S_API int b2s_pair_loss(const double* stats, const int64_t* meta, int64_t groups, int64_t inner,
                   int sources, int kind, int flags, double tau, int reduction, int pit, float* loss,
                   int32_t* perm, b2s_stream stream);
-/* grad_estimate[row i of group g] = grad_loss[.] * dl/de_i for the pairing the forward chose
- * (perm NULL: identity).  grad_loss indexes examples (pit) or rows (pit == 0).                     */
+/* `count` (<= B2S_MAX_LOSS_SET) PIT losses of the same statistics in one launch, plus their batch means
+ * (TasNet.loss, tasnet/model.py:154-176: three loss functions per step, each averaged over the batch):
+ * loss [count][examples], perm [count][examples][K], mean [count] = mean over examples of loss[c].
+ * kinds / reductions: HOST arrays.                                                                 */
+#define B2S_MAX_LOSS_SET 8
+B2S_API int b2s_pair_loss_set(const double* stats, const int64_t* meta, int64_t groups, int64_t inner,
+                      int sources, int count, const int* kinds, const int* reductions, int flags,
+                      double tau, float* loss, int32_t* perm, float* mean, b2s_stream stream);
+/* grad_estimate[row i of group g] = grad_scale * grad_loss[. * grad_loss_stride] * dl/de_i for the
+ * pairing the forward chose (perm NULL: identity).  grad_loss indexes examples (pit) or rows
+ * (pit == 0); stride 0 broadcasts one upstream value (the gradient of a batch mean: scale 1/B).    */
 B2S_API int b2s_pair_backward(const float* estimate, const float* target, const int64_t* meta,
                       int64_t groups, int64_t inner, int64_t max_length, int sources,
                       int64_t estimate_source_stride, int64_t target_source_stride,
                       const double* stats, int kind, int flags, double tau, int reduction, int pit,
-                      const int32_t* perm, const float* grad_loss, float* grad_estimate,
-                      b2s_stream stream);
+                      const int32_t* perm, const float* grad_loss, int64_t grad_loss_stride,
+                      double grad_scale, float* grad_estimate, b2s_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Deep-clustering affinity loss, deep_clustering_loss (padertorch/ops/losses/source_separation.py:

@@ -10,6 +10,7 @@
 // permutations and all loss kinds.  The gradient is a per-row affine map a e_i + b t_k + c.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "perm.cuh"
@@ -24,7 +25,11 @@ constexpr double kLn10 = 2.302585092994045684;
 __host__ __device__ inline int stats_per_group(int K) { return K * K + 4 * K; }
 
 int pair_chunks(int64_t groups, int64_t max_length) {
-  const int64_t capacity = (int64_t)kNumSMs * (2048 / kStatsThreads);
+  // 2 CTAs of 256 threads per SM, each thread with 4K 16-byte loads in flight, cover the latency-bandwidth
+  // product; more CTAs only shorten the per-thread loops and multiply the reduction epilogues (measured: 2 / 4 / 8
+  // CTAs per SM -> 27.0 / 28.6 / 35.8 us for the TasNet forward at batch 64 x 2 x 4 s)
+  static const int per_sm = [] { const char* e = getenv("B2S_PAIR_CTAS"); return e ? std::max(1, atoi(e)) : 2; }();
+  const int64_t capacity = (int64_t)kNumSMs * per_sm;
   int64_t c = capacity / std::max<int64_t>(1, groups);
   const int64_t most = std::max<int64_t>(1, max_length / (kStatsThreads * 8));
   return (int)std::max<int64_t>(1, std::min<int64_t>(c, most));
@@ -59,7 +64,65 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
       acc[K * K + 3 * K + i] += td[i];
     }
   };
-  int64_t n = n0 + threadIdx.x;
+  // rows that start at 16-byte aligned addresses are read with 16-byte loads, two per row in flight; whole
+  // float4 units are split over the chunks, the T % 4 tail samples belong to the last chunk
+  const bool vec = ((reinterpret_cast<uintptr_t>(e_) | reinterpret_cast<uintptr_t>(t_)) & 15) == 0 &&
+                   (est_stride & 3) == 0 && (tgt_stride & 3) == 0;
+  if (vec) {
+    const int64_t nv = T >> 2;
+    const int64_t v0 = nv * chunk / nchunks, v1 = nv * (chunk + 1) / nchunks;
+    const float4* e4 = reinterpret_cast<const float4*>(e_);
+    const float4* t4 = reinterpret_cast<const float4*>(t_);
+    const int64_t es4 = est_stride >> 2, ts4 = tgt_stride >> 2;
+    auto fold4 = [&](const float4 (&e)[K], const float4 (&t)[K]) {
+      float a[K], b[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) { a[i] = e[i].x; b[i] = t[i].x; }
+      fold(a, b);
+#pragma unroll
+      for (int i = 0; i < K; ++i) { a[i] = e[i].y; b[i] = t[i].y; }
+      fold(a, b);
+#pragma unroll
+      for (int i = 0; i < K; ++i) { a[i] = e[i].z; b[i] = t[i].z; }
+      fold(a, b);
+#pragma unroll
+      for (int i = 0; i < K; ++i) { a[i] = e[i].w; b[i] = t[i].w; }
+      fold(a, b);
+    };
+    int64_t v = v0 + threadIdx.x;
+    for (; K <= 3 && v + kStatsThreads < v1; v += 2 * kStatsThreads) {   // (register budget: K <= 3 only)
+      float4 ea[K], ta[K], eb[K], tb[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        ea[i] = __ldg(e4 + i * es4 + v);
+        ta[i] = __ldg(t4 + i * ts4 + v);
+        eb[i] = __ldg(e4 + i * es4 + v + kStatsThreads);
+        tb[i] = __ldg(t4 + i * ts4 + v + kStatsThreads);
+      }
+      fold4(ea, ta);
+      fold4(eb, tb);
+    }
+    for (; v < v1; v += kStatsThreads) {
+      float4 ea[K], ta[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        ea[i] = __ldg(e4 + i * es4 + v);
+        ta[i] = __ldg(t4 + i * ts4 + v);
+      }
+      fold4(ea, ta);
+    }
+    if (chunk == nchunks - 1 && (nv << 2) + threadIdx.x < T) {
+      const int64_t n = (nv << 2) + threadIdx.x;
+      float e0[K], t0[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        e0[i] = __ldg(e_ + i * est_stride + n);
+        t0[i] = __ldg(t_ + i * tgt_stride + n);
+      }
+      fold(e0, t0);
+    }
+  }
+  int64_t n = vec ? n1 : n0 + threadIdx.x;
   for (; n + kStatsThreads < n1; n += 2 * kStatsThreads) {  // two samples in flight per row
     float e0[K], t0[K], e1[K], t1[K];
 #pragma unroll
@@ -230,13 +293,96 @@ pair_loss_kernel(const double* __restrict__ stats, const int64_t* __restrict__ m
   }
 }
 
+// Several PIT losses of the same statistics in ONE launch, plus their batch means (TasNet.loss evaluates
+// three loss functions per step and averages each over the batch: 3 x (loss kernel + mean kernel) otherwise).
+// CTA = loss kind; thread = example (K <= 4: the K! <= 24 assignments are walked serially in itertools order).
+struct LossSet { int n; int kind[B2S_MAX_LOSS_SET]; int reduction[B2S_MAX_LOSS_SET]; };
+
+template <int K>
+__global__ void __launch_bounds__(256)
+pair_loss_set_kernel(const double* __restrict__ stats, const int64_t* __restrict__ meta, int64_t examples,
+                     int64_t inner, LossSet set, int flags, double tau, float* __restrict__ loss,
+                     int32_t* __restrict__ perm, float* __restrict__ mean) {
+  constexpr int NV = K * K + 4 * K;
+  __shared__ double red[256];
+  const int which = blockIdx.x, kind = set.kind[which], reduction = set.reduction[which];
+  double local = 0.0;
+  for (int64_t ex = threadIdx.x; ex < examples; ex += blockDim.x) {
+    double cost[K * K];
+#pragma unroll
+    for (int ij = 0; ij < K * K; ++ij) cost[ij] = 0.0;
+    for (int64_t c = 0; c < inner; ++c) {  // fixed order
+      const int64_t g = ex * inner + c;
+      const double* s = stats + g * NV;
+      const double T = (double)meta[g * B2S_PAIR_META];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+          cost[i * K + j] += eval_pair(kind, flags, tau, T, s[K * K + i], s[i * K + j], s[K * K + K + j],
+                                       s[K * K + 2 * K + i], s[K * K + 3 * K + j]).value;
+    }
+    int p[K], bp[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { p[k] = k; bp[k] = k; }
+    double best = 0.0;
+    int idx = 0;
+    do {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) if (p[k] == i) v += cost[i * K + k];
+      }
+      if (idx == 0 || candidate_better(v, idx, best, 0)) {   // strictly better only: the first minimum wins
+        best = v;
+#pragma unroll
+        for (int k = 0; k < K; ++k) bp[k] = p[k];
+      }
+      ++idx;
+    } while (next_permutation(p, K));
+    if (reduction == B2S_REDUCE_MEAN) best /= (double)(K * inner);
+    const float out = (float)best;
+    loss[which * examples + ex] = out;
+#pragma unroll
+    for (int k = 0; k < K; ++k) perm[(which * examples + ex) * K + k] = bp[k];
+    local += (double)out;
+  }
+  // batch mean, fixed order: thread partials (examples tid, tid + 256, ...) summed by thread 0 in thread order
+  red[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s8 = 0.0;
+    for (int j = 0; j < 8; ++j) s8 += red[threadIdx.x * 8 + j];
+    s8 = warp_sum(s8);
+    if (threadIdx.x == 0) mean[which] = (float)(s8 / (double)examples);
+  }
+}
+
+// fallback for K > 4: mean of each row of loss [n][examples], one CTA per row, fixed order
+__global__ void __launch_bounds__(256)
+row_mean_kernel(const float* __restrict__ loss, int64_t examples, float* __restrict__ mean) {
+  __shared__ double red[256];
+  double local = 0.0;
+  for (int64_t ex = threadIdx.x; ex < examples; ex += blockDim.x) local += (double)loss[blockIdx.x * examples + ex];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s8 = 0.0;
+    for (int j = 0; j < 8; ++j) s8 += red[threadIdx.x * 8 + j];
+    s8 = warp_sum(s8);
+    if (threadIdx.x == 0) mean[blockIdx.x] = (float)(s8 / (double)examples);
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kStatsThreads)
 pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
                      const int64_t* __restrict__ meta, int nchunks, int64_t inner, int64_t est_stride,
                      int64_t tgt_stride, const double* __restrict__ stats, int kind, int flags, double tau,
                      int reduction, int pit, const int32_t* __restrict__ perm,
-                     const float* __restrict__ grad_loss, float* __restrict__ grad_est) {
+                     const float* __restrict__ grad_loss, int64_t grad_stride, double grad_scale,
+                     float* __restrict__ grad_est) {
   constexpr int NV = K * K + 4 * K;
   __shared__ float ca[K], cb[K], cc[K];
   __shared__ int match[K];  // target index matched to estimate row i
@@ -266,16 +412,16 @@ pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tg
       }
       if (tau >= 0.0) sn += tau * st;
       dEe = 10.0 / (kLn10 * sn); dD = -2.0 * dEe;
-      up = (double)grad_loss[ex];
+      up = grad_scale * (double)grad_loss[ex * grad_stride];
     } else {
       const PairEval r = eval_pair(kind, flags, tau, (double)T, s[K * K + i], s[i * K + k], s[K * K + K + k],
                                    s[K * K + 2 * K + i], s[K * K + 3 * K + k]);
       dEe = r.dEe; dD = r.dD; dSe = r.dSe;
       if (pit) {
-        up = (double)grad_loss[ex];
+        up = grad_scale * (double)grad_loss[ex * grad_stride];
         if (reduction == B2S_REDUCE_MEAN) up /= (double)(K * inner);
       } else {
-        up = (double)grad_loss[(int64_t)g * K + i];
+        up = grad_scale * (double)grad_loss[((int64_t)g * K + i) * grad_stride];
       }
     }
     ca[i] = (float)(up * 2.0 * dEe);
@@ -284,7 +430,41 @@ pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tg
     match[i] = k;
   }
   __syncthreads();
-  const int64_t n0 = T * chunk / nchunks, n1 = T * (chunk + 1) / nchunks;
+  const bool vec = ((reinterpret_cast<uintptr_t>(e_) | reinterpret_cast<uintptr_t>(t_) |
+                     reinterpret_cast<uintptr_t>(g_)) & 15) == 0 && (est_stride & 3) == 0 && (tgt_stride & 3) == 0;
+  if (vec) {   // 16-byte loads and stores; the T % 4 tail samples belong to the last chunk
+    const int64_t nv = T >> 2;
+    const int64_t v0 = nv * chunk / nchunks, v1 = nv * (chunk + 1) / nchunks;
+    const float4* e4 = reinterpret_cast<const float4*>(e_);
+    const float4* t4 = reinterpret_cast<const float4*>(t_);
+    float4* g4 = reinterpret_cast<float4*>(g_);
+    const int64_t es4 = est_stride >> 2, ts4 = tgt_stride >> 2;
+    float a[K], bm[K], c[K];
+    int mt[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) { a[i] = ca[i]; bm[i] = cb[i]; c[i] = cc[i]; mt[i] = match[i]; }
+    for (int64_t v = v0 + threadIdx.x; v < v1; v += kStatsThreads) {
+      float4 t[K], e[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = __ldg(t4 + k * ts4 + v);
+#pragma unroll
+      for (int i = 0; i < K; ++i) e[i] = __ldg(e4 + i * es4 + v);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        float4 tm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (mt[i] == k) tm = t[k];
+        float4 o;
+        o.x = fmaf(a[i], e[i].x, fmaf(bm[i], tm.x, c[i]));
+        o.y = fmaf(a[i], e[i].y, fmaf(bm[i], tm.y, c[i]));
+        o.z = fmaf(a[i], e[i].z, fmaf(bm[i], tm.z, c[i]));
+        o.w = fmaf(a[i], e[i].w, fmaf(bm[i], tm.w, c[i]));
+        g4[i * es4 + v] = o;
+      }
+    }
+    if (chunk != nchunks - 1) return;
+  }
+  const int64_t n0 = vec ? (T & ~(int64_t)3) : T * chunk / nchunks, n1 = vec ? T : T * (chunk + 1) / nchunks;
   for (int64_t n = n0 + threadIdx.x; n < n1; n += kStatsThreads) {
     float t[K];
 #pragma unroll
@@ -361,22 +541,68 @@ int b2s_pair_loss(const double* stats, const int64_t* meta, int64_t groups, int6
   return B2S_OK;
 }
 
+int b2s_pair_loss_set(const double* stats, const int64_t* meta, int64_t groups, int64_t inner, int sources,
+                      int count, const int* kinds, const int* reductions, int flags, double tau, float* loss,
+                      int32_t* perm, float* mean, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
+  B2S_REQUIRE(count >= 1 && count <= B2S_MAX_LOSS_SET && kinds && reductions, "1..%d loss kinds per set (got %d)",
+              B2S_MAX_LOSS_SET, count);
+  B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
+  LossSet set;
+  set.n = count;
+  for (int i = 0; i < count; ++i) {
+    B2S_REQUIRE(kinds[i] >= B2S_LOSS_MSE && kinds[i] < B2S_LOSS_SA_SDR, "loss kind %d has no PIT variant", kinds[i]);
+    B2S_REQUIRE(reductions[i] == B2S_REDUCE_SUM || reductions[i] == B2S_REDUCE_MEAN, "PIT needs reduction sum or mean");
+    B2S_REQUIRE(!(flags & B2S_FLAG_OFFSET_INVARIANT) || kinds[i] == B2S_LOSS_SI_SDR,
+                "offset_invariant exists for si_sdr only");
+    set.kind[i] = kinds[i];
+    set.reduction[i] = reductions[i];
+  }
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(stats && meta && loss && perm && mean, "NULL device pointer");
+  const int64_t examples = groups / inner;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sources <= 4) {
+#define CALL(K) pair_loss_set_kernel<K><<<count, 256, 0, st>>>(stats, meta, examples, inner, set, flags, tau, loss, perm, mean)
+    switch (sources) {
+      case 1: CALL(1); break;
+      case 2: CALL(2); break;
+      case 3: CALL(3); break;
+      default: CALL(4); break;
+    }
+#undef CALL
+    B2S_LAUNCH_CHECK("pair_loss_set_kernel");
+  } else {
+    for (int i = 0; i < count; ++i) {
+      pair_loss_kernel<<<(unsigned)examples, 128, 0, st>>>(stats, meta, inner, sources, set.kind[i], flags, tau,
+                                                            set.reduction[i], 1, loss + i * examples,
+                                                            perm + i * examples * sources);
+      B2S_LAUNCH_CHECK("pair_loss_kernel");
+    }
+    row_mean_kernel<<<count, 256, 0, st>>>(loss, examples, mean);
+    B2S_LAUNCH_CHECK("row_mean_kernel");
+  }
+  return B2S_OK;
+}
+
 int b2s_pair_backward(const float* estimate, const float* target, const int64_t* meta, int64_t groups,
                       int64_t inner, int64_t max_length, int sources, int64_t estimate_source_stride,
                       int64_t target_source_stride, const double* stats, int kind, int flags, double tau,
                       int reduction, int pit, const int32_t* perm, const float* grad_loss,
-                      float* grad_estimate, b2s_stream stream) {
+                      int64_t grad_loss_stride, double grad_scale, float* grad_estimate, b2s_stream stream) {
   B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
   B2S_REQUIRE(kind >= B2S_LOSS_MSE && kind <= B2S_LOSS_SA_SDR, "unknown loss kind %d", kind);
   B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
   if (groups == 0) return B2S_OK;
   B2S_REQUIRE(estimate && target && meta && stats && grad_loss && grad_estimate, "NULL device pointer");
-  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_length / (kStatsThreads * 4) + 1, 64));
+  // about 8 CTAs per SM in one wave; at least 2 float4 units per thread and chunk
+  const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / groups);
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_length / (kStatsThreads * 8) + 1, std::min<int64_t>(want, 4096)));
   const dim3 grid((unsigned)groups, chunks);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(K) pair_backward_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
       inner, estimate_source_stride, target_source_stride, stats, kind, flags, tau, reduction, pit, perm, \
-      grad_loss, grad_estimate)
+      grad_loss, grad_loss_stride, grad_scale, grad_estimate)
   switch (sources) {
     case 1: CALL(1); break;
     case 2: CALL(2); break;

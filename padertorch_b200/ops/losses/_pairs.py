@@ -1,5 +1,7 @@
 """Shared driver of the pair-statistics kernels (b2s_pair_stats_forward / b2s_pair_loss /
 b2s_pair_backward): every time-domain regression loss and its PIT variant goes through here."""
+import ctypes
+
 import torch
 
 from ... import _lib
@@ -54,19 +56,43 @@ class PairProblem:
             _lib.check(rc, 'b2s_pair_loss')
         return loss, perm
 
-    def backward(self, stats, kind, flags, tau, reduction, pit, perm, grad_loss):
+    def loss_set(self, stats, kinds, reductions, flags=0, tau=-1.0):
+        """Several PIT losses and their batch means in one launch: (loss [n, examples],
+        perm [n, examples, K], mean [n])."""
+        lib = _lib.load()
+        device = self.estimate.device
+        examples = self.groups // self.inner
+        n = len(kinds)
+        loss = torch.empty((n, examples), dtype=torch.float32, device=device)
+        perm = torch.empty((n, examples, self.k), dtype=torch.int32, device=device)
+        mean = torch.full((n,), float('nan'), dtype=torch.float32, device=device) if not self.groups else \
+            torch.empty(n, dtype=torch.float32, device=device)
+        if self.groups:
+            c_kinds = (ctypes.c_int * n)(*kinds)
+            c_reductions = (ctypes.c_int * n)(*reductions)
+            with torch.cuda.device(device):
+                rc = lib.b2s_pair_loss_set(_lib.ptr(stats), _lib.ptr(self.meta), self.groups, self.inner,
+                                           self.k, n, c_kinds, c_reductions, flags, tau, _lib.ptr(loss),
+                                           _lib.ptr(perm), _lib.ptr(mean), _lib.stream_of(device))
+            _lib.check(rc, 'b2s_pair_loss_set')
+        return loss, perm, mean
+
+    def backward(self, stats, kind, flags, tau, reduction, pit, perm, grad_loss, broadcast_scale=None):
+        """broadcast_scale: `grad_loss` is ONE upstream value (the gradient of a batch mean) applied to
+        every example times this factor."""
         lib = _lib.load()
         device = self.estimate.device
         # padding beyond each length must stay zero; dense problems are overwritten completely
         grad = torch.empty_like(self.estimate) if self.covers_all and self.groups else torch.zeros_like(self.estimate)
         if self.groups:
             grad_loss = grad_loss.to(torch.float32).contiguous()
+            stride, scale = (1, 1.0) if broadcast_scale is None else (0, float(broadcast_scale))
             with torch.cuda.device(device):
                 rc = lib.b2s_pair_backward(
                     _lib.ptr(self.estimate), _lib.ptr(self.target), _lib.ptr(self.meta), self.groups,
                     self.inner, self.max_length, self.k, self.est_stride, self.tgt_stride,
                     _lib.ptr(stats), kind, flags, tau, reduction, int(pit), _lib.ptr(perm),
-                    _lib.ptr(grad_loss), _lib.ptr(grad), _lib.stream_of(device))
+                    _lib.ptr(grad_loss), stride, scale, _lib.ptr(grad), _lib.stream_of(device))
             _lib.check(rc, 'b2s_pair_backward')
         return grad
 

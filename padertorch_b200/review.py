@@ -120,23 +120,23 @@ class _TasnetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, estimate, problem, names):
         stats = problem.stats()
-        outs, perms = [], []
-        for name in names:
-            kind, reduction = _TASNET_KINDS[name]
-            loss, perm = problem.loss(stats, kind, 0, -1.0, reduction, True)
-            outs.append(loss)
-            perms.append(perm)
+        kinds = [_TASNET_KINDS[name][0] for name in names]
+        reductions = [_TASNET_KINDS[name][1] for name in names]
+        _, perms, means = problem.loss_set(stats, kinds, reductions)   # two launches for the whole forward
         ctx.problem, ctx.stats, ctx.perms, ctx.names = problem, stats, perms, names
-        return tuple(outs)
+        ctx.set_materialize_grads(False)   # losses without a weight get no backward pass
+        return tuple(means[i] for i in range(len(names)))
 
     @staticmethod
     def backward(ctx, *grads):
         total = None
-        for name, perm, grad in zip(ctx.names, ctx.perms, grads):
+        examples = ctx.problem.groups // ctx.problem.inner
+        for i, (name, grad) in enumerate(zip(ctx.names, grads)):
             if grad is None:
                 continue
             kind, reduction = _TASNET_KINDS[name]
-            g = ctx.problem.backward(ctx.stats, kind, 0, -1.0, reduction, True, perm, grad)
+            g = ctx.problem.backward(ctx.stats, kind, 0, -1.0, reduction, True, ctx.perms[i], grad.reshape(1),
+                                     broadcast_scale=1.0 / examples)
             total = g if total is None else total + g
         return total, None, None
 
@@ -157,7 +157,7 @@ def tasnet_losses(estimates, targets, num_samples, names=('si-sdr', 'log-mse', '
     problem = _pairs.PairProblem(e, t, meta, batch, 1, k, max(num_samples), length, length,
                                  covers_all=all(n == length for n in num_samples))
     values = _TasnetFunction.apply(e, problem, tuple(names))
-    return {name: v.mean() for name, v in zip(names, values)}
+    return dict(zip(names, values))
 
 
 def stft_mask_pit_step(mixture, sources, masks, stft=None, observation_abs=None, num_samples=None):
