@@ -9,8 +9,10 @@
 // point tiles, so the repeated channel reads hit L1.  fp32 FFMA on CUDA cores: 5.5 FLOP/B keeps this
 // HBM-bound, tensor cores would need a 3x split to hold fp32 accuracy and lose to the padding.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 using namespace b2s;
 
@@ -264,6 +266,135 @@ dc_gram_tiled_kernel(const float* __restrict__ emb, const float* __restrict__ tg
   dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
 }
 
+// ------------------------------------------------------------------------------------------- frame-tiled Gram
+// Fast path for the model's contiguous 't e f' layout (channel stride = bins, bin stride 1) with E + K <= 24:
+// the [E][F] embedding block and the [K][F] target block of one frame are each ONE contiguous span of global
+// memory, fetched by one TMA bulk copy each (cp.async.bulk -> mbarrier; the enclosing 16-byte aligned range
+// lands in shared memory, the block sits at the source's misalignment), double buffered per CTA.  Each of the 6
+// warps owns one 8 x 8 block pair; lanes own consecutive bins, so every operand is a conflict-free LDS.32
+// whatever the rows' alignment.  Replaces 2816 four-byte cp.async per 128 points (about 8 LSU cycles per warp
+// instruction: the copy, not the arithmetic, bounded the tiled kernel) by two descriptor-less bulk copies.
+constexpr int kFrWarps = 6;
+__host__ __device__ inline int frame_area(int rows, int F) { return (rows * F + 3 + 3) / 4 * 4 + 32; }
+
+__global__ void __launch_bounds__(32 * kFrWarps, 2)
+dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                     const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F, int E,
+                     int K, double* __restrict__ partial, int* __restrict__ counters,
+                     double* __restrict__ gram, float* __restrict__ loss) {
+  extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] frame buffers, then a row of zeros
+  __shared__ __align__(8) uint64_t full[2];
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = E + K;
+  const int area_e = frame_area(E, F), area_t = frame_area(K, F), buf_floats = area_e + area_t;
+  float* zrow = fsm + 2 * buf_floats;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  const int64_t N = T * F;
+  const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
+  for (int i = threadIdx.x; i < (F + 31) / 32 * 32; i += blockDim.x) zrow[i] = 0.f;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int s) {   // thread 0
+    const uintptr_t ae = reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t);
+    const uintptr_t at = reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t);
+    const unsigned be = (unsigned)(((ae & 15) + (size_t)E * F * 4 + 15) & ~(size_t)15);
+    const unsigned bt = (unsigned)(((at & 15) + (size_t)K * F * 4 + 15) & ~(size_t)15);
+    tma::fence_proxy_async();   // the buffer was last read through the generic proxy
+    tma::mbar_expect_tx(&full[s], be + bt);
+    tma::bulk_g2s(fsm + s * buf_floats, reinterpret_cast<const void*>(ae & ~(uintptr_t)15), be, &full[s]);
+    tma::bulk_g2s(fsm + s * buf_floats + area_e, reinterpret_cast<const void*>(at & ~(uintptr_t)15), bt, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    if (t0 < t1) issue(t0, 0);
+    if (t0 + 1 < t1) issue(t0 + 1, 1);
+  }
+  // this warp's block pair (ba <= bb) of the 3 x 3 upper triangle: 00 01 02 11 12 22
+  const int ba = warp < 3 ? 0 : (warp < 5 ? 1 : 2);
+  const int bb = warp < 3 ? warp : (warp < 5 ? warp - 2 : 2);
+  const bool active = ba * BS < C && bb * BS < C;
+  const bool diag = ba == bb;
+  float acc[BS][BS];
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
+
+  const int full_steps = F / 32;
+  for (int t = t0; t < t1; ++t) {
+    const int s = (t - t0) & 1;
+    tma::mbar_wait(&full[s], (unsigned)((t - t0) >> 1) & 1u);
+    if (active) {
+      const float* be_ = fsm + s * buf_floats + (int)((reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t) & 15) >> 2);
+      const float* bt_ = fsm + s * buf_floats + area_e + (int)((reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t) & 15) >> 2);
+      const float* ra[BS]; const float* rb[BS];
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        const int ca = ba * BS + i, cb = bb * BS + i;
+        ra[i] = (ca < E ? be_ + ca * F : (ca < C ? bt_ + (ca - E) * F : zrow)) + lane;
+        rb[i] = (cb < E ? be_ + cb * F : (cb < C ? bt_ + (cb - E) * F : zrow)) + lane;
+      }
+      // full steps of 32 bins without predicates; diagonal blocks accumulate their upper triangle only
+      if (diag) {
+#pragma unroll 4
+        for (int j = 0; j < full_steps; ++j) {
+          float va[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) va[i] = ra[i][32 * j];
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int jj = i; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], va[jj], acc[i][jj]);
+        }
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < full_steps; ++j) {
+          float va[BS], vb[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) va[i] = ra[i][32 * j];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) vb[i] = rb[i][32 * j];
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int jj = 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
+        }
+      }
+      if (lane + 32 * full_steps < F) {   // the F % 32 last bins
+        float va[BS], vb[BS];
+#pragma unroll
+        for (int i = 0; i < BS; ++i) { va[i] = ra[i][32 * full_steps]; vb[i] = rb[i][32 * full_steps]; }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int jj = 0; jj < BS; ++jj)
+            if (!diag || jj >= i) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
+      }
+    }
+    __syncthreads();   // every warp is done with buffer s
+    if (threadIdx.x == 0 && t + 2 < t1) issue(t + 2, s);
+  }
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * kTC * kTC;
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      if (diag && j < i) continue;   // (warp-uniform) the lower triangle of a diagonal block is its mirror image
+      const float sum = warp_sum(acc[i][j]);
+      if (lane == 0) {
+        mine[(ba * BS + i) * kTC + bb * BS + j] = (double)sum;
+        mine[(bb * BS + j) * kTC + ba * BS + i] = (double)sum;
+      }
+    }
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
+}
+
 // grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
 // Thread = 2 points x one block of 8 output channels; the coefficient matrix sits in shared memory.
 __global__ void __launch_bounds__(256)
@@ -447,7 +578,25 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
   int* counters = ws_counters(workspace);
   const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
   const Strides st{target_strides[0], target_strides[1], target_strides[2]};
-  if (g.tiled) {
+  const size_t frame_smem = sizeof(float) * (2 * (frame_area(embedding_dim, (int)bins) + frame_area(sources, (int)bins)) +
+                                            (bins + 31) / 32 * 32);
+  static const bool no_frame = getenv("B2S_DC_NO_FRAME") != nullptr;
+  if (g.tiled && !no_frame && se.c == bins && st.c == bins && frame_smem <= 100 * 1024 && max_frames < (1 << 30) &&
+      bins < (1 << 20)) {
+    static bool configured[64] = {};
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured[dev & 63] = true;
+    }
+    // frames are split over about two CTAs per SM (each double-buffers whole frames)
+    int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 4),
+                                                             (int64_t)kNumSMs * 2 / std::max<int64_t>(1, batch)));
+    nchunks = std::min(nchunks, g.nchunks);   // the workspace is sized for g.nchunks partial matrices
+    dc_gram_frame_kernel<<<dim3((unsigned)batch, nchunks), 32 * kFrWarps, frame_smem, (cudaStream_t)stream>>>(
+        embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss);
+  } else if (g.tiled) {
     dc_gram_tiled_kernel<<<dim3((unsigned)batch, g.nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
         embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, partial, counters, gram, loss);
   } else {
