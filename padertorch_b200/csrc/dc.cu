@@ -550,6 +550,150 @@ dc_backward_tiled_kernel(const float* __restrict__ emb, const float* __restrict_
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------- frame-tiled backward
+// grad[p][e] = sum_c z[p][c] * coef[c][e] for the contiguous 't e f' layout: the frame's [E][F] / [K][F] blocks
+// arrive by TMA bulk copies exactly as in dc_gram_frame_kernel (double buffered), the frame's [E][F] gradient
+// block is assembled in shared memory at the destination's phase within 16 bytes and leaves as ONE TMA bulk
+// store (double buffered; per-lane STG of rows that are only 4-byte aligned is several times slower).
+// Warp = (output group of 5 channels, half of the frame's 64-bin steps): its 5 x C coefficients stay in
+// registers, lanes own bins, two bins per lane in flight.  One CTA per SM.
+constexpr int kFbOut = 5;
+
+// FT / ET / KT != 0: bins / embedding channels / sources known at compile time (the reference's deep-clustering
+// configuration 513 / 20 / 2): every shared-memory access of the inner loops becomes base register + immediate.
+template <int FT, int ET, int KT>
+__global__ void __launch_bounds__(320, 1)
+dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                         const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
+                         int K_rt, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                         float* __restrict__ grad_emb) {
+  const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
+  extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] inputs, [2][area_o] outputs
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ float coef[kTC][kTC + 1];           // [c][e], zero padded
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = E + K;
+  const int groups = (E + kFbOut - 1) / kFbOut;   // blockDim = 64 * groups
+  const int og = warp % groups, half = warp / groups;
+  const int area_e = frame_area(E, F), area_t = frame_area(K, F), buf_floats = area_e + area_t;
+  const int area_o = frame_area(E, F);
+  float* outs = fsm + 2 * buf_floats;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
+  const int64_t N = T * F;
+  const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
+  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  for (int idx = threadIdx.x; idx < kTC * (kTC + 1); idx += blockDim.x) {
+    const int c = idx / (kTC + 1), e = idx - c * (kTC + 1);
+    double v = 0.0;
+    if (c < C && e < E) v = (c < E ? 1.0 : -1.0) * scale * gram[(int64_t)b * C * C + c * C + e];
+    coef[c][e] = (float)v;
+  }
+  if (threadIdx.x == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int s) {   // thread 0
+    const uintptr_t ae = reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t);
+    const uintptr_t at = reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t);
+    const unsigned be = (unsigned)(((ae & 15) + (size_t)E * F * 4 + 15) & ~(size_t)15);
+    const unsigned bt = (unsigned)(((at & 15) + (size_t)K * F * 4 + 15) & ~(size_t)15);
+    tma::fence_proxy_async();
+    tma::mbar_expect_tx(&full[s], be + bt);
+    tma::bulk_g2s(fsm + s * buf_floats, reinterpret_cast<const void*>(ae & ~(uintptr_t)15), be, &full[s]);
+    tma::bulk_g2s(fsm + s * buf_floats + area_e, reinterpret_cast<const void*>(at & ~(uintptr_t)15), bt, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    if (t0 < t1) issue(t0, 0);
+    if (t0 + 1 < t1) issue(t0 + 1, 1);
+  }
+  // this warp's coefficients: cf[c][j] for output channel og * 5 + j (zero beyond E / C)
+  float cf[kTC][kFbOut];
+#pragma unroll
+  for (int c = 0; c < kTC; ++c)
+#pragma unroll
+    for (int j = 0; j < kFbOut; ++j) cf[c][j] = coef[c][og * kFbOut + j];
+
+  const int pairs = F / 64;            // steps of 64 bins (two per lane), alternating between the two halves
+  const int rest0 = 64 * pairs;        // first bin of the remaining < 64 bins: one step of 32 per half
+  const int n = E * F;
+  for (int t = t0; t < t1; ++t) {
+    const int s = (t - t0) & 1;
+    float* gout = g_ + (int64_t)t * se_t;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(gout) & 15) >> 2);
+    float* stage = outs + s * area_o + phase;   // stage[i] <-> gout[i]
+    tma::mbar_wait(&full[s], (unsigned)((t - t0) >> 1) & 1u);
+    const float* be_ = fsm + s * buf_floats + (int)((reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t) & 15) >> 2) + lane;
+    const float* bt_ = fsm + s * buf_floats + area_e + (int)((reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t) & 15) >> 2) + lane;
+    float* so = stage + og * kFbOut * F + lane;
+    for (int ds = half; ds < pairs; ds += 2) {
+      const float* ze = be_ + 64 * ds;
+      const float* zt = bt_ + 64 * ds - E * F;
+      auto row = [&](int c) { return c < E ? ze + c * F : zt + c * F; };
+      float a0[kFbOut], a1[kFbOut];
+#pragma unroll
+      for (int j = 0; j < kFbOut; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+#pragma unroll
+      for (int c = 0; c < kTC; ++c) {
+        if (c < C) {   // uniform
+          const float* r = row(c);
+          const float z0 = r[0], z1 = r[32];
+#pragma unroll
+          for (int j = 0; j < kFbOut; ++j) { a0[j] = fmaf(z0, cf[c][j], a0[j]); a1[j] = fmaf(z1, cf[c][j], a1[j]); }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kFbOut; ++j) {
+        const int e = og * kFbOut + j;
+        if (e < E) {
+          so[j * F + 64 * ds] = a0[j];
+          so[j * F + 64 * ds + 32] = a1[j];
+        }
+      }
+    }
+    {
+      const int f = rest0 + 32 * half + lane;   // the F % 64 last bins
+      if (f < F) {
+        float a0[kFbOut];
+#pragma unroll
+        for (int j = 0; j < kFbOut; ++j) a0[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kTC; ++c) {
+          if (c < C) {
+            const float z0 = (c < E ? be_ + c * F : bt_ + (c - E) * F)[rest0 + 32 * half];
+#pragma unroll
+            for (int j = 0; j < kFbOut; ++j) a0[j] = fmaf(z0, cf[c][j], a0[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kFbOut; ++j) {
+          const int e = og * kFbOut + j;
+          if (e < E) stage[e * F + f] = a0[j];
+        }
+      }
+    }
+    tma::fence_proxy_async();                          // the block was written through the generic proxy
+    if (threadIdx.x == 0) tma::bulk_wait_read<0>();    // earlier stores have read their staging buffers
+    __syncthreads();                                   // inputs of buffer s consumed, block s complete
+    const int head = (4 - phase) & 3, mid = (n - head) & ~3, tail = n - head - mid;
+    if (threadIdx.x == 0) {
+      if (t + 2 < t1) issue(t + 2, s);
+      tma::bulk_s2g(gout + head, stage + head, (unsigned)mid * 4u);
+      tma::bulk_commit();
+    }
+    if (warp == 1) {
+      if (lane < head) gout[lane] = stage[lane];
+      if (lane < tail) gout[head + mid + lane] = stage[head + mid + lane];
+    }
+  }
+  if (threadIdx.x == 0) tma::bulk_wait<0>();   // shared memory must outlive the last store
+}
+
 }  // namespace
 
 extern "C" {
@@ -622,6 +766,29 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
   const Strides se{embedding_strides[0], embedding_strides[1], embedding_strides[2]};
   const Strides st{target_strides[0], target_strides[1], target_strides[2]};
   const int64_t points = std::max<int64_t>(1, max_frames * bins);
+  const size_t frame_smem = sizeof(float) * (2 * (frame_area(embedding_dim, (int)bins) + frame_area(sources, (int)bins)) +
+                                            2 * frame_area(embedding_dim, (int)bins));
+  static const bool no_frame = getenv("B2S_DC_NO_FRAME") != nullptr;
+  if (!no_frame && C <= kTC && embedding_dim <= 25 && se.f == 1 && st.f == 1 && se.c == bins && st.c == bins &&
+      frame_smem <= 200 * 1024 && max_frames < (1 << 30) && bins < (1 << 20)) {
+    static bool configured[64] = {};
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(dc_backward_frame_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B2S_CUDA(cudaFuncSetAttribute(dc_backward_frame_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured[dev & 63] = true;
+    }
+    const int groups = (embedding_dim + kFbOut - 1) / kFbOut;
+    const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 4),
+                                                                   (int64_t)kNumSMs / std::max<int64_t>(1, batch)));
+    auto kernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_backward_frame_kernel<513, 20, 2>
+                                                                     : dc_backward_frame_kernel<0, 0, 0>;
+    kernel<<<dim3((unsigned)batch, nchunks), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
+        embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, gram, grad_loss, grad_embedding);
+    B2S_LAUNCH_CHECK("dc_backward_frame_kernel");
+    return B2S_OK;
+  }
   if (C <= kTC && embedding_dim <= kBwdGroups * kBwdOut && se.f == 1 && st.f == 1) {
     const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 1024,
                                                std::max<int64_t>(1, (int64_t)kNumSMs * 2 * 4 / batch)));
