@@ -277,13 +277,53 @@ dc_gram_tiled_kernel(const float* __restrict__ emb, const float* __restrict__ tg
 constexpr int kFrWarps = 6;
 __host__ __device__ inline int frame_area(int rows, int F) { return (rows * F + 3 + 3) / 4 * 4 + 32; }
 
+// One frame of block pair (BA, BB): lanes own bins lane, lane + 32, ...; with compile-time geometry every
+// operand address is base register + immediate.
+template <int FT, int ET, int KT, int BA, int BB>
+__device__ __forceinline__ void gram_frame_block(const float* be_, const float* bt_, const float* zrow, int F_rt,
+                                                 int E_rt, int K_rt, int lane, float (&acc)[BS][BS]) {
+  const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, C = E + (KT ? KT : K_rt);
+  constexpr bool diag = BA == BB;
+  auto row = [&](int ch, int off) -> const float* {
+    return (ch < E ? be_ + ch * F : (ch < C ? bt_ + (ch - E) * F : zrow)) + off;
+  };
+  const int full_steps = F / 32;
+#pragma unroll 4
+  for (int j = 0; j < full_steps; ++j) {
+    float va[BS], vb[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) va[i] = row(BA * BS + i, 32 * j)[0];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) vb[i] = diag ? va[i] : row(BB * BS + i, 32 * j)[0];
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int jj = diag ? i : 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
+  }
+  if (lane + 32 * full_steps < F) {   // the F % 32 last bins
+    float va[BS], vb[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      va[i] = row(BA * BS + i, 32 * full_steps)[0];
+      vb[i] = diag ? va[i] : row(BB * BS + i, 32 * full_steps)[0];
+    }
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int jj = diag ? i : 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
+  }
+}
+
+// FT / ET / KT != 0: bins / embedding channels / sources known at compile time (513 / 20 / 2)
+template <int FT, int ET, int KT>
 __global__ void __launch_bounds__(32 * kFrWarps, 2)
 dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
-                     const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F, int E,
-                     int K, double* __restrict__ partial, int* __restrict__ counters,
+                     const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
+                     int K_rt, double* __restrict__ partial, int* __restrict__ counters,
                      double* __restrict__ gram, float* __restrict__ loss) {
   extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] frame buffers, then a row of zeros
   __shared__ __align__(8) uint64_t full[2];
+  const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
   const int b = blockIdx.x, chunk = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = E + K;
@@ -326,55 +366,20 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
 #pragma unroll
     for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
 
-  const int full_steps = F / 32;
   for (int t = t0; t < t1; ++t) {
     const int s = (t - t0) & 1;
     tma::mbar_wait(&full[s], (unsigned)((t - t0) >> 1) & 1u);
     if (active) {
-      const float* be_ = fsm + s * buf_floats + (int)((reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t) & 15) >> 2);
-      const float* bt_ = fsm + s * buf_floats + area_e + (int)((reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t) & 15) >> 2);
-      const float* ra[BS]; const float* rb[BS];
-#pragma unroll
-      for (int i = 0; i < BS; ++i) {
-        const int ca = ba * BS + i, cb = bb * BS + i;
-        ra[i] = (ca < E ? be_ + ca * F : (ca < C ? bt_ + (ca - E) * F : zrow)) + lane;
-        rb[i] = (cb < E ? be_ + cb * F : (cb < C ? bt_ + (cb - E) * F : zrow)) + lane;
-      }
-      // full steps of 32 bins without predicates; diagonal blocks accumulate their upper triangle only
-      if (diag) {
-#pragma unroll 4
-        for (int j = 0; j < full_steps; ++j) {
-          float va[BS];
-#pragma unroll
-          for (int i = 0; i < BS; ++i) va[i] = ra[i][32 * j];
-#pragma unroll
-          for (int i = 0; i < BS; ++i)
-#pragma unroll
-            for (int jj = i; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], va[jj], acc[i][jj]);
-        }
-      } else {
-#pragma unroll 4
-        for (int j = 0; j < full_steps; ++j) {
-          float va[BS], vb[BS];
-#pragma unroll
-          for (int i = 0; i < BS; ++i) va[i] = ra[i][32 * j];
-#pragma unroll
-          for (int i = 0; i < BS; ++i) vb[i] = rb[i][32 * j];
-#pragma unroll
-          for (int i = 0; i < BS; ++i)
-#pragma unroll
-            for (int jj = 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
-        }
-      }
-      if (lane + 32 * full_steps < F) {   // the F % 32 last bins
-        float va[BS], vb[BS];
-#pragma unroll
-        for (int i = 0; i < BS; ++i) { va[i] = ra[i][32 * full_steps]; vb[i] = rb[i][32 * full_steps]; }
-#pragma unroll
-        for (int i = 0; i < BS; ++i)
-#pragma unroll
-          for (int jj = 0; jj < BS; ++jj)
-            if (!diag || jj >= i) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
+      const float* be_ = fsm + s * buf_floats + (int)((reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t) & 15) >> 2) + lane;
+      const float* bt_ = fsm + s * buf_floats + area_e + (int)((reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t) & 15) >> 2) + lane;
+      const float* z_ = zrow + lane;
+      switch (warp) {   // warp-uniform
+        case 0: gram_frame_block<FT, ET, KT, 0, 0>(be_, bt_, z_, F, E, K, lane, acc); break;
+        case 1: gram_frame_block<FT, ET, KT, 0, 1>(be_, bt_, z_, F, E, K, lane, acc); break;
+        case 2: gram_frame_block<FT, ET, KT, 0, 2>(be_, bt_, z_, F, E, K, lane, acc); break;
+        case 3: gram_frame_block<FT, ET, KT, 1, 1>(be_, bt_, z_, F, E, K, lane, acc); break;
+        case 4: gram_frame_block<FT, ET, KT, 1, 2>(be_, bt_, z_, F, E, K, lane, acc); break;
+        default: gram_frame_block<FT, ET, KT, 2, 2>(be_, bt_, z_, F, E, K, lane, acc); break;
       }
     }
     __syncthreads();   // every warp is done with buffer s
@@ -731,14 +736,17 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
     int dev = 0;
     B2S_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-      B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured[dev & 63] = true;
     }
     // frames are split over about two CTAs per SM (each double-buffers whole frames)
     int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 4),
                                                              (int64_t)kNumSMs * 2 / std::max<int64_t>(1, batch)));
     nchunks = std::min(nchunks, g.nchunks);   // the workspace is sized for g.nchunks partial matrices
-    dc_gram_frame_kernel<<<dim3((unsigned)batch, nchunks), 32 * kFrWarps, frame_smem, (cudaStream_t)stream>>>(
+    auto kernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_gram_frame_kernel<513, 20, 2>
+                                                                     : dc_gram_frame_kernel<0, 0, 0>;
+    kernel<<<dim3((unsigned)batch, nchunks), 32 * kFrWarps, frame_smem, (cudaStream_t)stream>>>(
         embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss);
   } else if (g.tiled) {
     dc_gram_tiled_kernel<<<dim3((unsigned)batch, g.nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
