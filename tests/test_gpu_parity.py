@@ -387,6 +387,64 @@ def test_dc_review_golden(b2s, golden):
     assert_loss_close(loss2.cpu().numpy(), golden('models/dc/dc_loss'))
 
 
+def test_dc_review_reference_geometry(b2s):
+    """E = 20, K = 2, F = 513 (the geometry the frame-tiled kernels are specialised for at compile time),
+    ragged lengths, list and padded entry points, against the oracle in float64."""
+    from oracle import path as oracle_path
+    rng = np.random.RandomState(7)
+    lengths, E, K, F = [9, 4, 1, 6], 20, 2, 513
+    emb_np = [rng.randn(T, E, F).astype(np.float32) for T in lengths]
+    emb_np = [e / np.linalg.norm(e, axis=1, keepdims=True) for e in emb_np]
+    tm_np = [np.eye(K, dtype=np.float32)[rng.randint(0, K, (T, F))].transpose(0, 2, 1).copy() for T in lengths]
+    ref_emb = [torch.from_numpy(e).double().requires_grad_(True) for e in emb_np]
+    want, _ = oracle_path.dc_review_loss(ref_emb, [torch.from_numpy(t).double() for t in tm_np])
+    want_grads = torch.autograd.grad(want, ref_emb)
+    emb = [cuda(e).requires_grad_(True) for e in emb_np]
+    tm = [cuda(t) for t in tm_np]
+    loss = b2s.review.dc_review_loss(emb, tm)
+    assert_loss_close(loss.detach().cpu().numpy(), want.detach().numpy())
+    for b, (g, w) in enumerate(zip(torch.autograd.grad(loss, emb), want_grads)):
+        assert_spec_close(g.cpu().numpy(), w.numpy(), rtol=2e-4, what=f'grad {b}')
+    T = max(lengths)
+    pad = lambda seq: torch.stack([torch.nn.functional.pad(a.detach(), (0, 0, 0, 0, 0, T - a.shape[0])) for a in seq])  # noqa: E731
+    padded = pad(emb).requires_grad_(True)
+    loss2 = b2s.review.dc_review_loss(padded, pad(tm), lengths)
+    assert_loss_close(loss2.detach().cpu().numpy(), want.detach().numpy())
+    (g2,) = torch.autograd.grad(loss2, padded)
+    for b, w in enumerate(want_grads):
+        assert_spec_close(g2[b, :lengths[b]].cpu().numpy(), w.numpy(), rtol=2e-4, what=f'padded grad {b}')
+        assert float(g2[b, lengths[b]:].abs().max()) == 0.0 if lengths[b] < T else True
+    # an unaligned view: frames start at odd float offsets
+    base = torch.zeros(1 + emb_np[0].size, device=dev())
+    view = base[1:].view(emb_np[0].shape)
+    view.copy_(cuda(emb_np[0]))
+    single = b2s.review.dc_review_loss([view], [tm[0]])
+    want0, _ = oracle_path.dc_review_loss([torch.from_numpy(emb_np[0]).double()], [torch.from_numpy(tm_np[0]).double()])
+    assert_loss_close(single.cpu().numpy(), want0.numpy())
+
+
+@pytest.mark.parametrize('K', [3, 5])
+def test_tasnet_losses_more_sources(b2s, K):
+    """The one-launch loss set (K <= 4: thread per example) and its K > 4 fallback against the oracle."""
+    from oracle import path as oracle_path
+    rng = np.random.RandomState(K)
+    B, T = 5, 1500
+    num_samples = [1500, 1203, 1500, 777, 1001]
+    s = rng.randn(B, K, T).astype(np.float32)
+    est = (s[:, ::-1] + 0.4 * rng.randn(B, K, T)).astype(np.float32).copy()
+    ref_est = torch.from_numpy(est).double().requires_grad_(True)
+    want = oracle_path.tasnet_losses(ref_est, torch.from_numpy(s).double(), num_samples)
+    e = cuda(est).requires_grad_(True)
+    out = b2s.review.tasnet_losses(e, cuda(s), num_samples)
+    for name in ('si-sdr', 'log-mse', 'log1p-mse'):
+        assert_loss_close(out[name].detach().cpu().numpy(), want[name].detach().numpy(), what=name)
+    (grad,) = torch.autograd.grad(out['si-sdr'] + 0.5 * out['log1p-mse'], e)
+    (want_grad,) = torch.autograd.grad(want['si-sdr'] + 0.5 * want['log1p-mse'], ref_est)
+    assert_spec_close(grad.cpu().numpy(), want_grad.numpy(), rtol=2e-4, what='combined gradient')
+    for b, n in enumerate(num_samples):
+        assert float(grad[b, :, n:].abs().max()) == 0.0 if n < T else True
+
+
 def test_tasnet_losses_golden(b2s, golden):
     num_samples = golden.index['models']['tasnet']['num_samples']
     s = cuda(golden('models/tasnet/s'))
