@@ -224,6 +224,18 @@ B2S_API int b2s_stft_pit_forward(const b2s_stft_plan* plan, const float* mixture
                          int64_t frames, int64_t pad_left, float* loss, int32_t* perm, double* sse,
                          void* workspace, b2s_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batched target / feature preparation of the PIT example on the device:
+ * pre_batch_transform, padertorch/contrib/examples/source_separation/pit/data.py:49-77, which runs per
+ * example in numpy on the data-loader workers:
+ *     y_abs [B, M, F] = |Y|,  x_abs [B, M, K, F] = |X| ('k t f -> t k f'),
+ *     cos_phase_difference [B, M, K, F] = cos(angle(Y)[:, None, :] - angle(X))   (angle(0) = 0)
+ * spec_mixture [B, M, F, 2] and spec_sources [B, K, M, F, 2]: interleaved complex spectra as written by
+ * b2s_stft_forward (layout B2S_SPEC_INTERLEAVED) for the rows [B] and [B * K].  16-byte aligned buffers. */
+B2S_API int b2s_pit_targets(const float* spec_mixture, const float* spec_sources, int64_t batch, int sources,
+                    int64_t frames, int64_t bins, float* y_abs, float* x_abs,
+                    float* cos_phase_difference, b2s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
