@@ -134,10 +134,8 @@ def main():
         loss, perm, _ = problem.forward()
         g = torch.ones_like(loss)
         return lambda: problem.backward(perm, g)
-    record('pit_sse backward', time_graph(lambda i: sse_bwd(i, False), n), B * 4 * M * F * (3 * K + 1),
-           'includes the zero-fill of the gradient buffer')
-    record('pit_sse backward dual', time_graph(lambda i: sse_bwd(i, True), n), B * 4 * M * F * (4 * K + 1),
-           'includes the zero-fill of the gradient buffer')
+    record('pit_sse backward', time_graph(lambda i: sse_bwd(i, False), n), B * 4 * M * F * (3 * K + 1))
+    record('pit_sse backward dual', time_graph(lambda i: sse_bwd(i, True), n), B * 4 * M * F * (4 * K + 1))
 
     # ---- time-domain pair statistics (config 4 shape per GPU: batch 32 x 2 x 4 s; here batch 64)
     est = [s + 0.3 * torch.randn_like(s) for s in ss]
@@ -151,12 +149,12 @@ def main():
     def pair_bwd(i):
         rows = [[T, b * K * T, b * K * T] for b in range(B)]
         meta = meta_tensor(rows, dev, cache_key=('kb', B, K, T))
-        problem = _pairs.PairProblem(est[i], ss[i], meta, B, 1, K, T, T, T)
+        problem = _pairs.PairProblem(est[i], ss[i], meta, B, 1, K, T, T, T, covers_all=True)
         stats = problem.stats()
         loss, perm = problem.loss(stats, _lib.LOSS_SI_SDR, 0, -1.0, _lib.REDUCE_MEAN, True)
         g = torch.ones_like(loss)
         return lambda: problem.backward(stats, _lib.LOSS_SI_SDR, 0, -1.0, _lib.REDUCE_MEAN, True, perm, g)
-    record('si-sdr PIT backward', time_graph(pair_bwd, n), B * 3 * 4 * K * T, 'includes zero-fill of the gradient')
+    record('si-sdr PIT backward', time_graph(pair_bwd, n), B * 3 * 4 * K * T)
 
     # ---- deep clustering (config 3: batch 16, E = 20, K = 2; fixed 4 s here, ragged in tests)
     Bd, E = 16, 20
