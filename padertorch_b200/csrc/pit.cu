@@ -8,6 +8,7 @@
 // loads (F = 513 rows are not 16-byte aligned), two frames in flight per thread; partial sums leave
 // the CTA as doubles and the last CTA of an example (ticket counter) folds them in a fixed order.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "perm.cuh"
@@ -38,6 +39,8 @@ PitGrid pit_grid(int64_t batch, int64_t max_frames, int64_t bins) {
   int64_t t = capacity / std::max<int64_t>(1, batch * g.fchunks);
   const int64_t most = std::max<int64_t>(1, max_frames / kPitWarps);
   g.tchunks = (int)std::max<int64_t>(1, std::min<int64_t>(t, most));
+  static const int forced = [] { const char* e = getenv("B2S_PIT_TCHUNKS"); return e ? atoi(e) : 0; }();
+  if (forced > 0) g.tchunks = (int)std::min<int64_t>(forced, most);   // tuning aid
   return g;
 }
 
