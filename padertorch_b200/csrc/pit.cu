@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 #include "perm.cuh"
 
 using namespace b2s;
@@ -42,6 +43,65 @@ PitGrid pit_grid(int64_t batch, int64_t max_frames, int64_t bins) {
   static const int forced = [] { const char* e = getenv("B2S_PIT_TCHUNKS"); return e ? atoi(e) : 0; }();
   if (forced > 0) g.tchunks = (int)std::min<int64_t>(forced, most);   // tuning aid
   return g;
+}
+
+// CTA reduction (fixed tree) -> partial[b][chunk][NV]; the last CTA of an example (ticket) folds the chunks in
+// order and picks the permutation.  `sm`: shared scratch of NV * (warps + 1) doubles.  All threads call it.
+template <int K, bool DUAL>
+__device__ __forceinline__ void pit_finish(const float (&acc)[(DUAL ? 2 : 1) * K * K], double* sm, int b, int chunk,
+                                           int nchunks, int64_t T, int64_t F, double* __restrict__ partial,
+                                           int* __restrict__ counters, float* __restrict__ loss,
+                                           int32_t* __restrict__ perm, double* __restrict__ sse, int64_t batch) {
+  constexpr int NV = (DUAL ? 2 : 1) * K * K;
+  const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;
+  // ---- CTA reduction (fixed tree) -> partial[b][chunk][NV]
+  const int tid = threadIdx.x;
+  constexpr int nthreads = kPitThreads;
+  const int lane = lane_, warp = warp_;
+  constexpr int nwarps = kPitWarps;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0) sm[i * nwarps + warp] = (double)s;
+  }
+  __syncthreads();
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * NV;
+  for (int i = tid; i < NV; i += nthreads) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += sm[i * nwarps + w];
+    mine[i] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (tid == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- last CTA of this example: fold the chunks in order, pick the permutation
+  double* total = sm + NV * nwarps;
+  for (int i = tid; i < NV; i += nthreads) {
+    double s = 0.0;
+    const volatile double* p = partial + (int64_t)b * nchunks * NV + i;
+    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
+    total[i] = s;
+    sse[(int64_t)b * NV + i] = s;
+  }
+  __syncthreads();
+  const double count = (double)T * (double)K * (double)F;
+#pragma unroll
+  for (int slot = 0; slot < (DUAL ? 2 : 1); ++slot) {
+    double best;
+    int bp[B2S_MAX_SOURCES];
+    search_permutations(total + slot * K * K, K, best, bp);
+    if (tid == 0) {
+      loss[slot * batch + b] = (float)(best / count);
+      for (int k = 0; k < K; ++k) perm[(slot * batch + b) * K + k] = bp[k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counters[b] = 0;  // leave the workspace ready for the next call
 }
 
 template <int K, bool DUAL>
@@ -112,54 +172,139 @@ pit_sse_forward_kernel(const float* __restrict__ mask, const float* __restrict__
     }
   }
 
-  // ---- CTA reduction (fixed tree) -> partial[b][chunk][NV]
-  const int tid = threadIdx.x;
-  constexpr int nthreads = kPitThreads;
-  const int lane = lane_, warp = warp_;
-  constexpr int nwarps = kPitWarps;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float s = warp_sum(acc[i]);
-    if (lane == 0) sm[i * nwarps + warp] = (double)s;
-  }
-  __syncthreads();
-  double* mine = partial + ((int64_t)b * nchunks + chunk) * NV;
-  for (int i = tid; i < NV; i += nthreads) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += sm[i * nwarps + w];
-    mine[i] = s;
-  }
-  __threadfence();
-  __syncthreads();
-  __shared__ int s_last;
-  if (tid == 0) s_last = atomicAdd(counters + b, 1) == nchunks - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
+  pit_finish<K, DUAL>(acc, sm, b, chunk, nchunks, T, F, partial, counters, loss, perm, sse, batch);
+}
 
-  // ---- last CTA of this example: fold the chunks in order, pick the permutation
-  double* total = sm + NV * nwarps;
-  for (int i = tid; i < NV; i += nthreads) {
-    double s = 0.0;
-    const volatile double* p = partial + (int64_t)b * nchunks * NV + i;
-    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
-    total[i] = s;
-    sse[(int64_t)b * NV + i] = s;
+// ------------------------------------------------------------------------------------------- frame-staged forward
+// Consecutive frames of an example are contiguous in every operand ([T][K][F] mask / target / scale, [T][F]
+// observation): a stage of G frames arrives by one TMA bulk copy per operand (enclosing 16-byte aligned range,
+// the data sits at the source's misalignment), double buffered per CTA, two CTAs per SM.  Warps read their
+// frame's rows with conflict-free LDS.32 (lanes own bins).  Rows of 513 floats are only 4-byte aligned: the
+// direct kernel above reads them with 4-byte loads and stalls on every batch of them.
+constexpr int kStageBudget = 100 * 1024;   // dynamic shared memory per CTA (two stages)
+
+__host__ __device__ inline int stage_area(int64_t floats) { return (int)((floats + 3 + 3) / 4 * 4); }
+__host__ __device__ inline int stage_floats(int G, int K, int64_t F, bool has_obs, bool has_scale) {
+  return stage_area(G * K * F) * (has_scale ? 3 : 2) + (has_obs ? stage_area(G * F) : 0);
+}
+// frames per stage: the largest power of two <= 8 whose two stages fit the budget (0: use the direct kernel)
+inline int stage_frames(int K, int64_t F, bool has_obs, bool has_scale) {
+  for (int G = kPitWarps; G >= 1; G >>= 1)
+    if ((int64_t)stage_floats(G, K, F, has_obs, has_scale) * 2 * 4 <= kStageBudget) return G;
+  return 0;
+}
+
+template <int K, bool DUAL>
+__global__ void __launch_bounds__(kPitThreads, 2)
+pit_sse_frame_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
+                     const float* __restrict__ tgt, const float* __restrict__ scale,
+                     const int64_t* __restrict__ meta, int tchunks, int G, int F,
+                     double* __restrict__ partial, int* __restrict__ counters,
+                     float* __restrict__ loss, int32_t* __restrict__ perm, double* __restrict__ sse,
+                     int64_t batch) {
+  constexpr int NV = (DUAL ? 2 : 1) * K * K;
+  extern __shared__ __align__(16) float stage_sm[];   // [2][mask | target | (scale) | (observation)]
+  __shared__ __align__(8) uint64_t full[2];
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t T = meta[b * B2S_PIT_META + 0];
+  const float* m_ = mask + meta[b * B2S_PIT_META + 1];
+  const float* o_ = obs ? obs + meta[b * B2S_PIT_META + 2] : nullptr;
+  const float* x_ = tgt + meta[b * B2S_PIT_META + 3];
+  const float* s_ = scale ? scale + meta[b * B2S_PIT_META + 4] : nullptr;
+  const int t0 = (int)(T * chunk / tchunks), t1 = (int)(T * (chunk + 1) / tchunks);
+  const int area_k = stage_area((int64_t)G * K * F), area_o = o_ ? stage_area((int64_t)G * F) : 0;
+  const int off_x = area_k, off_s = 2 * area_k, off_o = (s_ ? 3 : 2) * area_k;
+  const int per_stage = off_o + area_o;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
   }
   __syncthreads();
-  const double count = (double)T * (double)K * (double)F;
-#pragma unroll
-  for (int slot = 0; slot < (DUAL ? 2 : 1); ++slot) {
-    double best;
-    int bp[B2S_MAX_SOURCES];
-    search_permutations(total + slot * K * K, K, best, bp);
-    if (tid == 0) {
-      loss[slot * batch + b] = (float)(best / count);
-      for (int k = 0; k < K; ++k) perm[(slot * batch + b) * K + k] = bp[k];
-    }
-    __syncthreads();
+  // stage n covers frames [t0 + n G, min(t1, t0 + (n + 1) G))
+  const int nstages = (t1 - t0 + G - 1) / G;
+  auto span = [&](const float* base, int64_t floats, float* dst, uint64_t* bar, unsigned& bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+    bytes = (unsigned)(((a & 15) + (size_t)floats * 4 + 15) & ~(size_t)15);
+    tma::bulk_g2s(dst, reinterpret_cast<const void*>(a & ~(uintptr_t)15), bytes, bar);
+  };
+  auto issue = [&](int n) {   // thread 0
+    const int s = n & 1;
+    const int t = t0 + n * G, g = min(G, t1 - t);
+    float* buf = stage_sm + s * per_stage;
+    const int64_t kf = (int64_t)K * F;
+    // expected bytes first: the sizes follow from the addresses
+    auto bytes_of = [&](const float* base, int64_t floats) {
+      return (unsigned)(((reinterpret_cast<uintptr_t>(base) & 15) + (size_t)floats * 4 + 15) & ~(size_t)15);
+    };
+    unsigned total = bytes_of(m_ + t * kf, g * kf) + bytes_of(x_ + t * kf, g * kf);
+    if (s_) total += bytes_of(s_ + t * kf, g * kf);
+    if (o_) total += bytes_of(o_ + (int64_t)t * F, (int64_t)g * F);
+    tma::fence_proxy_async();   // the buffer was last read through the generic proxy
+    tma::mbar_expect_tx(&full[s], total);
+    unsigned nb;
+    span(m_ + t * kf, g * kf, buf, &full[s], nb);
+    span(x_ + t * kf, g * kf, buf + off_x, &full[s], nb);
+    if (s_) span(s_ + t * kf, g * kf, buf + off_s, &full[s], nb);
+    if (o_) span(o_ + (int64_t)t * F, (int64_t)g * F, buf + off_o, &full[s], nb);
+  };
+  if (threadIdx.x == 0) {
+    if (nstages > 0) issue(0);
+    if (nstages > 1) issue(1);
   }
-  if (tid == 0) counters[b] = 0;  // leave the workspace ready for the next call
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  // warp -> (frame of the stage, part of the bins): G frames x (8 / G) parts
+  const int fi = warp % G, part = warp / G, parts = kPitWarps / G;
+  const int steps = (F + 31) / 32;
+  for (int n = 0; n < nstages; ++n) {
+    const int s = n & 1;
+    const int t = t0 + n * G, g = min(G, t1 - t);
+    tma::mbar_wait(&full[s], (unsigned)(n >> 1) & 1u);
+    if (fi < g) {
+      const float* buf = stage_sm + s * per_stage;
+      const int64_t kf = (int64_t)K * F;
+      auto mis = [&](const float* base) { return (int)((reinterpret_cast<uintptr_t>(base) & 15) >> 2); };
+      const float* mrow = buf + mis(m_ + t * kf) + fi * K * F + lane;
+      const float* xrow = buf + off_x + mis(x_ + t * kf) + fi * K * F + lane;
+      const float* srow = s_ ? buf + off_s + mis(s_ + t * kf) + fi * K * F + lane : nullptr;
+      const float* orow = o_ ? buf + off_o + mis(o_ + (int64_t)t * F) + fi * F + lane : nullptr;
+#pragma unroll 2
+      for (int j = part; j < steps; j += parts) {
+        if (lane + 32 * j < F) {
+          const float o = orow ? orow[32 * j] : 1.f;
+          float e[K], x[K], sc[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            e[i] = mrow[i * F + 32 * j] * o;
+            x[i] = xrow[i * F + 32 * j];
+            sc[i] = srow ? srow[i * F + 32 * j] : 1.f;
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) {
+              if (DUAL) {
+                const float d0 = e[i] - x[jj], d1 = e[i] - x[jj] * sc[jj];
+                acc[i * K + jj] = fmaf(d0, d0, acc[i * K + jj]);
+                acc[K * K + i * K + jj] = fmaf(d1, d1, acc[K * K + i * K + jj]);
+              } else {
+                const float d = e[i] - x[jj] * sc[jj];
+                acc[i * K + jj] = fmaf(d, d, acc[i * K + jj]);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with buffer s
+    if (threadIdx.x == 0 && n + 2 < nstages) issue(n + 2);
+  }
+  // the stage buffers are free (every copy was waited for): reuse them as the reduction scratch
+  pit_finish<K, DUAL>(acc, reinterpret_cast<double*>(stage_sm), b, chunk, tchunks, T, (int64_t)F, partial, counters,
+                      loss, perm, sse, batch);
 }
 
 // grad_mask[t,i,f] = sum_slot c_slot * o * (m*o - x_slot[inv_slot[i]]),  c = grad_loss * 2 / (T K F)
@@ -259,6 +404,29 @@ int launch_forward_k(const float* mask, const float* obs, const float* tgt, cons
   (void)nv;
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
+  // frame-staged TMA path: rows short enough for whole frames to be staged, bins not split over CTAs
+  static const bool no_frame = getenv("B2S_PIT_NO_FRAME") != nullptr;
+  const int G = (g.fchunks == 1 && F < (1 << 20) && max_frames < (1 << 30))
+      ? stage_frames(K, F, obs != nullptr, scale != nullptr) : 0;
+  if (G > 0 && !no_frame && max_frames >= 2 * G) {
+    const size_t smem = std::max<size_t>(sizeof(float) * 2 * stage_floats(G, K, F, obs != nullptr, scale != nullptr),
+                                         sizeof(double) * nv * (kPitWarps + 1));
+    auto kernel = dual ? pit_sse_frame_kernel<K, true> : pit_sse_frame_kernel<K, false>;
+    static bool configured[2][64] = {};
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    if (!configured[dual ? 1 : 0][dev & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBudget));
+      configured[dual ? 1 : 0][dev & 63] = true;
+    }
+    // the workspace holds g.nchunks() partial matrices per example: at most that many frame chunks
+    const int tchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(g.nchunks(), max_frames / (2 * G)),
+                                                                   (int64_t)kNumSMs * 2 / std::max<int64_t>(1, batch)));
+    kernel<<<dim3((unsigned)batch, tchunks), kPitThreads, smem, stream>>>(mask, obs, tgt, scale, meta, tchunks, G,
+        (int)F, partial, counters, loss, perm, sse, batch);
+    B2S_LAUNCH_CHECK("pit_sse_frame_kernel");
+    return B2S_OK;
+  }
   const dim3 grid((unsigned)batch, g.nchunks()), block(kPitThreads);
   const size_t smem = sizeof(double) * nv * (kPitWarps + 1);
   if (dual)
