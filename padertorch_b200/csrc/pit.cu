@@ -395,6 +395,150 @@ pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------- frame-staged backward
+// Inputs staged exactly as in pit_sse_frame_kernel; the stage's [G][K][F] gradient block -- contiguous in global
+// memory -- is assembled in shared memory at the destination's phase within 16 bytes and leaves as ONE TMA bulk
+// store (double buffered; at most 3 floats at either end from lanes).  grad_target is not produced here.
+inline int stage_frames_bwd(int K, int64_t F, bool has_obs, bool has_scale) {
+  for (int G = kPitWarps; G >= 1; G >>= 1)
+    if (((int64_t)stage_floats(G, K, F, has_obs, has_scale) + stage_area((int64_t)G * K * F)) * 2 * 4 <= kStageBudget)
+      return G;
+  return 0;
+}
+
+template <int K, bool DUAL>
+__global__ void __launch_bounds__(kPitThreads, 2)
+pit_sse_backward_frame_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
+                              const float* __restrict__ tgt, const float* __restrict__ scale,
+                              const int64_t* __restrict__ meta, int tchunks, int G, int F,
+                              const int32_t* __restrict__ perm, const float* __restrict__ grad_loss,
+                              float* __restrict__ grad_mask, int64_t batch) {
+  extern __shared__ __align__(16) float stage_sm[];   // [2][mask | target | (scale) | (observation)], [2][gradient]
+  __shared__ __align__(8) uint64_t full[2];
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t T = meta[b * B2S_PIT_META + 0];
+  const float* m_ = mask + meta[b * B2S_PIT_META + 1];
+  const float* o_ = obs ? obs + meta[b * B2S_PIT_META + 2] : nullptr;
+  const float* x_ = tgt + meta[b * B2S_PIT_META + 3];
+  const float* s_ = scale ? scale + meta[b * B2S_PIT_META + 4] : nullptr;
+  float* gm_ = grad_mask + meta[b * B2S_PIT_META + 5];
+  const int t0 = (int)(T * chunk / tchunks), t1 = (int)(T * (chunk + 1) / tchunks);
+  const int area_k = stage_area((int64_t)G * K * F), area_o = o_ ? stage_area((int64_t)G * F) : 0;
+  const int off_x = area_k, off_s = 2 * area_k, off_o = (s_ ? 3 : 2) * area_k;
+  const int per_stage = off_o + area_o;
+  float* outs = stage_sm + 2 * per_stage;
+  const double count = (double)T * (double)K * (double)F;
+  int inv0[K], inv1[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i0 = perm[(int64_t)b * K + k];
+#pragma unroll
+    for (int i = 0; i < K; ++i) if (i == i0) inv0[i] = k;
+    if (DUAL) {
+      const int i1 = perm[(batch + b) * K + k];
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (i == i1) inv1[i] = k;
+    }
+  }
+  const float c0 = (float)(2.0 * (double)grad_loss[b] / count);
+  const float c1 = DUAL ? (float)(2.0 * (double)grad_loss[batch + b] / count) : 0.f;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  const int nstages = (t1 - t0 + G - 1) / G;
+  const int64_t kf = (int64_t)K * F;
+  auto issue = [&](int n) {   // thread 0
+    const int s = n & 1;
+    const int t = t0 + n * G, g = min(G, t1 - t);
+    float* buf = stage_sm + s * per_stage;
+    auto bytes_of = [&](const float* base, int64_t floats) {
+      return (unsigned)(((reinterpret_cast<uintptr_t>(base) & 15) + (size_t)floats * 4 + 15) & ~(size_t)15);
+    };
+    auto span = [&](const float* base, int64_t floats, float* dst) {
+      tma::bulk_g2s(dst, reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)15),
+                    bytes_of(base, floats), &full[s]);
+    };
+    unsigned total = bytes_of(m_ + t * kf, g * kf) + bytes_of(x_ + t * kf, g * kf);
+    if (s_) total += bytes_of(s_ + t * kf, g * kf);
+    if (o_) total += bytes_of(o_ + (int64_t)t * F, (int64_t)g * F);
+    tma::fence_proxy_async();
+    tma::mbar_expect_tx(&full[s], total);
+    span(m_ + t * kf, g * kf, buf);
+    span(x_ + t * kf, g * kf, buf + off_x);
+    if (s_) span(s_ + t * kf, g * kf, buf + off_s);
+    if (o_) span(o_ + (int64_t)t * F, (int64_t)g * F, buf + off_o);
+  };
+  if (threadIdx.x == 0) {
+    if (nstages > 0) issue(0);
+    if (nstages > 1) issue(1);
+  }
+  const int fi = warp % G, part = warp / G, parts = kPitWarps / G;
+  const int steps = (F + 31) / 32;
+  for (int n = 0; n < nstages; ++n) {
+    const int s = n & 1;
+    const int t = t0 + n * G, g = min(G, t1 - t);
+    float* gout = gm_ + t * kf;                      // the stage's gradient block in global memory
+    const int phase = (int)((reinterpret_cast<uintptr_t>(gout) & 15) >> 2);
+    float* stage = outs + s * area_k + phase;        // stage[i] <-> gout[i]
+    tma::mbar_wait(&full[s], (unsigned)(n >> 1) & 1u);
+    if (fi < g) {
+      const float* buf = stage_sm + s * per_stage;
+      auto mis = [&](const float* base) { return (int)((reinterpret_cast<uintptr_t>(base) & 15) >> 2); };
+      const float* mrow = buf + mis(m_ + t * kf) + fi * K * F + lane;
+      const float* xrow = buf + off_x + mis(x_ + t * kf) + fi * K * F + lane;
+      const float* srow = s_ ? buf + off_s + mis(s_ + t * kf) + fi * K * F + lane : nullptr;
+      const float* orow = o_ ? buf + off_o + mis(o_ + (int64_t)t * F) + fi * F + lane : nullptr;
+      float* grow = stage + fi * K * F + lane;
+#pragma unroll 2
+      for (int j = part; j < steps; j += parts) {
+        if (lane + 32 * j < F) {
+          const float o = orow ? orow[32 * j] : 1.f;
+          float e[K], x[K], sc[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            e[i] = mrow[i * F + 32 * j] * o;
+            x[i] = xrow[i * F + 32 * j];
+            sc[i] = srow ? srow[i * F + 32 * j] : 1.f;
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float xa = 0.f, xb = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              if (inv0[i] == k) xa = DUAL ? x[k] : x[k] * sc[k];
+              if (DUAL && inv1[i] == k) xb = x[k] * sc[k];
+            }
+            float gv = c0 * (e[i] - xa);
+            if (DUAL) gv = fmaf(c1, e[i] - xb, gv);
+            grow[i * F + 32 * j] = gv * o;
+          }
+        }
+      }
+    }
+    tma::fence_proxy_async();                          // the block was written through the generic proxy
+    if (threadIdx.x == 0) tma::bulk_wait_read<0>();    // earlier stores have read their staging buffers
+    __syncthreads();                                   // inputs of buffer s consumed, gradient block s complete
+    const int nflt = (int)(g * kf);
+    const int head = min(nflt, (4 - phase) & 3), mid = (nflt - head) & ~3, tail = nflt - head - mid;
+    if (threadIdx.x == 0) {
+      if (n + 2 < nstages) issue(n + 2);
+      if (mid > 0) {
+        tma::bulk_s2g(gout + head, stage + head, (unsigned)mid * 4u);
+        tma::bulk_commit();
+      }
+    }
+    if (warp == 1) {
+      if (lane < head) gout[lane] = stage[lane];
+      if (lane < tail) gout[head + mid + lane] = stage[head + mid + lane];
+    }
+  }
+  if (threadIdx.x == 0) tma::bulk_wait<0>();   // shared memory must outlive the last store
+}
+
 template <int K>
 int launch_forward_k(const float* mask, const float* obs, const float* tgt, const float* scale,
                      const int64_t* meta, int64_t batch, int64_t max_frames, int64_t F, int dual,
@@ -444,6 +588,27 @@ int launch_backward_k(const float* mask, const float* obs, const float* tgt, con
                       const int64_t* meta, int64_t batch, int64_t max_frames, int64_t F, int dual,
                       const int32_t* perm, const float* grad_loss, float* grad_mask,
                       float* grad_target, cudaStream_t stream) {
+  static const bool no_frame = getenv("B2S_PIT_NO_FRAME") != nullptr;
+  const int G = (!grad_target && F <= 16384 && max_frames < (1 << 30))
+      ? stage_frames_bwd(K, F, obs != nullptr, scale != nullptr) : 0;
+  if (G > 0 && !no_frame && max_frames >= 2 * G) {
+    const size_t smem = sizeof(float) * 2 * ((size_t)stage_floats(G, K, F, obs != nullptr, scale != nullptr) +
+                                             stage_area((int64_t)G * K * F));
+    auto kernel = dual ? pit_sse_backward_frame_kernel<K, true> : pit_sse_backward_frame_kernel<K, false>;
+    static bool configured[2][64] = {};
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    if (!configured[dual ? 1 : 0][dev & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBudget));
+      configured[dual ? 1 : 0][dev & 63] = true;
+    }
+    const int tchunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_frames / (2 * G),
+                                                                   (int64_t)kNumSMs * 2 / std::max<int64_t>(1, batch)));
+    kernel<<<dim3((unsigned)batch, tchunks), kPitThreads, smem, stream>>>(mask, obs, tgt, scale, meta, tchunks, G,
+        (int)F, perm, grad_loss, grad_mask, batch);
+    B2S_LAUNCH_CHECK("pit_sse_backward_frame_kernel");
+    return B2S_OK;
+  }
   PitGrid g = pit_grid(batch, max_frames, F);
   // elementwise: more CTAs than the reduction wants are fine
   g.tchunks = (int)std::max<int64_t>(g.tchunks, std::min<int64_t>(max_frames / (2 * kPitWarps) + 1, 64));
