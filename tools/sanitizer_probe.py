@@ -20,3 +20,26 @@ for B, K, T in ((2, 2, 9000), (1, 3, 5001)):
     torch.cuda.synchronize()
     print('ok', float((ya.cpu() - want_yabs).abs().max()), float((back[..., :T].cpu() - torch.from_numpy(y)).abs().max()),
           float((loss.cpu() - want_loss).abs().max()), float((loss2.cpu() - want_loss).abs().max()), perm.tolist() == [list(p) for p in want_perm])
+
+# ---- frame-staged TMA kernels (PIT-SSE, deep clustering), pair statistics, target preparation
+for K, F, lengths in ((2, 513, [11, 7, 3]), (3, 257, [9, 5])):
+    masks = [torch.rand(T, K, F, device=dev, requires_grad=True) for T in lengths]
+    yab = [torch.rand(T, F, device=dev) for T in lengths]
+    xab = [torch.rand(T, K, F, device=dev) for T in lengths]
+    cpd = [torch.rand(T, K, F, device=dev) * 2 - 1 for T in lengths]
+    out = b2s.review.pit_review_losses(masks, yab, xab, cpd)
+    (out['pit_mse_loss'] + out['pit_ips_loss']).backward()
+    out1 = b2s.review.pit_review_losses(masks, yab, xab)
+    out1['pit_mse_loss'].backward()
+for E, K, F, lengths in ((20, 2, 513, [6, 4, 1]), (7, 3, 65, [5, 9])):
+    emb = [torch.nn.functional.normalize(torch.randn(T, E, F, device=dev), dim=1).requires_grad_(True) for T in lengths]
+    tm = [torch.nn.functional.one_hot(torch.randint(0, K, (T, F), device=dev), K).permute(0, 2, 1).float().contiguous()
+          for T in lengths]
+    b2s.review.dc_review_loss(emb, tm).backward()
+s = torch.randn(3, 2, 4001, device=dev)
+est = (s + 0.3 * torch.randn_like(s)).requires_grad_(True)
+out = b2s.review.tasnet_losses(est, s, [4001, 3000, 4001])
+(out['si-sdr'] + out['log-mse']).backward()
+prep = b2s.review.prepare_pit_targets(s.sum(1), s, stft=stft)
+torch.cuda.synchronize()
+print('ok losses', float(out['si-sdr']), prep['X_abs'].shape)
