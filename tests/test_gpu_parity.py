@@ -640,3 +640,89 @@ def test_three_speaker_eight_seconds(b2s):
                             return_permutation=True)
         assert tuple(perm[b].tolist()) == tuple(wp)
         assert_loss_close(loss[b].cpu().numpy(), w.numpy())
+
+
+def test_deep_clustering_full_size_properties(b2s):
+    """BASELINE config 3 shape: batch 16, variable length 2-8 s (128..503 frames), E = 20, K = 2, F = 513.
+    Size-independent properties of deep_clustering_loss (source_separation.py:13-31):
+    L(aV) = a^4 |V^T V|^2 - 2 a^2 |V^T Y|^2 + |Y^T Y|^2 (over N^2), <grad L, V> = dL(aV)/da at a = 1."""
+    torch.manual_seed(3)
+    d = dev()
+    B, E, K, F = 16, 20, 2, 513
+    lengths = [int(v) for v in torch.randint(128, 504, (B,))]
+    lengths[0], lengths[1] = 503, 128
+    T = max(lengths)
+    emb = torch.nn.functional.normalize(torch.randn(B, T, E, F, device=d), dim=2)
+    labels = torch.randint(0, K, (B, T, F), device=d)
+    tm = torch.nn.functional.one_hot(labels, K).permute(0, 1, 3, 2).float().contiguous()
+    per_example = lambda e: b2s.review.dc_losses_per_example(e, tm, lengths)  # noqa: E731
+    # perfect embedding: the target itself in the first K channels -> V V^T == Y Y^T -> 0
+    perfect = torch.zeros_like(emb)
+    perfect[:, :, :K] = tm
+    assert float(per_example(perfect).abs().max()) <= 1e-6
+    # invariance under a permutation of the embedding channels
+    base = per_example(emb)
+    shuffled = per_example(emb[:, :, torch.randperm(E, device=d)].contiguous())
+    torch.testing.assert_close(shuffled, base, rtol=1e-5, atol=0)
+    # list entry point == padded entry point; reruns are bit identical
+    as_list = b2s.review.dc_losses_per_example([emb[b, :n] for b, n in enumerate(lengths)],
+                                               [tm[b, :n] for b, n in enumerate(lengths)])
+    torch.testing.assert_close(as_list, base, rtol=1e-5, atol=0)
+    assert torch.equal(per_example(emb), base)
+    # quartic in the scale of V: fit A, B, C from a = 1, 0.5, 2 and predict a = 1.5; <grad, V> = 4A - 4B
+    l1, lh, l2, l15 = (per_example(a * emb).double() for a in (1.0, 0.5, 2.0, 1.5))
+    # l1 = A - 2B + C, lh = A/16 - B/2 + C, l2 = 16A - 8B + C
+    A = (l2 - l1 - 4.0 * (l1 - lh)) / 11.25
+    Bc = (15.0 * A - (l2 - l1)) / 6.0
+    C = l1 - A + 2.0 * Bc
+    torch.testing.assert_close(1.5 ** 4 * A - 2 * 1.5 ** 2 * Bc + C, l15, rtol=2e-4, atol=0)
+    v = emb.clone().requires_grad_(True)
+    b2s.review.dc_losses_per_example(v, tm, lengths).sum().backward()
+    along = (v.grad.double() * emb.double()).sum(dim=(1, 2, 3))
+    torch.testing.assert_close(along, 4.0 * A - 4.0 * Bc, rtol=2e-3, atol=0)
+    for b, n in enumerate(lengths):
+        if n < T:
+            assert float(v.grad[b, n:].abs().max()) == 0.0
+
+
+def test_tasnet_losses_full_size_properties(b2s):
+    """BASELINE config 4 shape per GPU: batch 32 x 2 speakers x 4 s, PIT over si-sdr / log-mse / log1p-mse
+    (tasnet/model.py:154-176): planted permutations, scale invariance, known SNR, batch mean == mean of
+    single-example losses (tests/test_models/test_bss.py:57-83), an independent float64 evaluation on the GPU."""
+    torch.manual_seed(4)
+    d = dev()
+    B, K, T = 32, 2, 64000
+    s = torch.randn(B, K, T, device=d)
+    swap = torch.arange(B, device=d) % 2 == 1
+    noise = 0.1 * torch.randn(B, K, T, device=d)
+    est = torch.where(swap[:, None, None], s.flip(1), s) + noise
+    num = [T] * B
+    out = b2s.review.tasnet_losses(est, s, num)
+    # independent float64 evaluation with the planted assignment
+    e64 = torch.where(swap[:, None, None], est.flip(1), est).double()
+    s64 = s.double()
+    alpha = (e64 * s64).sum(-1, keepdim=True) / (s64 * s64).sum(-1, keepdim=True)
+    si_sdr = -10 * torch.log10((alpha * s64).pow(2).sum(-1) / (e64 - alpha * s64).pow(2).sum(-1))
+    mse = (e64 - s64).pow(2).mean(-1)
+    assert_loss_close(out['si-sdr'].cpu().numpy(), si_sdr.mean(-1).mean().cpu().numpy(), what='si-sdr')
+    assert_loss_close(out['log-mse'].cpu().numpy(), torch.log10(mse).sum(-1).mean().cpu().numpy(), what='log-mse')
+    assert_loss_close(out['log1p-mse'].cpu().numpy(), torch.log10(1 + mse).sum(-1).mean().cpu().numpy(), what='log1p')
+    # known SNR: 20 dB of independent noise -> si-sdr within 0.1 dB of -20
+    assert abs(float(out['si-sdr']) + 20.0) < 0.1
+    # planted permutation, bit exact; scale invariance of si-sdr
+    for b in (0, 1, 30, 31):
+        value, perm = b2s.ops.pit_loss(est[b], s[b], axis=0, loss_fn=b2s.ops.si_sdr_loss, return_permutation=True)
+        assert tuple(perm) == ((1, 0) if b % 2 else (0, 1))
+        scaled = b2s.ops.pit_loss(3.7 * est[b], s[b], axis=0, loss_fn=b2s.ops.si_sdr_loss)
+        torch.testing.assert_close(scaled, value, rtol=1e-5, atol=1e-5)
+    # minibatch loss == mean of single-example losses
+    singles = torch.stack([b2s.review.tasnet_losses(est[b:b + 1], s[b:b + 1], [T])['si-sdr'] for b in range(0, B, 8)])
+    eight = b2s.review.tasnet_losses(est[::8].contiguous(), s[::8].contiguous(), [T] * 4)['si-sdr']
+    np.testing.assert_allclose(float(singles.mean()), float(eight), atol=1e-5)
+    # gradient: descends the loss, zero beyond the length of a shortened example
+    e = est.clone().requires_grad_(True)
+    short = [T] * (B - 1) + [T // 2]
+    b2s.review.tasnet_losses(e, s, short)['si-sdr'].backward()
+    assert torch.isfinite(e.grad).all() and float(e.grad[-1, :, T // 2:].abs().max()) == 0.0
+    stepped = b2s.review.tasnet_losses((e - 100.0 * e.grad).detach(), s, short)['si-sdr']
+    assert float(stepped) < float(b2s.review.tasnet_losses(est, s, short)['si-sdr'])
