@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 #include "perm.cuh"
 
 using namespace b2s;
@@ -174,6 +175,169 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
   if (threadIdx.x == 0) counters[g] = 0;
 }
 
+// ------------------------------------------------------------------------------------------- segment-staged statistics
+// The (group, segment of S samples) units of the whole call form one list; CTA i of a persistent grid owns the
+// contiguous range [i total / P, (i + 1) total / P) -- equal work per CTA whatever the number of groups (the
+// (group, chunk) grid above puts 64 x 4 = 256 CTAs on 148 SMs and leaves 27 % of the SM-time idle).  A unit's 2K
+// row segments arrive by TMA bulk copies (enclosing 16-byte aligned range, data at the source's misalignment:
+// any row alignment is served at full rate), double buffered; threads read them with conflict-free LDS.32.
+// At a group boundary the CTA flushes its partial statistics; the last contributor of a group (ticket) folds
+// them in slot order.
+// resident CTAs per SM: the K * K + 4K double accumulators set the register budget
+__host__ __device__ constexpr int seg_ctas(int K) { return K <= 2 ? 3 : (K <= 4 ? 2 : 1); }
+__host__ __device__ constexpr int seg_samples(int K) { return K <= 2 ? 2048 : (K <= 4 ? 1024 : 512); }
+__host__ __device__ constexpr int seg_row_floats(int K) { return seg_samples(K) + 8; }
+
+struct SegGrid { int64_t units_per_group, total; int ctas, slots; };
+SegGrid seg_grid(int64_t groups, int64_t max_length, int K) {
+  SegGrid g;
+  g.units_per_group = std::max<int64_t>(1, ceil_div(max_length, (int64_t)seg_samples(K)));
+  g.total = groups * g.units_per_group;
+  g.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(g.total, (int64_t)kNumSMs * seg_ctas(K)));
+  g.slots = (int)(ceil_div(g.units_per_group * g.ctas, g.total) + 2);
+  return g;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kStatsThreads, seg_ctas(K))
+pair_stats_seg_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                      const int64_t* __restrict__ meta, int64_t units_per_group, int64_t total, int slots,
+                      int64_t est_stride, int64_t tgt_stride, double* __restrict__ partial,
+                      int* __restrict__ counters, double* __restrict__ stats) {
+  constexpr int NV = K * K + 4 * K;
+  constexpr int S = seg_samples(K), RF = seg_row_floats(K);
+  extern __shared__ __align__(16) float seg_sm[];   // [2][2K][RF]
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ double red[NV * (kStatsThreads / 32)];
+  __shared__ int s_last;
+  const int64_t P = gridDim.x, me = blockIdx.x;
+  const int64_t q0 = me * total / P, q1 = (me + 1) * total / P;
+  if (threadIdx.x == 0) {
+    tma::mbar_init(&full[0], 1);
+    tma::mbar_init(&full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  // row r < K: estimate row r, else target row r - K; the unit's segment of it
+  auto issue = [&](int64_t q, int s) {   // thread 0
+    const int64_t g = q / units_per_group, u = q - g * units_per_group;
+    const int64_t T = meta[g * B2S_PAIR_META + 0];
+    const int64_t n0 = u * S;
+    const int len = (int)max((int64_t)0, min((int64_t)S, T - n0));
+    const float* e_ = est + meta[g * B2S_PAIR_META + 1] + n0;
+    const float* t_ = tgt + meta[g * B2S_PAIR_META + 2] + n0;
+    unsigned total_bytes = 0;
+    if (len > 0) {
+#pragma unroll
+      for (int r = 0; r < 2 * K; ++r) {
+        const float* src = r < K ? e_ + r * est_stride : t_ + (r - K) * tgt_stride;
+        total_bytes += (unsigned)(((reinterpret_cast<uintptr_t>(src) & 15) + (size_t)len * 4 + 15) & ~(size_t)15);
+      }
+    }
+    tma::fence_proxy_async();   // the buffer was last read through the generic proxy
+    tma::mbar_expect_tx(&full[s], total_bytes);
+    if (len > 0) {
+#pragma unroll
+      for (int r = 0; r < 2 * K; ++r) {
+        const float* src = r < K ? e_ + r * est_stride : t_ + (r - K) * tgt_stride;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        tma::bulk_g2s(seg_sm + (s * 2 * K + r) * RF, reinterpret_cast<const void*>(a & ~(uintptr_t)15),
+                      (unsigned)(((a & 15) + (size_t)len * 4 + 15) & ~(size_t)15), &full[s]);
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    if (q0 < q1) issue(q0, 0);
+    if (q0 + 1 < q1) issue(q0 + 1, 1);
+  }
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = kStatsThreads / 32;
+
+  // flush the CTA's partial statistics of group g
+  auto flush = [&](int64_t g) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double v = warp_sum(acc[i]);
+      if (lane == 0) red[i * nwarps + warp] = v;
+      acc[i] = 0.0;
+    }
+    __syncthreads();
+    const int64_t first_owner = ((g * units_per_group + 1) * P + total - 1) / total - 1;
+    const int64_t last_owner = (((g + 1) * units_per_group) * P + total - 1) / total - 1;
+    const int slot = (int)(me - first_owner), nparts = (int)(last_owner - first_owner + 1);
+    double* mine = partial + (g * slots + slot) * NV;
+    for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
+      double v = 0.0;
+      for (int w = 0; w < nwarps; ++w) v += red[i * nwarps + w];
+      mine[i] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counters + g, 1) == nparts - 1;
+    __syncthreads();
+    if (s_last) {   // block-uniform
+      __threadfence();
+      for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
+        double v = 0.0;
+        const volatile double* p = partial + g * slots * NV + i;
+        for (int c = 0; c < nparts; ++c) v += p[(int64_t)c * NV];
+        stats[g * NV + i] = v;
+      }
+      if (threadIdx.x == 0) counters[g] = 0;
+    }
+    __syncthreads();   // red / s_last may be reused
+  };
+
+  int64_t g_cur = q0 < q1 ? q0 / units_per_group : -1;
+  for (int64_t q = q0; q < q1; ++q) {
+    const int s = (int)((q - q0) & 1);
+    const int64_t g = q / units_per_group, u = q - g * units_per_group;
+    if (g != g_cur) {   // block-uniform
+      flush(g_cur);
+      g_cur = g;
+    }
+    const int64_t T = meta[g * B2S_PAIR_META + 0];
+    const int64_t n0 = u * S;
+    const int len = (int)max((int64_t)0, min((int64_t)S, T - n0));
+    tma::mbar_wait(&full[s], (unsigned)(((q - q0) >> 1) & 1));
+    if (len > 0) {
+      const float* rows[2 * K];
+#pragma unroll
+      for (int r = 0; r < 2 * K; ++r) {
+        const float* src = (r < K ? est + meta[g * B2S_PAIR_META + 1] + r * est_stride
+                                  : tgt + meta[g * B2S_PAIR_META + 2] + (r - K) * tgt_stride) + n0;
+        rows[r] = seg_sm + (s * 2 * K + r) * RF + (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2) + threadIdx.x;
+      }
+#pragma unroll 2
+      for (int j = 0; j < S / kStatsThreads; ++j) {
+        if (threadIdx.x + j * kStatsThreads < len) {
+          double ed[K], td[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            ed[i] = (double)rows[i][j * kStatsThreads];
+            td[i] = (double)rows[K + i][j * kStatsThreads];
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+#pragma unroll
+            for (int jj = 0; jj < K; ++jj) acc[i * K + jj] = fma(ed[i], td[jj], acc[i * K + jj]);
+            acc[K * K + i] = fma(ed[i], ed[i], acc[K * K + i]);
+            acc[K * K + K + i] = fma(td[i], td[i], acc[K * K + K + i]);
+            acc[K * K + 2 * K + i] += ed[i];
+            acc[K * K + 3 * K + i] += td[i];
+          }
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with buffer s
+    if (threadIdx.x == 0 && q + 2 < q1) issue(q + 2, s);
+  }
+  if (g_cur >= 0) flush(g_cur);
+}
+
 // Value of one pair loss and its partial derivatives w.r.t. the estimate-side statistics.
 struct PairEval { double value, dEe, dD, dSe; };
 
@@ -306,49 +470,59 @@ pair_loss_set_kernel(const double* __restrict__ stats, const int64_t* __restrict
   constexpr int NV = K * K + 4 * K;
   __shared__ double red[256];
   const int which = blockIdx.x, kind = set.kind[which], reduction = set.reduction[which];
+  // thread = (example of the tile, pair (i, j)): the K * K double-precision loss evaluations of an example (log10
+  // chains, latency bound) run side by side; the thread of pair 0 then walks the K! assignments
+  constexpr int KK = K * K, TE = 256 / KK;   // examples per tile
+  __shared__ double cost_sm[TE * KK];
+  const int te = threadIdx.x / KK, ij = threadIdx.x - te * KK;
+  const int ci = ij / K, cj = ij - ci * K;
   double local = 0.0;
-  for (int64_t ex = threadIdx.x; ex < examples; ex += blockDim.x) {
-    double cost[K * K];
-#pragma unroll
-    for (int ij = 0; ij < K * K; ++ij) cost[ij] = 0.0;
-    for (int64_t c = 0; c < inner; ++c) {  // fixed order
-      const int64_t g = ex * inner + c;
-      const double* s = stats + g * NV;
-      const double T = (double)meta[g * B2S_PAIR_META];
-#pragma unroll
-      for (int i = 0; i < K; ++i)
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-          cost[i * K + j] += eval_pair(kind, flags, tau, T, s[K * K + i], s[i * K + j], s[K * K + K + j],
-                                       s[K * K + 2 * K + i], s[K * K + 3 * K + j]).value;
-    }
-    int p[K], bp[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { p[k] = k; bp[k] = k; }
-    double best = 0.0;
-    int idx = 0;
-    do {
+  for (int64_t base = 0; base < examples; base += TE) {
+    const int64_t ex = base + te;
+    const bool on = te < TE && ex < examples;
+    if (on) {
       double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int i = 0; i < K; ++i) if (p[k] == i) v += cost[i * K + k];
+      for (int64_t c = 0; c < inner; ++c) {  // fixed order
+        const int64_t g = ex * inner + c;
+        const double* s = stats + g * NV;
+        const double T = (double)meta[g * B2S_PAIR_META];
+        v += eval_pair(kind, flags, tau, T, s[K * K + ci], s[ci * K + cj], s[K * K + K + cj],
+                       s[K * K + 2 * K + ci], s[K * K + 3 * K + cj]).value;
       }
-      if (idx == 0 || candidate_better(v, idx, best, 0)) {   // strictly better only: the first minimum wins
-        best = v;
+      cost_sm[te * KK + ij] = v;
+    }
+    __syncthreads();
+    if (on && ij == 0) {
+      const double* cost = cost_sm + te * KK;
+      int p[K], bp[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) bp[k] = p[k];
-      }
-      ++idx;
-    } while (next_permutation(p, K));
-    if (reduction == B2S_REDUCE_MEAN) best /= (double)(K * inner);
-    const float out = (float)best;
-    loss[which * examples + ex] = out;
+      for (int k = 0; k < K; ++k) { p[k] = k; bp[k] = k; }
+      double best = 0.0;
+      int idx = 0;
+      do {
+        double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) perm[(which * examples + ex) * K + k] = bp[k];
-    local += (double)out;
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) if (p[k] == i) v += cost[i * K + k];
+        }
+        if (idx == 0 || candidate_better(v, idx, best, 0)) {   // strictly better only: the first minimum wins
+          best = v;
+#pragma unroll
+          for (int k = 0; k < K; ++k) bp[k] = p[k];
+        }
+        ++idx;
+      } while (next_permutation(p, K));
+      if (reduction == B2S_REDUCE_MEAN) best /= (double)(K * inner);
+      const float out = (float)best;
+      loss[which * examples + ex] = out;
+#pragma unroll
+      for (int k = 0; k < K; ++k) perm[(which * examples + ex) * K + k] = bp[k];
+      local += (double)out;
+    }
+    __syncthreads();   // cost_sm is rewritten by the next tile
   }
-  // batch mean, fixed order: thread partials (examples tid, tid + 256, ...) summed by thread 0 in thread order
+  // batch mean, fixed order: thread partials (one per example slot of the tiles) folded in thread order
   red[threadIdx.x] = local;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -486,7 +660,7 @@ extern "C" {
 
 int64_t b2s_pair_workspace_bytes(int64_t groups, int64_t max_length, int sources) {
   if (groups <= 0 || sources <= 0) return 16;
-  const int chunks = pair_chunks(groups, max_length);
+  const int chunks = std::max(pair_chunks(groups, max_length), seg_grid(groups, max_length, sources).slots);
   return kTicketBytes + (int64_t)sizeof(double) * groups * chunks * stats_per_group(sources) + 16;
 }
 
@@ -503,8 +677,44 @@ int b2s_pair_stats_forward(const float* estimate, const float* target, const int
   const int chunks = pair_chunks(groups, max_length);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
-  const dim3 grid((unsigned)groups, chunks);
   cudaStream_t st = (cudaStream_t)stream;
+  // Rows that start at 16-byte aligned addresses go to the (group, chunk) kernel with 16-byte loads; anything
+  // else to the segment-staged kernel, whose TMA copies serve any alignment at the same rate (equal timings on
+  // aligned rows: 26.6 vs 28.1 us for the TasNet forward).  Offsets inside `meta` are multiples of the strides
+  // for every wrapper in this package.  B2S_PAIR_SEG=1 / 0 forces the choice.
+  static const int force_seg = [] { const char* e = getenv("B2S_PAIR_SEG"); return e ? atoi(e) : -1; }();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(estimate) | reinterpret_cast<uintptr_t>(target)) & 15) == 0 &&
+                       estimate_source_stride % 4 == 0 && target_source_stride % 4 == 0;
+  if ((force_seg == 1 || (force_seg < 0 && !aligned)) && max_length >= 1) {
+    const SegGrid sg = seg_grid(groups, max_length, sources);
+    const size_t smem = sizeof(float) * 2 * 2 * sources * seg_row_floats(sources);
+#define CALL_SEG(K) do {                                                                                      \
+      static bool configured[64] = {};                                                                         \
+      int dev = 0;                                                                                             \
+      B2S_CUDA(cudaGetDevice(&dev));                                                                           \
+      if (!configured[dev & 63]) {                                                                             \
+        B2S_CUDA(cudaFuncSetAttribute(pair_stats_seg_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                             \
+        configured[dev & 63] = true;                                                                           \
+      }                                                                                                        \
+      pair_stats_seg_kernel<K><<<sg.ctas, kStatsThreads, smem, st>>>(estimate, target, meta, sg.units_per_group, \
+          sg.total, sg.slots, estimate_source_stride, target_source_stride, partial, counters, stats);          \
+    } while (0)
+    switch (sources) {
+      case 1: CALL_SEG(1); break;
+      case 2: CALL_SEG(2); break;
+      case 3: CALL_SEG(3); break;
+      case 4: CALL_SEG(4); break;
+      case 5: CALL_SEG(5); break;
+      case 6: CALL_SEG(6); break;
+      case 7: CALL_SEG(7); break;
+      default: CALL_SEG(8); break;
+    }
+#undef CALL_SEG
+    B2S_LAUNCH_CHECK("pair_stats_seg_kernel");
+    return B2S_OK;
+  }
+  const dim3 grid((unsigned)groups, chunks);
 #define CALL(K) pair_stats_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
       estimate_source_stride, target_source_stride, partial, counters, stats)
   switch (sources) {
