@@ -617,12 +617,7 @@ pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tg
     int mt[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) { a[i] = ca[i]; bm[i] = cb[i]; c[i] = cc[i]; mt[i] = match[i]; }
-    for (int64_t v = v0 + threadIdx.x; v < v1; v += kStatsThreads) {
-      float4 t[K], e[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) t[k] = __ldg(t4 + k * ts4 + v);
-#pragma unroll
-      for (int i = 0; i < K; ++i) e[i] = __ldg(e4 + i * es4 + v);
+    auto emit = [&](int64_t v, const float4 (&t)[K], const float4 (&e)[K]) {
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         float4 tm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -635,6 +630,24 @@ pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tg
         o.w = fmaf(a[i], e[i].w, fmaf(bm[i], tm.w, c[i]));
         g4[i * es4 + v] = o;
       }
+    };
+    int64_t v = v0 + threadIdx.x;
+    for (; K <= 4 && v + kStatsThreads < v1; v += 2 * kStatsThreads) {   // 4K 16-byte loads in flight
+      float4 ta[K], ea[K], tb[K], eb[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { ta[k] = __ldg(t4 + k * ts4 + v); tb[k] = __ldg(t4 + k * ts4 + v + kStatsThreads); }
+#pragma unroll
+      for (int i = 0; i < K; ++i) { ea[i] = __ldg(e4 + i * es4 + v); eb[i] = __ldg(e4 + i * es4 + v + kStatsThreads); }
+      emit(v, ta, ea);
+      emit(v + kStatsThreads, tb, eb);
+    }
+    for (; v < v1; v += kStatsThreads) {
+      float4 t[K], e[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = __ldg(t4 + k * ts4 + v);
+#pragma unroll
+      for (int i = 0; i < K; ++i) e[i] = __ldg(e4 + i * es4 + v);
+      emit(v, t, e);
     }
     if (chunk != nchunks - 1) return;
   }
@@ -805,8 +818,10 @@ int b2s_pair_backward(const float* estimate, const float* target, const int64_t*
   B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
   if (groups == 0) return B2S_OK;
   B2S_REQUIRE(estimate && target && meta && stats && grad_loss && grad_estimate, "NULL device pointer");
-  // about 8 CTAs per SM in one wave; at least 2 float4 units per thread and chunk
-  const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / groups);
+  // one wave of 4 resident CTAs per SM (the register limit of the kernel): 2 / 3 / 4 / 6 / 8 CTAs per SM worth of
+  // chunks -> 31.4 / 28.6 / 25.0 / 29.1 / 27.3 us at batch 64 x 2 x 4 s; at least 2 float4 units per thread and chunk
+  static const int per_sm = [] { const char* e = getenv("B2S_PAIR_BWD_CTAS"); return e ? std::max(1, atoi(e)) : 4; }();
+  const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * per_sm / groups);
   const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_length / (kStatsThreads * 8) + 1, std::min<int64_t>(want, 4096)));
   const dim3 grid((unsigned)groups, chunks);
   cudaStream_t st = (cudaStream_t)stream;
