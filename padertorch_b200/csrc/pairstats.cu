@@ -43,6 +43,7 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
                   double* __restrict__ partial, int* __restrict__ counters, double* __restrict__ stats) {
   constexpr int NV = K * K + 4 * K;
   __shared__ double sm[NV * (kStatsThreads / 32)];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent (the loss-set kernel) may be scheduled
   const int g = blockIdx.x, chunk = blockIdx.y;
   const int64_t T = meta[g * B2S_PAIR_META + 0];
   const float* e_ = est + meta[g * B2S_PAIR_META + 1];
@@ -210,6 +211,7 @@ pair_stats_seg_kernel(const float* __restrict__ est, const float* __restrict__ t
   __shared__ __align__(8) uint64_t full[2];
   __shared__ double red[NV * (kStatsThreads / 32)];
   __shared__ int s_last;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int64_t P = gridDim.x, me = blockIdx.x;
   const int64_t q0 = me * total / P, q1 = (me + 1) * total / P;
   if (threadIdx.x == 0) {
@@ -470,6 +472,8 @@ pair_loss_set_kernel(const double* __restrict__ stats, const int64_t* __restrict
   constexpr int NV = K * K + 4 * K;
   __shared__ double red[256];
   const int which = blockIdx.x, kind = set.kind[which], reduction = set.reduction[which];
+  // launched with programmatic stream serialization: everything above overlaps the tail of the statistics kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // thread = (example of the tile, pair (i, j)): the K * K double-precision loss evaluations of an example (log10
   // chains, latency bound) run side by side; the thread of pair 0 then walks the K! assignments
   constexpr int KK = K * K, TE = 256 / KK;   // examples per tile
@@ -786,7 +790,16 @@ int b2s_pair_loss_set(const double* stats, const int64_t* meta, int64_t groups, 
   const int64_t examples = groups / inner;
   cudaStream_t st = (cudaStream_t)stream;
   if (sources <= 4) {
-#define CALL(K) pair_loss_set_kernel<K><<<count, 256, 0, st>>>(stats, meta, examples, inner, set, flags, tau, loss, perm, mean)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)count);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define CALL(K) B2S_CUDA(cudaLaunchKernelEx(&cfg, pair_loss_set_kernel<K>, stats, meta, examples, inner, set, flags, tau, loss, perm, mean))
     switch (sources) {
       case 1: CALL(1); break;
       case 2: CALL(2); break;
