@@ -38,6 +38,7 @@ SOURCES = 2
 SIZE, SHIFT = 1024, 256
 FRAMES, BINS = 253, 513
 ROTATE = 3            # input sets cycled so a step's 215 MB of inputs were evicted from the 126 MB L2
+GRAPH_STEPS = 12      # steps captured in one CUDA graph (a multiple of ROTATE)
 WORKLOAD = ('fused STFT->mask->PIT-loss path, batch 64 x 4 s x 16 kHz, 2 speakers, STFT(1024,256) '
             '(253 frames x 513 bins); masks synthetic U(0,1), mask network excluded (SURVEY 8d(i))')
 
@@ -247,13 +248,21 @@ def run_ours(args, rank, world, local_rank):
     # The two launches of a step cost ~10x more host time through Python than the kernels run on the
     # device, so the steady-state loop replays one CUDA graph per input set (plans, workspaces and
     # output buffers are created by the warm-up above / inside the capture pool).
-    graphs, results = [], []
+    # One more graph holds GRAPH_STEPS consecutive steps (whole rounds of the input sets): inside it the front-end
+    # of step n + 1 is chained to the fused kernel of step n by programmatic dependent launch like the two kernels
+    # of a step are (its launch and prologue overlap the predecessor's tail); K steps = K // GRAPH_STEPS replays
+    # of it + K % GRAPH_STEPS single-step graphs.
+    graphs, results, round_graph = [], [], None
     if not args.eager:
         for data in sets:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 results.append(step(data))
             graphs.append(g)
+        if not args.single_step_graphs:
+            round_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(round_graph):
+                round_results = [step(sets[j % ROTATE]) for j in range(GRAPH_STEPS)]
         torch.cuda.synchronize()
 
     def run_step(i):
@@ -262,8 +271,20 @@ def run_ours(args, rank, world, local_rank):
             return results[i % ROTATE]
         return step(sets[i % ROTATE])
 
-    for i in range(max(args.warmup, 3)):
-        loss, perm = run_step(i)
+    def run_steps(n):
+        """Exactly n steps, cycling through the input sets; returns the last step's result."""
+        out, i = None, 0
+        if round_graph is not None:
+            for _ in range(n // GRAPH_STEPS):
+                round_graph.replay()
+            i = n - n % GRAPH_STEPS
+            if i:
+                out = round_results[-1]
+        for j in range(i, n):
+            out = run_step(j)
+        return out
+
+    loss, perm = run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -274,8 +295,7 @@ def run_ours(args, rank, world, local_rank):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     start.record()
-    for i in range(args.steps):
-        loss, perm = run_step(i)
+    loss, perm = run_steps(args.steps)
     end.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
@@ -290,10 +310,8 @@ def run_ours(args, rank, world, local_rank):
     t_hold = time.perf_counter()
     i = 0
     while time.perf_counter() - t_hold < 1.0:
-        run_step(i)
-        i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
+        run_steps(63)
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     t_wall2 = time.perf_counter()
     sampler.stop()
@@ -375,7 +393,7 @@ def run_ours(args, rank, world, local_rank):
             'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'samples': SAMPLES, 'sources': SOURCES,
                        'l2': f'inputs larger than L2: {ROTATE} rotating input sets of 215 MB each',
                        'parallelism': f'{world} independent shard(s), no data-path collective',
-                       'launch': 'python eager' if args.eager else 'CUDA graph replay (2 kernel nodes per step)'},
+                       'launch': 'python eager' if args.eager else ('CUDA graph replay (2 kernel nodes per step)' if args.single_step_graphs else f'CUDA graph replay ({GRAPH_STEPS} steps = {2 * GRAPH_STEPS} kernel nodes per graph, 2 kernel nodes per step)')},
             'e2e': {'value': world * BATCH * e2e_steps / e2e_s, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
             'gpu_launches': 2 * args.steps,
@@ -409,6 +427,7 @@ def main():
     parser.add_argument('--warmup', type=int, default=10)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     parser.add_argument('--eager', action='store_true', help='launch from Python instead of CUDA graphs')
+    parser.add_argument('--single-step-graphs', action='store_true', help='one CUDA graph per step instead of one per round of input sets')
     args = parser.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -132,6 +132,9 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     fence_mbar_init();
   }
   __syncwarp();
+  // a kernel launched with programmatic stream serialization behind this one (normally the next STFT front-end,
+  // which waits for this kernel before it touches any data) may be scheduled as SMs free up
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   rf::LaneConsts k;
   k.load(lane_table, lane);
   // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side

@@ -159,10 +159,14 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     tma::fence_mbar_init();
   }
   __syncwarp();
-  // a kernel launched with programmatic stream serialization behind this one (the fused loss) may start now
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
-  k.load(lane_table, lane);
+  k.load(lane_table, lane);   // immutable plan data: may be read before the preceding kernel has finished
+  // Launched with programmatic stream serialization: barriers and constants above overlap the tail of the
+  // preceding kernel; nothing of the caller's data is touched before this wait.  Only then may a kernel launched
+  // the same way behind this one (the fused loss) start -- it reads its own inputs before ITS wait and must not
+  // overtake this kernel's predecessor.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int kS = LAYOUT == B2S_SPEC_INTERLEAVED ? 2 : 1;
   const int offa0 = kS * rf::bin_a(lane, 0), offa4 = kS * (rf::bin_a(lane, 4) - 256);
   const int offb0 = kS * rf::kHalf - offa0, offb4 = kS * rf::kHalf - offa4;
@@ -527,6 +531,18 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
     const int out_area = (kPipeFrames * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
     const size_t smem = kPipeWarps * (sizeof(float) * (kPipeStages * span + out_area) +
                                       sizeof(float2) * kPipeFrames * rf::kTile1);
+    static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * kPipeWarps);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    const int shift_arg = plan->shift;
 #define B2S_PIPE(L, D, S)                                                                               \
     do {                                                                                                \
       static bool configured[64] = {};                                                                  \
@@ -535,8 +551,8 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));        \
         configured[plan->device & 63] = true;                                                           \
       }                                                                                                 \
-      stft1024_warp_kernel<L, D, S><<<grid, 32 * kPipeWarps, smem, stream>>>(x, rows, samples,          \
-          row_stride, pad_left, frames, plan->shift, table, out, ablate);                               \
+      B2S_CUDA(cudaLaunchKernelEx(&cfg, stft1024_warp_kernel<L, D, S>, x, rows, samples, row_stride,    \
+                                  pad_left, frames, shift_arg, table, out, ablate));                    \
     } while (0)
 #define B2S_PIPE_S(L, D) do { if (plan->shift == 256) B2S_PIPE(L, D, true); else B2S_PIPE(L, D, false); } while (0)
     switch (layout) {
