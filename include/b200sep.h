@@ -236,6 +236,14 @@ B2S_API int b2s_pit_targets(const float* spec_mixture, const float* spec_sources
                     int64_t frames, int64_t bins, float* y_abs, float* x_abs,
                     float* cos_phase_difference, b2s_stream stream);
 
+/* The same preparation straight from the waveforms, the complex spectra never leaving the registers (fast
+ * plans: size 1024 / window_length 1024 / shift % 4 == 0; 1..3 sources; all examples full length):
+ * mixture [B, samples], sources [B, K, samples] -> y_abs [B, frames, F], x_abs / cos_phase_difference
+ * [B, frames, K, F].  frames / pad_left as for b2s_stft_forward.                                      */
+B2S_API int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources,
+                         int64_t batch, int64_t samples, int sources_k, int64_t frames, int64_t pad_left,
+                         float* y_abs, float* x_abs, float* cos_phase_difference, b2s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

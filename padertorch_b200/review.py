@@ -216,10 +216,25 @@ def prepare_pit_targets(mixture, sources, stft=None):
     assert mixture.dim() == 2 and sources.dim() == 3 and sources.shape[0] == mixture.shape[0] and \
         sources.shape[2] == mixture.shape[1], (mixture.shape, sources.shape)
     batch, k, samples = sources.shape
+    device = mixture.device
+    plan = stft._plan(device)
+    frames_call, pad_left = stft._frames_of_call(samples)
+    if (lib.b2s_stft_plan_is_fast(plan.handle) and stft.window_length == 1024 and stft.shift % 4 == 0
+            and stft.shift <= 1024 and k <= 3 and batch * frames_call > 0):
+        # one kernel: transforms, magnitudes and phase term in registers (b2s_stft_pit_targets)
+        bins = stft.size // 2 + 1
+        y_abs = torch.empty((batch, frames_call, bins), dtype=torch.float32, device=device)
+        x_abs = torch.empty((batch, frames_call, k, bins), dtype=torch.float32, device=device)
+        cpd = torch.empty((batch, frames_call, k, bins), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            rc = lib.b2s_stft_pit_targets(plan.handle, _lib.ptr(mixture), _lib.ptr(sources), batch, samples, k,
+                                          frames_call, pad_left, _lib.ptr(y_abs), _lib.ptr(x_abs), _lib.ptr(cpd),
+                                          _lib.stream_of(device))
+        _lib.check(rc, 'b2s_stft_pit_targets')
+        return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=frames_call)
     spec_y = stft._spectrum(mixture, _lib.SPEC_INTERLEAVED)       # [B, M, F, 2]
     spec_x = stft._spectrum(sources, _lib.SPEC_INTERLEAVED)       # [B, K, M, F, 2]
     frames, bins = spec_y.shape[1], spec_y.shape[2]
-    device = mixture.device
     y_abs = torch.empty((batch, frames, bins), dtype=torch.float32, device=device)
     x_abs = torch.empty((batch, frames, k, bins), dtype=torch.float32, device=device)
     cpd = torch.empty((batch, frames, k, bins), dtype=torch.float32, device=device)

@@ -114,10 +114,10 @@ def main():
            time_graph(lambda i: (lambda: review.stft_mask_pit_step(ys[i], ss[i], masks[i], stft=stft)), n),
            B * (4 * T * (1 + K) + 4 * M * F * K))
 
-    # ---- batched target preparation on the device: 2 complex STFT launches + 1 pass
+    # ---- batched target preparation on the device
     record('prepare_pit_targets (|Y|, |X|, cpd)',
            time_graph(lambda i: (lambda: review.prepare_pit_targets(ys[i], ss[i], stft=stft)), n),
-           B * (4 * T * (1 + K) + 4 * M * F * (1 + 2 * K)), '3 launches; complex spectra round-trip through HBM')
+           B * (4 * T * (1 + K) + 4 * M * F * (1 + 2 * K)), 'one kernel: transforms, magnitudes and phase term in registers')
 
     # ---- un-fused PIT-SSE (targets materialised), forward and backward, single and dual
     xabs = [stft.magnitude(s).transpose(1, 2).contiguous() for s in ss]
