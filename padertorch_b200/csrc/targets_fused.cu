@@ -22,10 +22,11 @@ using namespace b2s::tma;
 
 namespace {
 
-// warps per CTA: shared memory per warp (K + 1 frames, exchange tiles, 1 + 2K staged rows) grows with K and two
-// CTAs must fit in 227 KB
-__host__ __device__ constexpr int tgt_warps(int K) { return K <= 2 ? 3 : 2; }
-constexpr int kTgtCtasPerSm = 2;
+// warps per CTA: shared memory per warp (K + 1 frames, exchange tiles, 1 + 2K staged rows) grows with K; ONE CTA
+// per SM with as many warps as fit in 227 KB (7 x 31.8 KB at K = 2; two CTAs of 3 warps would leave a seventh
+// pipeline's worth of shared memory unused)
+__host__ __device__ constexpr int tgt_warps(int K) { return K <= 1 ? 8 : (K == 2 ? 7 : 5); }
+constexpr int kTgtCtasPerSm = 1;
 constexpr int F = rf::kBins;
 
 __host__ __device__ constexpr int row_area(int rows) { return (rows * F + 3 + 3) / 4 * 4; }   // + misalignment
@@ -256,10 +257,10 @@ int launch_targets(const b2s_stft_plan* plan, const float* mixture, const float*
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kTgtWarps),
                                                                (int64_t)kNumSMs * kTgtCtasPerSm));
   const size_t smem = sizeof(float) * kTgtWarps * tgt_warp_floats(K);
-  B2S_REQUIRE(smem <= 110 * 1024, "internal: %zu bytes of shared memory", smem);
+  B2S_REQUIRE(smem <= 227 * 1024, "internal: %zu bytes of shared memory", smem);
   static bool configured[64] = {};
   if (!configured[plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(stft_targets_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    B2S_CUDA(cudaFuncSetAttribute(stft_targets_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[plan->device & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
