@@ -32,9 +32,15 @@ using namespace b2s::tma;
 
 namespace {
 
-constexpr int kFusedCtasPerSm = 2;   // <= 255 registers: two interleaved transforms stay in registers
+// Resident pipelines per SM: registers (<= 255 per thread: two interleaved transforms stay in registers) allow 8
+// warps, shared memory per warp grows with K (frames + mask rows).  K <= 2: 2 CTAs x 4 warps; K = 3: ONE CTA with
+// the 7 warps that fit in 227 KB (two CTAs of 3 warps left a seventh pipeline's worth unused); K = 4: 2 x 3.
+__host__ __device__ constexpr int fused_ctas(int K) { return K == 3 ? 1 : 2; }
 // warps per CTA: shared memory per warp grows with K (frames + mask rows); two CTAs must fit in 227 KB
-__host__ __device__ constexpr int fused_warps(int K) { return K <= 2 ? 4 : 3; }
+// (recompute: the variant that also transforms the mixture stages one more frame per warp)
+__host__ __device__ constexpr int fused_warps(int K, bool recompute = false) {
+  return K <= 2 ? 4 : (K == 3 ? (recompute ? 6 : 7) : 3);
+}
 
 struct FusedGrid {
   int grid;            // persistent CTAs
@@ -43,12 +49,12 @@ struct FusedGrid {
   int slots;           // partial-sum slots per example
 };
 
-FusedGrid fused_grid(int64_t batch, int64_t frames, int sources) {
+FusedGrid fused_grid(int64_t batch, int64_t frames, int sources, bool recompute = false) {
   FusedGrid g;
-  const int warps = fused_warps(sources);
+  const int warps = fused_warps(sources, recompute);
   g.total = batch * std::max<int64_t>(1, frames);
   g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, warps),
-                                                       (int64_t)kNumSMs * kFusedCtasPerSm));
+                                                       (int64_t)kNumSMs * fused_ctas(sources)));
   g.warps = std::min<int64_t>((int64_t)g.grid * warps, g.total);   // surplus warps of the last CTA idle
   g.slots = (int)(ceil_div(std::max<int64_t>(1, frames) * g.warps, g.total) + 2);
   return g;
@@ -96,7 +102,7 @@ __device__ __forceinline__ void warp_search_permutations(const double* cost, int
 // One frame position = (K [+1]) transforms whose magnitudes stay in registers as packed (A side, B side)
 // pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in lane 0 only).
 template <int K, bool RECOMPUTE_Y>
-__global__ void __launch_bounds__(32 * fused_warps(K), kFusedCtasPerSm)
+__global__ void __launch_bounds__(32 * fused_warps(K, RECOMPUTE_Y), fused_ctas(K))
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
                       const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames,
@@ -105,7 +111,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
                       int32_t* __restrict__ perm, double* __restrict__ sse, unsigned long long* __restrict__ trace) {
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
-  constexpr int kFusedWarps = fused_warps(K);
+  constexpr int kFusedWarps = fused_warps(K, RECOMPUTE_Y);
   constexpr int NT = RECOMPUTE_Y ? K + 1 : K;   // transforms per position; with RECOMPUTE_Y the mixture is first
   constexpr int kWarpFloats = NT * rf::kSize + 4 * rf::kTile1 + row_area_floats(K);
   extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, 2 exchange tiles, mask / |Y| rows
@@ -403,8 +409,8 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
                  int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
                  cudaStream_t stream) {
-  const FusedGrid g = fused_grid(batch, frames, K);
-  constexpr int kFusedWarps = fused_warps(K);
+  const FusedGrid g = fused_grid(batch, frames, K, yabs == nullptr);
+  const int kFusedWarps = fused_warps(K, yabs == nullptr);
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   // the transform reads its frame with 16-byte shared-memory loads and TMA copies 16-byte units
@@ -416,11 +422,11 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
   const int nt = yabs ? K : K + 1;
   const size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 4 * rf::kTile1 + row_area_floats(K));
   auto kernel = yabs ? stft_pit_fused_kernel<K, false> : stft_pit_fused_kernel<K, true>;
-  B2S_REQUIRE(smem <= 220 * 1024, "internal: %zu bytes of shared memory", smem);
+  B2S_REQUIRE(smem <= 224 * 1024, "internal: %zu bytes of shared memory", smem);
   static bool configured[2][64] = {};   // per (variant, device)
   const int variant = yabs ? 0 : 1;
   if (!configured[variant][plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     configured[variant][plan->device & 63] = true;
   }
   static const bool want_trace = getenv("B2S_FUSED_TRACE") != nullptr;
