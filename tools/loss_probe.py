@@ -28,3 +28,13 @@ for _ in range(3):
     loss.backward()
     emb.grad = None
 torch.cuda.synchronize()
+# PIT-SSE (dual) forward / backward and the target preparation at the bench shape
+import padertorch_b200 as b2s  # noqa: E402
+stft = b2s.ops.STFT(1024, 256)
+prep = review.prepare_pit_targets(s.sum(1), s, stft=stft)
+masks = torch.rand(B, M, K, F, device=dev, requires_grad=True)
+for _ in range(2):
+    out = review.pit_review_losses(masks, prep['Y_abs'], prep['X_abs'], prep['cos_phase_difference'])
+    (out['pit_mse_loss'] + out['pit_ips_loss']).backward()
+    masks.grad = None
+torch.cuda.synchronize()
