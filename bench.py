@@ -270,13 +270,17 @@ def run_ours(args, rank, world, local_rank):
                 fork = torch.cuda.Event()
                 fork.record(main)
                 side.wait_event(fork)
-                round_results, last = [], None
+                # every step keeps its own |Y| buffer alive for the life of the graph: a buffer freed during the
+                # capture could be handed to the next front-end on the side stream while the loss kernel on the
+                # main stream still reads it
+                round_results, round_features = [], []
                 for j in range(GRAPH_STEPS):
                     data = sets[j % ROTATE]
                     with torch.cuda.stream(side):
                         y_abs = stft.magnitude(data['y'])
                         ready = torch.cuda.Event()
                         ready.record(side)
+                    round_features.append(y_abs)
                     main.wait_event(ready)
                     round_results.append(review.stft_mask_pit_step(None, data['s'], data['masks'], stft=stft,
                                                                    observation_abs=y_abs))
@@ -331,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
     if round_graph is not None:
         round_graph.replay()
         torch.cuda.synchronize()
-        for j in (0, GRAPH_STEPS - 1):
+        for j in range(GRAPH_STEPS):
             want_loss, want_perm = step(sets[j % ROTATE])
             got_loss, got_perm = round_results[j]
             assert torch.equal(got_loss, want_loss) and torch.equal(got_perm, want_perm), 'captured graph differs from the eager step'
