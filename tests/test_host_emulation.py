@@ -27,3 +27,15 @@ def test_packed_rfft_host_emulation(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     err = float(out.stdout.split()[-1])
     assert err < 1e-6, out.stdout
+
+
+@pytest.mark.skipif(shutil.which('g++') is None or _cuda_include() is None, reason='needs g++ and the CUDA headers')
+def test_pair_transform_prototype_host_emulation(tmp_path):
+    """tools/prototypes/cfft_pair.cuh (two real frames per 1024-point complex FFT, one exchange): both spectra
+    against a double-precision DFT, lane by lane on the CPU."""
+    exe = tmp_path / 'cfft_pair_emulate'
+    subprocess.run(['g++', '-O1', '-std=c++17', '-I', _cuda_include(), '-o', str(exe),
+                    os.path.join(ROOT, 'tests', 'host', 'cfft_pair_emulate.cpp')], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert float(out.stdout.split()[-1]) < 1e-6, out.stdout
