@@ -1,7 +1,7 @@
 // Throughput of the prototype pair transform (tools/prototypes/cfft_pair.cuh: two real frames per 1024-point
 // complex FFT, one exchange) with NO global traffic in the loop: frames resident in shared memory, 2 CTAs x 4
-// warps per SM.  Compare with the SM-side floor of the fused kernel (profiles/r1_fused_floor.txt: 43.6 us for
-// 32 384 transforms + SSE = 1.35 ns per frame chip-wide).
+// warps per SM.  Compare with rfft_rate.cu (the transform in the tree in the same setting) and with the SM-side
+// floor of the fused kernel (profiles/r1_fused_floor.txt: 43.6 us for 32 384 transforms + SSE = 1.35 ns per frame).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o pair_rate pair_rate.cu && ./pair_rate
 #include <cstdio>
 #include <vector>
