@@ -184,6 +184,33 @@ B2S_API int b2s_pair_backward(const float* estimate, const float* target, const 
                       const int32_t* perm, const float* grad_loss, int64_t grad_loss_stride,
                       double grad_scale, float* grad_estimate, b2s_stream stream);
 
+/* compute_pairwise_losses (padertorch/ops/losses/source_separation.py:127-241) from the statistics:
+ * matrix[example][i][j] = reduce over the example's `inner` groups of l(e_i, t_j), `reduction` SUM or MEAN
+ * (the loss_fn's own default over the leading axes of estimate[i], :230-241).  float [examples][K][K].        */
+B2S_API int b2s_pair_loss_matrix(const double* stats, const int64_t* meta, int64_t groups, int64_t inner,
+                         int sources, int kind, int flags, double tau, int reduction, float* matrix,
+                         b2s_stream stream);
+/* grad_estimate = d/d estimate of sum_{example,i,j} grad_matrix[example][i][j] * matrix[example][i][j]
+ * (autograd of the matrix above; the reference differentiates K^2 separate loss_fn calls).                    */
+B2S_API int b2s_pair_matrix_backward(const float* estimate, const float* target, const int64_t* meta,
+                             int64_t groups, int64_t inner, int64_t max_length, int sources,
+                             int64_t estimate_source_stride, int64_t target_source_stride,
+                             const double* stats, int kind, int flags, double tau, int reduction,
+                             const float* grad_matrix, float* grad_estimate, b2s_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Assignment on the device for a batch of K x K cost matrices (float [batch][K][K], K <= B2S_MAX_SOURCES),
+ * replacing the host round trip of pit_loss_from_loss_matrix (padertorch/ops/losses/source_separation.py:
+ * 285-298: to_numpy + scipy.optimize.linear_sum_assignment / pb_bss greedy).  Exhaustive search, exact.
+ *   orientation 0: assignment[k] = row matched to column k, candidates in itertools.permutations order, first
+ *                  minimum wins (pit_loss, :112-122);
+ *   orientation 1: assignment[i] = column matched to row i (scipy's col_ind), first minimum in lexicographic order;
+ *   greedy != 0 (orientation 1): repeatedly the smallest remaining entry (algorithm='greedy', parity unpinned:
+ *                  pb_bss is not part of the reference tree).
+ * value (may be NULL): float [batch], the assignment's total cost.                                            */
+B2S_API int b2s_assign(const float* cost, int64_t batch, int sources, int orientation, int greedy,
+               int32_t* assignment, float* value, b2s_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Deep-clustering affinity loss, deep_clustering_loss (padertorch/ops/losses/source_separation.py:
  * 13-31) batched over the per-example loop of DeepClusteringModel.review (padertorch/contrib/tcl/

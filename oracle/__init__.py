@@ -11,7 +11,7 @@ Rules (see the task statement, item 3):
 * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
   ``--impl reference`` legs may import this package, and only as the checker or as the
   timed CPU baseline -- never as the thing shipped.  ``padertorch_b200`` (the product)
-  must not import it; ``tests/test_layout.py`` enforces that.
+  must not import it; ``tests/test_capi_cpu.py::test_product_never_imports_oracle`` enforces that.
 * parity status: **pinned**.  ``tests/test_oracle_golden.py`` checks this package against
   (a) the known-answer vectors the reference's own tests / doctests hold for the path and
   (b) fixtures under ``tests/golden/`` that ``oracle/make_golden.py`` recorded by running

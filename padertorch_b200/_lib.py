@@ -52,6 +52,11 @@ SIGNATURES = {
     'b2s_pair_backward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
                                   c_void, c_int, c_int, c_dbl, c_int, c_int, c_void, c_void, c_i64,
                                   c_dbl, c_void, c_void]),
+    'b2s_pair_loss_matrix': (c_int, [c_void, c_void, c_i64, c_i64, c_int, c_int, c_int, c_dbl, c_int, c_void,
+                                     c_void]),
+    'b2s_pair_matrix_backward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
+                                         c_void, c_int, c_int, c_dbl, c_int, c_void, c_void, c_void]),
+    'b2s_assign': (c_int, [c_void, c_i64, c_int, c_int, c_int, c_void, c_void, c_void]),
     'b2s_dc_workspace_bytes': (c_i64, [c_i64, c_i64, c_i64, c_int]),
     'b2s_dc_forward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_int,
                                ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_void,

@@ -25,15 +25,30 @@ def _nvcc():
     return 'nvcc'
 
 
-def _newest_input():
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))]
+STAMP = os.path.join(OBJ, 'source.sha256')
+
+
+def source_hash():
+    """sha256 over every input of the build (sources, headers, the C ABI header, this file, the flags)."""
+    import hashlib
+    paths = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh')))
     paths.append(os.path.join(HERE, '..', 'include', 'b200sep.h'))
     paths.append(os.path.abspath(__file__))
-    return max(os.path.getmtime(p) for p in paths)
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def is_current():
-    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_input()
+    """True when the library on disk was built from exactly the sources on disk (content hash, not mtime: a
+    checkout or a copy to another box changes every mtime but not the contents)."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == source_hash()
 
 
 def build(force=False, verbose=False):
@@ -61,6 +76,8 @@ def build(force=False, verbose=False):
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError(f'link failed:\n{proc.stdout}\n{proc.stderr}')
+    with open(STAMP, 'w') as f:
+        f.write(source_hash() + '\n')
     return LIB
 
 

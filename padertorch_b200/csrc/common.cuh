@@ -38,6 +38,23 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: a C entry
+// point must not leave a different current device behind (callers other than the Python wrappers rely on it).
+struct DeviceGuard {
+  int previous = -1;
+  cudaError_t status;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&previous);
+    if (status == cudaSuccess && previous != device) status = cudaSetDevice(device); else if (status == cudaSuccess) previous = -1;
+  }
+  ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define B2S_ON_DEVICE(device)                 \
+  ::b2s::DeviceGuard device_guard__(device);  \
+  B2S_CUDA(device_guard__.status)
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 // Reduction workspaces: [kMaxTickets int ticket counters][double partial sums].  The counters sit at a

@@ -32,32 +32,54 @@ using namespace b2s::tma;
 
 namespace {
 
-// Resident pipelines per SM: registers (<= 255 per thread: two interleaved transforms stay in registers) allow 8
-// warps, shared memory per warp grows with K (frames + mask rows).  K <= 2: 2 CTAs x 4 warps; K = 3: ONE CTA with
-// the 7 warps that fit in 227 KB (two CTAs of 3 warps left a seventh pipeline's worth unused); K = 4: 2 x 3.
-__host__ __device__ constexpr int fused_ctas(int K) { return K == 3 ? 1 : 2; }
-// warps per CTA: shared memory per warp grows with K (frames + mask rows); two CTAs must fit in 227 KB
-// (recompute: the variant that also transforms the mixture stages one more frame per warp)
-__host__ __device__ constexpr int fused_warps(int K, bool recompute = false) {
-  return K <= 2 ? 4 : (K == 3 ? (recompute ? 6 : 7) : 3);
+// Resident pipelines per SM.  A pipeline (= warp) needs shared memory for its NT frames, NS exchange tiles and the
+// mask / |Y| rows of a position, and registers for NS interleaved transforms.  Default: NS = 2 (two transforms
+// interleaved, <= 255 registers), 8 warps per SM.  Measured alternatives at the north-star shape (B200, round 2,
+// profiles/r2_fused_shapes.txt): one transform at a time at <= 168 registers and 12 warps per SM (19 040 bytes per
+// warp at K = 2) in one, two or three CTAs takes 58.3 / 60.0 / 59.6 us against 50.5 us, 10 warps at <= 200
+// registers 55.7 us -- the SM's time per position is the same 0.36 us whatever the number of resident warps (the
+// transform alone: 0.78 ns per frame at 8 warps per SM, 0.73 at 12, tools/ubench/rfft_rate.cu): the kernel is bound
+// by the work per position on the shared-memory and FP32 pipes, not by latency hiding.
+struct FusedShape { int warps, ctas, ns; };
+__host__ __device__ constexpr FusedShape fused_shape(int K, bool recompute, int variant) {
+  // variant 0 = default of this (K, recompute); others are tuning alternatives (B2S_FUSED_VARIANT, K <= 2 only)
+  if (K <= 2 && !recompute) {
+    switch (variant) {
+      case 1: return FusedShape{12, 1, 1};
+      case 2: return FusedShape{6, 2, 1};
+      case 3: return FusedShape{4, 3, 1};
+      case 4: return FusedShape{10, 1, 1};   // <= 200 registers
+      default: return FusedShape{4, 2, 2};
+    }
+  }
+  if (K <= 2) return FusedShape{4, 2, 2};
+  if (K == 3) return FusedShape{recompute ? 6 : 7, 1, 2};
+  return FusedShape{3, 2, 2};
 }
+constexpr int kFusedVariants = 5;
 
 struct FusedGrid {
   int grid;            // persistent CTAs
-  int64_t warps;       // pipelines = grid * kFusedWarps
+  int64_t warps;       // pipelines = grid * warps per CTA
   int64_t total;       // batch * frames positions (dense enumeration over `frames`)
   int slots;           // partial-sum slots per example
 };
 
-FusedGrid fused_grid(int64_t batch, int64_t frames, int sources, bool recompute = false) {
+FusedGrid fused_grid(int64_t batch, int64_t frames, FusedShape shape) {
   FusedGrid g;
-  const int warps = fused_warps(sources, recompute);
   g.total = batch * std::max<int64_t>(1, frames);
-  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, warps),
-                                                       (int64_t)kNumSMs * fused_ctas(sources)));
-  g.warps = std::min<int64_t>((int64_t)g.grid * warps, g.total);   // surplus warps of the last CTA idle
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, shape.warps),
+                                                       (int64_t)kNumSMs * shape.ctas));
+  g.warps = std::min<int64_t>((int64_t)g.grid * shape.warps, g.total);   // surplus warps of the last CTA idle
   g.slots = (int)(ceil_div(std::max<int64_t>(1, frames) * g.warps, g.total) + 2);
   return g;
+}
+// the workspace must hold the partial sums of whichever shape is launched
+int fused_max_slots(int64_t batch, int64_t frames, int K) {
+  int slots = 0;
+  for (int r = 0; r < 2; ++r)
+    for (int v = 0; v < kFusedVariants; ++v) slots = std::max(slots, fused_grid(batch, frames, fused_shape(K, r != 0, v)).slots);
+  return slots;
 }
 
 // first position of warp w: floor(w * total / warps); warp owning position x: ceil((x + 1) * warps / total) - 1
@@ -101,20 +123,21 @@ __device__ __forceinline__ void warp_search_permutations(const double* cost, int
 
 // One frame position = (K [+1]) transforms whose magnitudes stay in registers as packed (A side, B side)
 // pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in lane 0 only).
-template <int K, bool RECOMPUTE_Y>
-__global__ void __launch_bounds__(32 * fused_warps(K, RECOMPUTE_Y), fused_ctas(K))
+template <int K, bool RECOMPUTE_Y, int WARPS, int CTAS, int NS>
+__global__ void __launch_bounds__(32 * WARPS, CTAS)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
                       const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames,
                       int shift, int64_t pad_left, const float4* __restrict__ lane_table, int slots,
                       double* __restrict__ partial, int* __restrict__ counters, float* __restrict__ loss,
-                      int32_t* __restrict__ perm, double* __restrict__ sse, unsigned long long* __restrict__ trace) {
+                      int32_t* __restrict__ perm, double* __restrict__ sse, unsigned long long* __restrict__ trace,
+                      int ablate /* tuning only: 1 no SSE, 2 no square roots, 4 no row copies, 8 no frame copies */) {
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
-  constexpr int kFusedWarps = fused_warps(K, RECOMPUTE_Y);
+  constexpr int kFusedWarps = WARPS;
   constexpr int NT = RECOMPUTE_Y ? K + 1 : K;   // transforms per position; with RECOMPUTE_Y the mixture is first
-  constexpr int kWarpFloats = NT * rf::kSize + 4 * rf::kTile1 + row_area_floats(K);
-  extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, 2 exchange tiles, mask / |Y| rows
+  constexpr int kWarpFloats = NT * rf::kSize + 2 * NS * rf::kTile1 + row_area_floats(K);
+  extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, NS exchange tiles, mask / |Y| rows
   __shared__ __align__(8) uint64_t bars[kFusedWarps][2];
   __shared__ double totals_sm[kFusedWarps][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,9 +150,14 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     }
   };
   stamp(0);
+  if (trace && lane == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[((size_t)blockIdx.x * kFusedWarps + warp) * 8 + 6] = smid;
+  }
   float* sig = smem + warp * kWarpFloats;                          // frame of transform t at sig + t * 1024
   float2* tile = reinterpret_cast<float2*>(sig + NT * rf::kSize);
-  float* rows_area = sig + NT * rf::kSize + 4 * rf::kTile1;
+  float* rows_area = sig + NT * rf::kSize + 2 * NS * rf::kTile1;
   uint64_t* bar_sig = &bars[warp][0];
   uint64_t* bar_rows = &bars[warp][1];
   if (lane == 0) {
@@ -192,13 +220,15 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (q >= p_end) return;
     set_ctx(b);
     if (m >= ctx_M) { sig_by_tma = false; return; }
+    if ((ablate & 8) && q != p_begin) { sig_by_tma = false; return; }
     const int s0 = m * shift - pad;
     const bool a16 = ctx_a16 && (s0 & 3) == 0;
     const bool bulk = a16 && s0 >= 0 && s0 + rf::kSize <= ctx_T;
     sig_by_tma = bulk;
     if (bulk) {
       if (lane == 0) {
-        fence_proxy_async();   // the frames were last read through the generic proxy
+        // (no fence.proxy.async: the area was only READ through the generic proxy, every lane's loads were consumed
+        // before the __syncwarp() that precedes this call, and the copy's writes arrive a memory latency later)
         mbar_expect_tx(bar_sig, NT * rf::kSize * 4u);
 #pragma unroll
         for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, ctx_row[t] + s0, rf::kSize * 4u, bar_sig);
@@ -234,6 +264,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (q >= p_end) return;
     set_ctx(b);
     if (m >= ctx_M) return;
+    if ((ablate & 4) && q != p_begin) return;
     const uintptr_t am = reinterpret_cast<uintptr_t>(ctx_mask + m * (K * F));
     const uintptr_t ay = RECOMPUTE_Y ? 0 : reinterpret_cast<uintptr_t>(ctx_y + m * F);
     off_m = (int)(am & 15) >> 2;
@@ -241,7 +272,6 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (lane == 0) {
       const unsigned bytes_m = (unsigned)(((am & 15) + K * F * 4 + 15) & ~15u);
       const unsigned bytes_y = RECOMPUTE_Y ? 0u : (unsigned)(((ay & 15) + F * 4 + 15) & ~15u);
-      fence_proxy_async();
       mbar_expect_tx(bar_rows, bytes_m + bytes_y);
       bulk_g2s(rows_area, reinterpret_cast<const void*>(am & ~(uintptr_t)15), bytes_m, bar_rows);
       if (!RECOMPUTE_Y)
@@ -282,8 +312,15 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       const int vi = lane % NV, c0 = lane / NV;
       double s = 0.0;
       if (c0 < per) {
+        // four loads in flight per lane (the values come from L2: one round trip instead of one per slot)
         const volatile double* p = partial + b * slots * NV + vi;
-        for (int c = c0; c < nparts; c += per) s += p[(int64_t)c * NV];
+        for (int c = c0; c < nparts; c += 4 * per) {
+          const double d0 = p[(int64_t)c * NV];
+          const double d1 = c + per < nparts ? p[(int64_t)(c + per) * NV] : 0.0;
+          const double d2 = c + 2 * per < nparts ? p[(int64_t)(c + 2 * per) * NV] : 0.0;
+          const double d3 = c + 3 * per < nparts ? p[(int64_t)(c + 3 * per) * NV] : 0.0;
+          s += d0; s += d1; s += d2; s += d3;
+        }
       }
 #pragma unroll
       for (int j = 1; j < per; ++j) {
@@ -312,9 +349,11 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   int64_t b = p_begin / frames;
   int m = (int)(p_begin - b * frames);
   const int frames_i = (int)frames;
-  start_signals(p_begin, b, m);
-  // everything above is independent of the preceding kernel; |Y| (and, conservatively, the masks) are not
+  // Barriers, the constant table and the index arithmetic above are independent of the preceding kernel; every
+  // caller tensor (source / mixture waveforms, masks, |Y|) may have been written by it: nothing of them is
+  // requested before this wait.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  start_signals(p_begin, b, m);
   start_rows(p_begin, b, m);
   stamp(1);
   int64_t b_cur = p_begin < p_end ? b : -1;
@@ -347,13 +386,13 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     // holds bin 256 on both sides: its B copy is zeroed (and so is the matching mask load)
     auto magnitudes = [&](const float2 (&ya)[8], const float2 (&yb)[8], float ydc, float ynyq, float2 (&x)[9]) {
 #pragma unroll
-      for (int p = 0; p < 8; ++p) x[p] = mag2(ya[p], yb[p]);
+      for (int p = 0; p < 8; ++p) x[p] = (ablate & 2) ? make_float2(ya[p].x + ya[p].y, yb[p].x + yb[p].y) : mag2(ya[p], yb[p]);
       if (first) x[7].y = 0.f;
       x[8] = first ? make_float2(fabsf(ydc), fabsf(ynyq)) : make_float2(0.f, 0.f);
     };
     float2 x[NT][9];   // with RECOMPUTE_Y x[0] = |Y|, sources follow
 #pragma unroll(K <= 2 ? 2 : 1)
-    for (int t = 0; t + 1 < NT; t += 2) {
+    for (int t = 0; NS == 2 && t + 1 < NT; t += 2) {
       float2 ya[2][8], yb[2][8];
       float ydc[2], ynyq[2];
       // the frames of the LAST transforms are in registers after pass 1: start the next position's copy
@@ -362,20 +401,30 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
       magnitudes(ya[1], yb[1], ydc[1], ynyq[1], x[t + 1]);
     }
-    if (NT & 1) {
+    // one transform at a time: all of them (NS == 1) or the odd one out (NS == 2)
+#pragma unroll
+    for (int t = (NS == 2 ? (NT & ~1) : 0); t < NT; ++t) {
       float2 ya[1][8], yb[1][8];
       float ydc[1], ynyq[1];
-      auto next_copy = [&]() { start_signals(q + 1, bn, mn); };
-      rf::rfft_streams<1, false, false>(sig + (NT - 1) * rf::kSize, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
-      magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[NT - 1]);
+      auto next_copy = [&]() { if (t == NT - 1) start_signals(q + 1, bn, mn); };
+      rf::rfft_streams<1, false, false>(sig + t * rf::kSize, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
+      magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
     }
     constexpr int XS = RECOMPUTE_Y ? 1 : 0;   // x[XS + j] = |STFT(s_j)|
 
     // ---- SSE of this frame: e_i = mask_i * |Y| against every source magnitude
-    mbar_wait(bar_rows, rows_phase);   // the rows of this frame have landed
-    rows_phase ^= 1;
+    if (!(ablate & 4) || q == p_begin) {
+      mbar_wait(bar_rows, rows_phase);   // the rows of this frame have landed
+      rows_phase ^= 1;
+    }
     const float* mrow = rows_area + off_m;
     const float* yrow = rows_area + mask_area_floats(K) + off_y;
+    if (ablate & 1) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int p = 0; p < 9; ++p) acc[t % NV] = rf::add2(acc[t % NV], x[t][p]);
+    } else
 #pragma unroll
     for (int p = 0; p < 9; ++p) {
       const int ka = p < 8 ? (p < 4 ? k0 : k4) + 64 * p : 0;
@@ -404,13 +453,14 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   stamp(5);
 }
 
-template <int K>
-int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* yabs, const float* sources,
-                 const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
-                 int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
-                 cudaStream_t stream) {
-  const FusedGrid g = fused_grid(batch, frames, K, yabs == nullptr);
-  const int kFusedWarps = fused_warps(K, yabs == nullptr);
+template <int K, bool RECOMPUTE, int VARIANT>
+int launch_fused_shape(const b2s_stft_plan* plan, const float* mixture, const float* yabs, const float* sources,
+                       const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
+                       int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
+                       cudaStream_t stream) {
+  constexpr FusedShape shape = fused_shape(K, RECOMPUTE, VARIANT);
+  const FusedGrid g = fused_grid(batch, frames, shape);
+  constexpr int kFusedWarps = shape.warps;
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   // the transform reads its frame with 16-byte shared-memory loads and TMA copies 16-byte units
@@ -419,26 +469,26 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
   B2S_REQUIRE(frames >= 1, "the fused STFT->PIT kernel needs at least one frame");
   B2S_REQUIRE(samples < ((int64_t)1 << 30) && frames < ((int64_t)1 << 20) && pad_left < ((int64_t)1 << 30),
               "signal too long for the fused STFT->PIT kernel (%lld samples)", (long long)samples);
-  const int nt = yabs ? K : K + 1;
-  const size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 4 * rf::kTile1 + row_area_floats(K));
-  auto kernel = yabs ? stft_pit_fused_kernel<K, false> : stft_pit_fused_kernel<K, true>;
-  B2S_REQUIRE(smem <= 224 * 1024, "internal: %zu bytes of shared memory", smem);
-  static bool configured[2][64] = {};   // per (variant, device)
-  const int variant = yabs ? 0 : 1;
-  if (!configured[variant][plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    configured[variant][plan->device & 63] = true;
+  constexpr int nt = RECOMPUTE ? K + 1 : K;
+  constexpr size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 2 * shape.ns * rf::kTile1 + row_area_floats(K));
+  static_assert(smem <= 227 * 1024, "pipeline shape exceeds the shared memory of an SM");
+  auto kernel = stft_pit_fused_kernel<K, RECOMPUTE, shape.warps, shape.ctas, shape.ns>;
+  static bool configured[64] = {};   // per device (one static per instantiation)
+  if (!configured[plan->device & 63]) {
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[plan->device & 63] = true;
   }
   static const bool want_trace = getenv("B2S_FUSED_TRACE") != nullptr;
   unsigned long long* trace = nullptr;
   const size_t nstamps = (size_t)g.grid * kFusedWarps * 8;
+  (void)smem;
   if (want_trace) {
     B2S_CUDA(cudaMalloc(&trace, nstamps * sizeof(unsigned long long)));
     B2S_CUDA(cudaMemsetAsync(trace, 0, nstamps * sizeof(unsigned long long), stream));
   }
   // Programmatic dependent launch: the kernel may start while its predecessor in the stream (normally the STFT
-  // front-end that produces |Y|) drains -- constants, barriers and the first source frames do not depend on it;
-  // the kernel executes griddepcontrol.wait before it touches |Y|.  B2S_PDL=0 falls back to a plain launch.
+  // front-end that produces |Y|) drains -- barriers, the constant table and the index arithmetic do not depend on
+  // it; the kernel executes griddepcontrol.wait before it requests ANY caller tensor.  B2S_PDL=0 = plain launch.
   static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.grid);
@@ -453,8 +503,10 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
   const int shift = plan->shift;
   const float4* table = plan->lane_fwd;
   const int slots = g.slots;
+  const char* ab = getenv("B2S_FUSED_ABLATE");   // tuning only (results are wrong with any bit set)
+  const int ablate = ab ? atoi(ab) : 0;
   B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, mixture, yabs, sources, mask, meta, batch, samples, frames, shift,
-                              pad_left, table, slots, partial, counters, loss, perm, sse, trace));
+                              pad_left, table, slots, partial, counters, loss, perm, sse, trace, ablate));
   B2S_LAUNCH_CHECK("stft_pit_fused_kernel");
   if (want_trace) {   // tuning aid: per-warp timeline statistics on stderr
     std::vector<unsigned long long> h(nstamps);
@@ -499,6 +551,17 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
       bmin = std::min(bmin, s4 / kFusedWarps); bmax = std::max(bmax, s4 / kFusedWarps);
     }
     fprintf(stderr, "  per-block mean loop duration: min %.1f max %.1f us\n", bmin, bmax);
+    if (const char* path = getenv("B2S_FUSED_TRACE_FILE")) {   // raw stamps: warp, smid, us since the first entry
+      if (FILE* f = fopen(path, "w")) {
+        for (size_t w = 0; w < nstamps / 8; ++w) {
+          if (!h[w * 8]) continue;
+          fprintf(f, "%zu %llu", w, h[w * 8 + 6]);
+          for (int i = 0; i < 6; ++i) fprintf(f, " %.3f", h[w * 8 + i] ? (double)(h[w * 8 + i] - t0) * 1e-3 : -1.0);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
     // loop duration by kind of range: with / without frames that touch the zero padding (first / last 3 frames)
     double se = 0, sn = 0; size_t ne = 0, nn = 0;
     for (int64_t w = 0; w < g.warps; ++w) {
@@ -515,14 +578,35 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
   return B2S_OK;
 }
 
+template <int K>
+int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* yabs, const float* sources,
+                 const float* mask, const int64_t* meta, int64_t batch, int64_t samples, int64_t frames,
+                 int64_t pad_left, float* loss, int32_t* perm, double* sse, void* workspace,
+                 cudaStream_t stream) {
+#define B2S_FUSED_ARGS plan, mixture, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse, workspace, stream
+  if (!yabs) return launch_fused_shape<K, true, 0>(B2S_FUSED_ARGS);
+  if (K == 2) {   // tuning alternatives of the headline configuration (tools/hot_bench.py)
+    const char* e = getenv("B2S_FUSED_VARIANT");   // read per launch: one process can sweep the shapes
+    const int variant = e ? atoi(e) : 0;
+    switch (variant) {
+      case 1: return launch_fused_shape<K, false, K == 2 ? 1 : 0>(B2S_FUSED_ARGS);
+      case 2: return launch_fused_shape<K, false, K == 2 ? 2 : 0>(B2S_FUSED_ARGS);
+      case 3: return launch_fused_shape<K, false, K == 2 ? 3 : 0>(B2S_FUSED_ARGS);
+      case 4: return launch_fused_shape<K, false, K == 2 ? 4 : 0>(B2S_FUSED_ARGS);
+      default: break;
+    }
+  }
+  return launch_fused_shape<K, false, 0>(B2S_FUSED_ARGS);
+#undef B2S_FUSED_ARGS
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t b2s_stft_pit_workspace_bytes(int64_t batch, int64_t frames, int sources) {
   if (batch <= 0 || sources <= 0) return kTicketBytes + 16;
-  const FusedGrid g = fused_grid(batch, frames, sources);
-  return kTicketBytes + (int64_t)sizeof(double) * batch * g.slots * sources * sources + 16;
+  return kTicketBytes + (int64_t)sizeof(double) * batch * fused_max_slots(batch, frames, sources) * sources * sources + 16;
 }
 
 int b2s_stft_pit_forward(const b2s_stft_plan* plan, const float* mixture, const float* observation_abs,
@@ -538,7 +622,7 @@ int b2s_stft_pit_forward(const b2s_stft_plan* plan, const float* mixture, const 
   B2S_REQUIRE(mixture || observation_abs, "need the mixture or its magnitude spectrogram");
   if (batch == 0) return B2S_OK;
   B2S_REQUIRE(sources && mask && loss && perm && sse && workspace, "NULL device pointer");
-  B2S_CUDA(cudaSetDevice(plan->device));
+  B2S_ON_DEVICE(plan->device);
   cudaStream_t st = (cudaStream_t)stream;
   switch (sources_k) {
     case 1: return launch_fused<1>(plan, mixture, observation_abs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse, workspace, st);

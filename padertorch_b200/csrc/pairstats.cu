@@ -671,6 +671,135 @@ pair_backward_kernel(const float* __restrict__ est, const float* __restrict__ tg
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- pairwise loss matrix
+// compute_pairwise_losses (padertorch/ops/losses/source_separation.py:127-241): matrix[ex][i][j] =
+// reduce over the example's `inner` groups of l(e_i, t_j) -- every entry is a function of the statistics the
+// forward pass already holds, so the K x K matrix costs no further read of the signals.  One CTA per example.
+__global__ void __launch_bounds__(64)
+pair_loss_matrix_kernel(const double* __restrict__ stats, const int64_t* __restrict__ meta, int64_t inner, int K,
+                        int kind, int flags, double tau, int reduction, float* __restrict__ matrix) {
+  const int64_t ex = blockIdx.x;
+  const int NV = stats_per_group(K);
+  for (int ij = threadIdx.x; ij < K * K; ij += blockDim.x) {
+    const int i = ij / K, j = ij - i * K;
+    double v = 0.0;
+    for (int64_t c = 0; c < inner; ++c) {  // fixed order
+      const int64_t g = ex * inner + c;
+      const double* s = stats + g * NV;
+      const double T = (double)meta[g * B2S_PAIR_META];
+      v += eval_pair(kind, flags, tau, T, s[K * K + i], s[i * K + j], s[K * K + K + j], s[K * K + 2 * K + i],
+                     s[K * K + 3 * K + j]).value;
+    }
+    if (reduction == B2S_REDUCE_MEAN) v /= (double)inner;
+    matrix[ex * K * K + ij] = (float)v;
+  }
+}
+
+// Gradient of sum_{i,j} G[ex][i][j] matrix[ex][i][j] w.r.t. the estimate rows: every pair loss is a function of
+// (Ee_i, D_ij, Se_i), so  grad e_i = (sum_j 2 G_ij dEe_ij) e_i + sum_j (G_ij dD_ij) t_j + sum_j G_ij dSe_ij  -- one
+// streaming pass that reads the K estimate rows and the K target rows of a group once.
+template <int K>
+__global__ void __launch_bounds__(kStatsThreads)
+pair_matrix_backward_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                            const int64_t* __restrict__ meta, int nchunks, int64_t inner, int64_t est_stride,
+                            int64_t tgt_stride, const double* __restrict__ stats, int kind, int flags, double tau,
+                            int reduction, const float* __restrict__ grad_matrix, float* __restrict__ grad_est) {
+  constexpr int NV = K * K + 4 * K;
+  __shared__ float ca[K], cb[K][K], cc[K];
+  const int g = blockIdx.x, chunk = blockIdx.y;
+  const int64_t ex = g / inner;
+  const int64_t T = meta[g * B2S_PAIR_META + 0];
+  const int64_t eoff = meta[g * B2S_PAIR_META + 1];
+  const float* e_ = est + eoff;
+  const float* t_ = tgt + meta[g * B2S_PAIR_META + 2];
+  float* g_ = grad_est + eoff;
+  if (threadIdx.x < K) {
+    const int i = threadIdx.x;
+    const double* s = stats + (int64_t)g * NV;
+    const double w = reduction == B2S_REDUCE_MEAN ? 1.0 / (double)inner : 1.0;
+    double a = 0.0, c = 0.0;
+    for (int j = 0; j < K; ++j) {
+      const PairEval r = eval_pair(kind, flags, tau, (double)T, s[K * K + i], s[i * K + j], s[K * K + K + j],
+                                   s[K * K + 2 * K + i], s[K * K + 3 * K + j]);
+      const double up = w * (double)grad_matrix[(ex * K + i) * K + j];
+      a += up * 2.0 * r.dEe;
+      c += up * r.dSe;
+      cb[i][j] = (float)(up * r.dD);
+    }
+    ca[i] = (float)a;
+    cc[i] = (float)c;
+  }
+  __syncthreads();
+  const int64_t n0 = T * chunk / nchunks, n1 = T * (chunk + 1) / nchunks;
+  for (int64_t n = n0 + threadIdx.x; n < n1; n += kStatsThreads) {
+    float t[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) t[j] = __ldg(t_ + j * tgt_stride + n);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float v = fmaf(ca[i], __ldg(e_ + i * est_stride + n), cc[i]);
+#pragma unroll
+      for (int j = 0; j < K; ++j) v = fmaf(cb[i][j], t[j], v);
+      g_[i * est_stride + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- assignment
+// Optimal assignment of a batch of K x K cost matrices by exhaustive search (K <= 8: at most 40 320 candidates,
+// one CTA per matrix), replacing the host round trip of pit_loss_from_loss_matrix
+// (padertorch/ops/losses/source_separation.py:285-288: to_numpy + scipy.optimize.linear_sum_assignment).
+//   orientation 0: out[k] = row (estimate) matched to column (target) k, candidates in itertools.permutations
+//                  order, first minimum wins -- the convention of pit_loss (:112-122);
+//   orientation 1: out[i] = column matched to row i (scipy's col_ind for row_ind = 0..K-1), first minimum in
+//                  lexicographic order of col_ind;
+//   greedy != 0  : orientation 1 by repeatedly taking the smallest remaining entry (ties: lowest row, then
+//                  lowest column) -- the 'greedy' algorithm of :291-296 (pb_bss is not on disk: parity unpinned).
+__global__ void __launch_bounds__(256)
+assign_kernel(const float* __restrict__ cost, int K, int orientation, int greedy, int32_t* __restrict__ out,
+              float* __restrict__ value) {
+  __shared__ double c[B2S_MAX_SOURCES * B2S_MAX_SOURCES];
+  const int64_t ex = blockIdx.x;
+  const float* m = cost + ex * K * K;
+  for (int ij = threadIdx.x; ij < K * K; ij += blockDim.x) {
+    const int i = ij / K, j = ij - i * K;
+    // search_permutations minimises sum_k c[p[k] * K + k]
+    c[orientation == 0 ? ij : j * K + i] = (double)m[ij];
+  }
+  __syncthreads();
+  if (greedy) {
+    if (threadIdx.x == 0) {
+      bool row_used[B2S_MAX_SOURCES] = {}, col_used[B2S_MAX_SOURCES] = {};
+      double total = 0.0;
+      for (int step = 0; step < K; ++step) {
+        int bi = -1, bj = -1;
+        double bv = 0.0;
+        for (int i = 0; i < K; ++i) {
+          if (row_used[i]) continue;
+          for (int j = 0; j < K; ++j) {
+            if (col_used[j]) continue;
+            const double v = (double)m[i * K + j];
+            if (bi < 0 || v < bv) { bi = i; bj = j; bv = v; }
+          }
+        }
+        row_used[bi] = true; col_used[bj] = true;
+        out[ex * K + bi] = bj;
+        total += bv;
+      }
+      if (value) value[ex] = (float)total;
+    }
+    return;
+  }
+  double best;
+  int bp[B2S_MAX_SOURCES];
+  search_permutations(c, K, best, bp);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < K; ++k) out[ex * K + k] = bp[k];
+    if (value) value[ex] = (float)best;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -853,6 +982,68 @@ int b2s_pair_backward(const float* estimate, const float* target, const int64_t*
   }
 #undef CALL
   B2S_LAUNCH_CHECK("pair_backward_kernel");
+  return B2S_OK;
+}
+
+int b2s_pair_loss_matrix(const double* stats, const int64_t* meta, int64_t groups, int64_t inner, int sources,
+                         int kind, int flags, double tau, int reduction, float* matrix, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
+  B2S_REQUIRE(kind >= B2S_LOSS_MSE && kind < B2S_LOSS_SA_SDR, "loss kind %d has no pairwise form", kind);
+  B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
+  B2S_REQUIRE(reduction == B2S_REDUCE_SUM || reduction == B2S_REDUCE_MEAN, "reduction must be sum or mean");
+  B2S_REQUIRE(!(flags & B2S_FLAG_OFFSET_INVARIANT) || kind == B2S_LOSS_SI_SDR,
+              "offset_invariant exists for si_sdr only");
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(stats && meta && matrix, "NULL device pointer");
+  pair_loss_matrix_kernel<<<(unsigned)(groups / inner), 64, 0, (cudaStream_t)stream>>>(
+      stats, meta, inner, sources, kind, flags, tau, reduction, matrix);
+  B2S_LAUNCH_CHECK("pair_loss_matrix_kernel");
+  return B2S_OK;
+}
+
+int b2s_pair_matrix_backward(const float* estimate, const float* target, const int64_t* meta, int64_t groups,
+                             int64_t inner, int64_t max_length, int sources, int64_t estimate_source_stride,
+                             int64_t target_source_stride, const double* stats, int kind, int flags, double tau,
+                             int reduction, const float* grad_matrix, float* grad_estimate, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES, "sources=%d unsupported", sources);
+  B2S_REQUIRE(kind >= B2S_LOSS_MSE && kind < B2S_LOSS_SA_SDR, "loss kind %d has no pairwise form", kind);
+  B2S_REQUIRE(inner >= 1 && groups % inner == 0, "groups must be a multiple of inner");
+  B2S_REQUIRE(reduction == B2S_REDUCE_SUM || reduction == B2S_REDUCE_MEAN, "reduction must be sum or mean");
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(estimate && target && meta && stats && grad_matrix && grad_estimate, "NULL device pointer");
+  const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * 4 / groups);
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(max_length / (kStatsThreads * 4) + 1, std::min<int64_t>(want, 4096)));
+  const dim3 grid((unsigned)groups, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(K) pair_matrix_backward_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
+      inner, estimate_source_stride, target_source_stride, stats, kind, flags, tau, reduction, grad_matrix, \
+      grad_estimate)
+  switch (sources) {
+    case 1: CALL(1); break;
+    case 2: CALL(2); break;
+    case 3: CALL(3); break;
+    case 4: CALL(4); break;
+    case 5: CALL(5); break;
+    case 6: CALL(6); break;
+    case 7: CALL(7); break;
+    default: CALL(8); break;
+  }
+#undef CALL
+  B2S_LAUNCH_CHECK("pair_matrix_backward_kernel");
+  return B2S_OK;
+}
+
+int b2s_assign(const float* cost, int64_t batch, int sources, int orientation, int greedy, int32_t* assignment,
+               float* value, b2s_stream stream) {
+  B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
+              "device assignment supports 1..%d sources (got %d)", B2S_MAX_SOURCES, sources);
+  B2S_REQUIRE(orientation == 0 || orientation == 1, "orientation must be 0 (pit_loss) or 1 (col_ind)");
+  B2S_REQUIRE(!greedy || orientation == 1, "the greedy assignment returns col_ind (orientation 1)");
+  B2S_REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return B2S_OK;
+  B2S_REQUIRE(cost && assignment, "NULL device pointer");
+  assign_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(cost, sources, orientation, greedy, assignment, value);
+  B2S_LAUNCH_CHECK("assign_kernel");
   return B2S_OK;
 }
 

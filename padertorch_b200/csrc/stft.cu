@@ -198,7 +198,7 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
       by_tma = bulk ? (by_tma | (1u << slot)) : (by_tma & ~(1u << slot));
       if (bulk) {
         if (lane == 0) {
-          tma::fence_proxy_async();   // the slot was last read through the generic proxy
+          // (no fence.proxy.async: the slot was only READ through the generic proxy, see fused.cu)
           tma::mbar_expect_tx(bar + slot, (unsigned)span * 4u);
           tma::bulk_g2s(ring + slot * span, xr + s0, (unsigned)span * 4u, bar + slot);
         }
@@ -504,11 +504,46 @@ int64_t floor_div(int64_t a, int64_t b) {
 
 int check_plan(const b2s_stft_plan* plan) {
   B2S_REQUIRE(plan != nullptr, "stft plan is NULL");
-  B2S_CUDA(cudaSetDevice(plan->device));
   return B2S_OK;
 }
 
 bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
+// launch of one instantiation of the warp-pipeline kernel
+struct PipeArgs {
+  const float* x; int64_t rows, samples, row_stride, pad_left, frames; int shift; const float4* table; float* out;
+  int ablate, layout, device; cudaStream_t stream;
+};
+template <int L, bool D, bool S, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm, bool COMPACT = false,
+          int STAGES = kPipeStages>
+int launch_pipe(const PipeArgs& a) {
+  const int64_t units = a.rows * ceil_div(a.frames, NS);
+  const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * CTAS);
+  const int span = (NS - 1) * a.shift + fft::kSize;
+  const int out_area = (NS * (L <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
+  const size_t smem = kPipeWarps * (sizeof(float) * (STAGES * span + out_area) + sizeof(float2) * NS * rf::kTile1);
+  static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(32 * kPipeWarps);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  auto kernel = stft1024_warp_kernel<L, D, S, NS, CTAS, COMPACT, STAGES>;
+  static bool configured[64] = {};
+  if (!configured[a.device & 63]) {
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[a.device & 63] = true;
+  }
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, a.x, a.rows, a.samples, a.row_stride, a.pad_left, a.frames, a.shift,
+                              a.table, a.out, a.ablate));
+  B2S_LAUNCH_CHECK("stft1024_warp_kernel");
+  return B2S_OK;
+}
 
 // forward-type launch shared by b2s_stft_forward and b2s_istft_backward
 int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int64_t samples,
@@ -522,39 +557,23 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
     const bool twice = interior_scale == 2.f;
     const float4* table = twice ? plan->lane_adj : plan->lane_fwd;   // (synthesis, doubled) / (analysis)
     B2S_REQUIRE(win == (twice ? plan->swin : plan->awin), "internal: window / table mismatch");
-    const int64_t units = rows * ceil_div(frames, kPipeFrames);
-    B2S_REQUIRE(units < ((int64_t)1 << 30) && samples < ((int64_t)1 << 30) && pad_left < ((int64_t)1 << 30),
-                "signal too large for the STFT warp kernel (%lld units of %lld samples)", (long long)units,
+    B2S_REQUIRE(rows * frames < ((int64_t)1 << 30) && samples < ((int64_t)1 << 30) && pad_left < ((int64_t)1 << 30),
+                "signal too large for the STFT warp kernel (%lld frames of %lld samples)", (long long)(rows * frames),
                 (long long)samples);
-    const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * kPipeCtasPerSm);
-    const int span = (kPipeFrames - 1) * plan->shift + fft::kSize;
-    const int out_area = (kPipeFrames * (layout <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
-    const size_t smem = kPipeWarps * (sizeof(float) * (kPipeStages * span + out_area) +
-                                      sizeof(float2) * kPipeFrames * rf::kTile1);
-    static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(32 * kPipeWarps);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    const int shift_arg = plan->shift;
-#define B2S_PIPE(L, D, S)                                                                               \
-    do {                                                                                                \
-      static bool configured[64] = {};                                                                  \
-      if (!configured[plan->device & 63]) {                                                             \
-        B2S_CUDA(cudaFuncSetAttribute(stft1024_warp_kernel<L, D, S>,                                    \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));        \
-        configured[plan->device & 63] = true;                                                           \
-      }                                                                                                 \
-      B2S_CUDA(cudaLaunchKernelEx(&cfg, stft1024_warp_kernel<L, D, S>, x, rows, samples, row_stride,    \
-                                  pad_left, frames, shift_arg, table, out, ablate));                    \
-    } while (0)
-#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) B2S_PIPE(L, D, true); else B2S_PIPE(L, D, false); } while (0)
+    const PipeArgs pa{x, rows, samples, row_stride, pad_left, frames, plan->shift, table, out, ablate, layout,
+                      plan->device, stream};
+    // tuning alternatives of the headline configuration (|Y| epilogue, shift 256): tools/hot_bench.py
+    const char* ve = getenv("B2S_FWD_VARIANT");   // read per launch: one process can sweep the shapes
+    const int variant = ve ? atoi(ve) : 0;
+    if (layout == B2S_SPEC_ABS && plan->shift == 256 && variant != 0) {
+      switch (variant) {
+        case 1: return launch_pipe<B2S_SPEC_ABS, false, true, 2, 3, false, 1>(pa);
+        case 2: return launch_pipe<B2S_SPEC_ABS, false, true, 1, 3, false, 2>(pa);
+        case 3: return launch_pipe<B2S_SPEC_ABS, false, true, 1, 4, true, 1>(pa);
+        default: break;
+      }
+    }
+#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) return launch_pipe<L, D, true>(pa); else return launch_pipe<L, D, false>(pa); } while (0)
     switch (layout) {
       case B2S_SPEC_INTERLEAVED: if (twice) B2S_PIPE_S(B2S_SPEC_INTERLEAVED, true); else B2S_PIPE_S(B2S_SPEC_INTERLEAVED, false); break;
       case B2S_SPEC_CONCAT: if (twice) B2S_PIPE_S(B2S_SPEC_CONCAT, true); else B2S_PIPE_S(B2S_SPEC_CONCAT, false); break;
@@ -562,8 +581,6 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
       default: B2S_PIPE_S(B2S_SPEC_LOG1P_ABS, false); break;
     }
 #undef B2S_PIPE_S
-#undef B2S_PIPE
-    B2S_LAUNCH_CHECK("stft1024_warp_kernel");
   } else if (plan->fast) {
     const int64_t want = ceil_div(total, kFwdWarps);
     const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 3 * 4);
@@ -683,7 +700,7 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
   B2S_REQUIRE(window_length >= 1 && window_length <= size,
               "window_length must be in [1, size] (got %d, size %d)", window_length, size);
   B2S_REQUIRE(analysis_window && synthesis_window, "window pointers must not be NULL");
-  B2S_CUDA(cudaSetDevice(device));
+  B2S_ON_DEVICE(device);
   std::vector<float> aw(size, 0.f), sw(size, 0.f);
   for (int k = 0; k < window_length; ++k) {
     aw[k] = (float)analysis_window[k];
@@ -745,7 +762,7 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
 
 int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
   if (!plan) return B2S_OK;
-  cudaSetDevice(plan->device);
+  DeviceGuard guard(plan->device);
   cudaFree(plan->awin); cudaFree(plan->swin); cudaFree(plan->tw);
   cudaFree(plan->lane_fwd); cudaFree(plan->lane_adj);
   cudaFree(plan->lane_inv_syn); cudaFree(plan->lane_inv_ana);
@@ -764,6 +781,7 @@ int b2s_stft_forward(const b2s_stft_plan* plan, const float* signal, int64_t row
                      int64_t row_stride, int64_t pad_left, int64_t frames, int layout, float* spec,
                      b2s_stream stream) {
   if (int rc = check_plan(plan)) return rc;
+  B2S_ON_DEVICE(plan->device);
   B2S_REQUIRE(layout >= 0 && layout <= 3, "unknown spectrum layout %d", layout);
   B2S_REQUIRE(rows >= 0 && samples >= 0 && frames >= 0 && pad_left >= 0, "negative extent");
   B2S_REQUIRE(rows * frames == 0 || (signal && spec), "NULL device pointer");
@@ -775,6 +793,7 @@ int b2s_istft_backward(const b2s_stft_plan* plan, const float* grad_signal, int6
                        int64_t samples_out, int64_t crop_left, int64_t frames, int layout,
                        float* grad_spec, b2s_stream stream) {
   if (int rc = check_plan(plan)) return rc;
+  B2S_ON_DEVICE(plan->device);
   B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
   B2S_REQUIRE(rows * frames == 0 || (grad_signal && grad_spec), "NULL device pointer");
   // d signal / d Re,Im = c_f * STFT with the synthesis window (c_f = 2 for interior bins)
@@ -786,6 +805,7 @@ int b2s_istft_forward(const b2s_stft_plan* plan, const float* spec, int64_t rows
                       int layout, int64_t crop_left, int64_t samples_out, float* signal,
                       float* scratch, b2s_stream stream) {
   if (int rc = check_plan(plan)) return rc;
+  B2S_ON_DEVICE(plan->device);
   B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
   B2S_REQUIRE(rows * samples_out == 0 || (spec || frames == 0) && signal, "NULL device pointer");
   return launch_inverse(plan, spec, rows, frames, layout, crop_left, samples_out, plan->swin, 2.f,
@@ -796,6 +816,7 @@ int b2s_stft_backward(const b2s_stft_plan* plan, const float* grad_spec, int64_t
                       int layout, int64_t pad_left, int64_t samples, float* grad_signal,
                       float* scratch, b2s_stream stream) {
   if (int rc = check_plan(plan)) return rc;
+  B2S_ON_DEVICE(plan->device);
   B2S_REQUIRE(layout == B2S_SPEC_INTERLEAVED || layout == B2S_SPEC_CONCAT, "layout must be complex");
   B2S_REQUIRE(rows * samples == 0 || (grad_spec || frames == 0) && grad_signal, "NULL device pointer");
   return launch_inverse(plan, grad_spec, rows, frames, layout, pad_left, samples, plan->awin, 1.f,

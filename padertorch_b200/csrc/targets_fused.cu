@@ -107,7 +107,8 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
     sig_by_tma = bulk;
     if (bulk) {
       if (lane == 0) {
-        fence_proxy_async();   // the frames were last read through the generic proxy
+        // (no fence.proxy.async: the area was only READ through the generic proxy, every lane's loads were consumed
+        // before the __syncwarp() that precedes this call, and the copy's writes arrive a memory latency later)
         mbar_expect_tx(bar_sig, NT * rf::kSize * 4u);
 #pragma unroll
         for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, ctx_row[t] + s0, rf::kSize * 4u, bar_sig);
@@ -298,7 +299,7 @@ int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const 
               "signal too long for the fused target preparation (%lld samples)", (long long)samples);
   if (batch * frames == 0) return B2S_OK;
   B2S_REQUIRE(mixture && sources && y_abs && x_abs && cos_phase_difference, "NULL device pointer");
-  B2S_CUDA(cudaSetDevice(plan->device));
+  B2S_ON_DEVICE(plan->device);
   cudaStream_t st = (cudaStream_t)stream;
   switch (sources_k) {
     case 1: return launch_targets<1>(plan, mixture, sources, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);

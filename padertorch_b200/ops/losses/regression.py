@@ -30,6 +30,15 @@ def _get_threshold(soft_sdr_max):
     return 10 ** (-soft_sdr_max / 10)
 
 
+def _real_view(estimate, target):
+    """abs(e - t)^2 of complex signals (regression.py:4-18 take ``torch.abs`` first) is the squared norm of
+    the difference's (re, im) view: complex inputs become real rows of twice the length."""
+    if torch.is_complex(estimate) or torch.is_complex(target):
+        estimate = torch.view_as_real(estimate.to(torch.complex64)).flatten(-2)
+        target = torch.view_as_real(target.to(torch.complex64)).flatten(-2)
+    return estimate, target
+
+
 def _rowwise(estimate, target, kind, flags=0, tau=-1.0):
     _lib.require_cuda_float(estimate, 'estimate')
     _lib.require_cuda_float(target, 'target')
@@ -37,6 +46,8 @@ def _rowwise(estimate, target, kind, flags=0, tau=-1.0):
     if estimate.shape != target.shape:
         estimate, target = torch.broadcast_tensors(estimate, target)
     lead = estimate.shape[:-1]
+    if lead.numel() == 0:   # no rows: nothing to launch
+        return estimate.new_zeros(lead) + 0 * estimate.sum()
     dense, problem = _pairs.rowwise_problem(estimate, target)
     values, _ = _pairs.PairLossFunction.apply(dense, problem, kind, flags, tau, _lib.REDUCE_NONE, False)
     return values.view(lead)
@@ -48,7 +59,12 @@ def mse_loss(estimate: torch.Tensor, target: torch.Tensor, reduction: str = 'sum
     >>> mse_loss(torch.tensor([[1., 2, 3], [4, 5, 6]]).cuda(), torch.tensor([[2., 3, 4], [4, 0, 6]]).cuda())  # doctest: +SKIP
     tensor(9.3333, device='cuda:0')
     """
-    return _reduce(_rowwise(estimate, target, _lib.LOSS_MSE), reduction=reduction)
+    complex_input = torch.is_complex(estimate) or torch.is_complex(target)
+    estimate, target = _real_view(estimate, target)
+    value = _rowwise(estimate, target, _lib.LOSS_MSE)
+    if complex_input:   # the mean runs over T complex samples, the kernel averaged 2T real ones
+        value = value * 2
+    return _reduce(value, reduction=reduction)
 
 
 def log_mse_loss(estimate: torch.Tensor, target: torch.Tensor, reduction: str = 'sum',
@@ -63,10 +79,7 @@ def sdr_loss(estimate: torch.Tensor, target: torch.Tensor, reduction: str = 'mea
              soft_sdr_max: float = None):
     """``sdr_loss`` (regression.py:131-175): -10 log10(|t|^2 / (|e - t|^2 [+ tau |t|^2]))."""
     tau = _get_threshold(soft_sdr_max)
-    if torch.is_complex(estimate) or torch.is_complex(target):
-        # |.|^2 of a complex difference equals the squared norm of its real view
-        estimate = torch.view_as_real(estimate).flatten(-2)
-        target = torch.view_as_real(target).flatten(-2)
+    estimate, target = _real_view(estimate, target)   # doctest regression.py:153-156
     # the kernel returns -10 log10(.) per row, i.e. already the negated SDR
     return _reduce(_rowwise(estimate, target, _lib.LOSS_SDR, tau=tau), reduction=reduction)
 
@@ -95,10 +108,15 @@ def source_aggregated_sdr_loss(estimate: torch.Tensor, target: torch.Tensor,
                                soft_sdr_max: float = None) -> torch.Tensor:
     """``source_aggregated_sdr_loss`` (regression.py:344-376): squares of all targets and all
     errors are summed before the ratio."""
+    estimate, target = _real_view(estimate, target)
     _lib.require_cuda_float(estimate, 'estimate')
     _lib.require_cuda_float(target, 'target')
     _pairs.check_target(target)
     tau = _get_threshold(soft_sdr_max)
+    if estimate.shape != target.shape:   # the reference broadcasts through ``estimate - target``
+        estimate, target = torch.broadcast_tensors(estimate, target)
+    if estimate.numel() == 0:            # 0 / 0, as the reference's sums over nothing give
+        return estimate.new_full((), float('nan'))
     dense, problem = _pairs.rowwise_problem(estimate, target)
     problem.inner = problem.groups          # one example made of every row
     value, _ = _pairs.PairLossFunction.apply(dense, problem, _lib.LOSS_SA_SDR, 0, tau,

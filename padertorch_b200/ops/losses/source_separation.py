@@ -112,8 +112,8 @@ def deep_clustering_loss(x, t):
 
 
 # ------------------------------------------------------------------------------------------ PIT
-# loss_fn identity -> how the kernels evaluate it inside pit_loss:
-#   ('sse',)                              torch.nn.functional.mse_loss over [outer, K, inner]
+# loss_fn identity -> how the kernels evaluate it:
+#   ('sse',)                              torch.nn.functional.mse_loss (mean over every element)
 #   ('pair', kind, flags, reduction)      time-domain regression loss with its default reduction
 _FAST_PIT = {
     torch.nn.functional.mse_loss: ('sse',),
@@ -123,23 +123,83 @@ _FAST_PIT = {
     regression.sdr_loss: ('pair', _lib.LOSS_SDR, 0, _lib.REDUCE_MEAN),
     regression.si_sdr_loss: ('pair', _lib.LOSS_SI_SDR, 0, _lib.REDUCE_MEAN),
 }
+_CROSS_ENTROPY = (torch.nn.functional.cross_entropy,)
 
 
 def register_fast_loss(loss_fn, like):
     """Let `loss_fn` (e.g. the reference's own ``padertorch.ops.losses.si_sdr_loss`` object) take
-    the kernel path of our function `like` inside pit_loss."""
+    the kernel path of our function `like` inside pit_loss / compute_pairwise_losses."""
     _FAST_PIT[loss_fn] = _FAST_PIT[like]
 
 
-def _pair_pit_problem(estimate, target):
-    """estimate / target [K, ..., T] -> groups over the middle axes."""
-    k, length = estimate.shape[0], estimate.shape[-1]
-    e = estimate.reshape(k, -1, length).contiguous()
-    t = target.reshape(k, -1, length).contiguous()
-    inner = e.shape[1]
+def _fast_spec(loss_fn):
+    try:
+        return _FAST_PIT.get(loss_fn)
+    except TypeError:       # unhashable callable
+        return None
+
+
+def _check_pit_arguments(estimate, target, axis, loss_fn):
+    """The argument contract of source_separation.py:95-110 (same messages)."""
+    sources = estimate.size()[axis]
+    assert sources < 30, f'Are you sure? sources={sources}, estimate.shape={estimate.shape}, target.shape={target.shape}'
+    if loss_fn in _CROSS_ENTROPY:
+        assert axis % estimate.ndimension() == 1, axis
+        without_k = [n for d, n in enumerate(estimate.shape) if d != axis % estimate.ndimension()]
+        assert without_k == list(target.shape), (
+            f'{estimate.shape} (N, K, ...) does not match {target.shape} (N, ...)'
+        )
+    else:
+        assert estimate.size() == target.size(), f'{estimate.size()} != {target.size()}'
+    return sources
+
+
+def _pair_rows(estimate, target, axis, spec):
+    """Rows for the statistics kernel: [K, inner, length] with the permuted axis in front.
+    'sse' (torch mse_loss = mean over every element): one row per source; regression losses: the last
+    axis is time, the axes in between are reduced with the loss's own default reduction."""
+    k = estimate.shape[axis]
+    e = estimate.movedim(axis, 0)
+    t = target.movedim(axis, 0)
+    if spec[0] == 'sse':
+        e, t = e.reshape(k, 1, -1), t.reshape(k, 1, -1)
+    else:
+        e, t = e.reshape(k, -1, e.shape[-1]), t.reshape(k, -1, t.shape[-1])
+    e, t = e.contiguous(), t.contiguous()
+    inner, length = e.shape[1], e.shape[2]
     meta = _pairs.dense_meta(inner, length, length, e.device)
-    return e, _pairs.PairProblem(e, t, meta, inner, inner, k, length, inner * length, inner * length,
+    problem = _pairs.PairProblem(e, t, meta, inner, inner, k, length, inner * length, inner * length,
                                  covers_all=True)
+    return e, problem
+
+
+def _pair_args(spec):
+    if spec[0] == 'sse':
+        return _lib.LOSS_MSE, 0, _lib.REDUCE_SUM
+    return spec[1], spec[2], spec[3]
+
+
+def _cross_entropy_matrix(estimate, target, sources):
+    """[c, k] = mean over positions of -log_softmax(estimate)[:, c] where the label is k
+    (the matrix of source_separation.py:203-221; cross entropy is not on the kernel path)."""
+    log_p = torch.log_softmax(estimate, dim=1).movedim(1, -1)              # [..., c]
+    hit = torch.nn.functional.one_hot(target, num_classes=sources).to(estimate.dtype)   # [..., k]
+    positions = target.numel()
+    return -(log_p.reshape(positions, sources).t() @ hit.reshape(positions, sources)) / positions
+
+
+def _first_minimum(matrix_batch, orientation=0, greedy=False):
+    """Device assignment (b2s_assign) of float32 [B, K, K] cost matrices -> (int32 [B, K], float32 [B])."""
+    lib = _lib.load()
+    m = matrix_batch.detach().to(torch.float32).contiguous()
+    batch, k = m.shape[0], m.shape[1]
+    out = torch.empty((batch, k), dtype=torch.int32, device=m.device)
+    value = torch.empty(batch, dtype=torch.float32, device=m.device)
+    with torch.cuda.device(m.device):
+        rc = lib.b2s_assign(_lib.ptr(m), batch, k, orientation, int(greedy), _lib.ptr(out), _lib.ptr(value),
+                            _lib.stream_of(m.device))
+    _lib.check(rc, 'b2s_assign')
+    return out, value
 
 
 def pit_loss(
@@ -150,78 +210,98 @@ def pit_loss(
         return_permutation: bool = False
 ):
     """
-    Permutation invariant loss function (source_separation.py:34-124).  Calls `loss_fn` on every
-    possible permutation between `estimate`s and `target`s and returns the minimum loss among them.
-    The tensors are permuted along `axis`; ``estimate[permutation[k]]`` is matched with
-    ``target[k]``.  Does not support batch dimension.  Does not support PackedSequence.
+    Permutation invariant loss function (source_separation.py:34-124): the minimum of `loss_fn` over
+    all permutations of `estimate` along `axis`; ``estimate[permutation[k]]`` is matched with
+    ``target[k]``, the first minimum in ``itertools.permutations`` order wins.  Does not support a
+    batch dimension or PackedSequence.
 
-    For ``torch.nn.functional.mse_loss`` and the regression losses of this package the K x K pair
-    terms are accumulated in one kernel pass and the permutations are searched on the device; any
-    other callable runs the reference's permutation loop on the device tensors.
+    ``torch.nn.functional.mse_loss`` and the regression losses of this package: the K x K pair terms
+    are accumulated in one kernel pass and the permutations are searched on the device.
+    ``cross_entropy``: pair matrix + the same device search.  Any other callable has no pairwise
+    structure to exploit: it is evaluated once per permutation on the device tensors.
     """
-    sources = estimate.size()[axis]
-    assert sources < 30, f'Are you sure? sources={sources}, estimate.shape={estimate.shape}, target.shape={target.shape}'
+    sources = _check_pit_arguments(estimate, target, axis, loss_fn)
+    spec = _fast_spec(loss_fn)
+    ndim = estimate.ndimension()
 
-    if loss_fn in [torch.nn.functional.cross_entropy]:
-        assert axis % estimate.ndimension() == 1, axis
-        estimate_shape = list(estimate.shape)
-        del estimate_shape[axis]
-        assert estimate_shape == list(target.shape), (
-            f'{estimate.shape} (N, K, ...) does not match {target.shape} (N, ...)'
-        )
-    else:
-        assert estimate.size() == target.size(), (
-            f'{estimate.size()} != {target.size()}'
-        )
-
-    fast = _FAST_PIT.get(loss_fn) if callable(loss_fn) else None
-    if fast is not None and sources <= _lib.MAX_SOURCES:
+    if spec is not None and sources <= _lib.MAX_SOURCES:
         _lib.require_cuda_float(estimate, 'estimate')
         _lib.require_cuda_float(target, 'target')
-        ndim = estimate.ndimension()
-        if fast[0] == 'sse':
+        if spec[0] == 'sse':
             ax = axis % ndim
             outer = 1
-            for s in estimate.shape[:ax]:
-                outer *= s
+            for n in estimate.shape[:ax]:
+                outer *= n
             e3 = estimate.reshape(outer, sources, -1).contiguous()
             t3 = target.reshape(outer, sources, -1).contiguous()
             if e3.shape[-1] > 0 and outer > 0:
                 problem = _sse.dense_problem(e3, t3)
-                if target.requires_grad:
-                    loss, perm, _ = _sse.PitSseFunction.apply(problem, 1, e3, t3)
-                else:
-                    loss, perm, _ = _sse.PitSseFunction.apply(problem, 1, e3)
-                min_loss = loss[0, 0]
+                inputs = (e3, t3) if target.requires_grad else (e3,)
+                loss, perm, _ = _sse.PitSseFunction.apply(problem, 1, *inputs)
                 if return_permutation:
-                    return min_loss, tuple(perm[0, 0].tolist())
-                return min_loss
-        elif axis % ndim == 0 and ndim >= 2:
+                    return loss[0, 0], tuple(perm[0, 0].tolist())
+                return loss[0, 0]
+        elif ndim >= 2:
             _pairs.check_target(target)
-            dense, problem = _pair_pit_problem(estimate, target)
-            _, kind, flags, reduction = fast
+            dense, problem = _pair_rows(estimate, target, axis, spec)
+            kind, flags, reduction = _pair_args(spec)
             loss, perm = _pairs.PairLossFunction.apply(dense, problem, kind, flags, -1.0, reduction, True)
-            min_loss = loss[0]
             if return_permutation:
-                return min_loss, tuple(perm[0].tolist())
-            return min_loss
+                return loss[0], tuple(perm[0].tolist())
+            return loss[0]
 
-    # generic path: the reference algorithm on the caller's (device) tensors
-    candidates = []
-    indexer = [slice(None), ] * estimate.ndim
-    permutations = list(itertools.permutations(range(sources)))
-    for permutation in permutations:
-        indexer[axis] = permutation
-        candidates.append(loss_fn(
-            estimate[tuple(indexer)],
-            target
-        ))
-    min_loss, idx = torch.min(torch.stack(candidates), dim=0)
+    if loss_fn in _CROSS_ENTROPY and estimate.is_cuda and sources <= _lib.MAX_SOURCES:
+        matrix = _cross_entropy_matrix(estimate, target, sources)            # [c, k]
+        perm, _ = _first_minimum(matrix[None])
+        picked = matrix[perm[0].long(), torch.arange(sources, device=matrix.device)].sum()
+        if return_permutation:
+            return picked, tuple(perm[0].tolist())
+        return picked
 
+    # opaque callable: one evaluation per permutation, all on the device; the scalar candidates are compared on
+    # the host, which is where the first-minimum rule of a CPU torch.min (:119) is defined
+    orders = list(itertools.permutations(range(sources)))
+    rows = torch.tensor(orders, dtype=torch.long, device=estimate.device).reshape(len(orders), sources)
+    values = [loss_fn(estimate.index_select(axis, row), target) for row in rows]
+    stacked = torch.stack(values)
+    winner = int(torch.min(stacked.detach().cpu(), dim=0).indices)
     if return_permutation:
-        return min_loss, permutations[int(idx)]
-    else:
-        return min_loss
+        return stacked[winner], orders[winner]
+    return stacked[winner]
+
+
+class _PairMatrixFunction(torch.autograd.Function):
+    """estimate rows -> K x K loss matrix of one example, from the pair statistics (b2s_pair_loss_matrix),
+    differentiable w.r.t. the estimate (b2s_pair_matrix_backward)."""
+
+    @staticmethod
+    def forward(ctx, rows, problem, kind, flags, tau, reduction):
+        lib = _lib.load()
+        stats = problem.stats()
+        examples = problem.groups // problem.inner
+        matrix = torch.empty((examples, problem.k, problem.k), dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            rc = lib.b2s_pair_loss_matrix(_lib.ptr(stats), _lib.ptr(problem.meta), problem.groups, problem.inner,
+                                          problem.k, kind, flags, tau, reduction, _lib.ptr(matrix),
+                                          _lib.stream_of(rows.device))
+        _lib.check(rc, 'b2s_pair_loss_matrix')
+        ctx.problem, ctx.stats, ctx.args = problem, stats, (kind, flags, tau, reduction)
+        return matrix
+
+    @staticmethod
+    def backward(ctx, grad_matrix):
+        lib = _lib.load()
+        p = ctx.problem
+        kind, flags, tau, reduction = ctx.args
+        grad = torch.empty_like(p.estimate)
+        g = grad_matrix.to(torch.float32).contiguous()
+        with torch.cuda.device(grad.device):
+            rc = lib.b2s_pair_matrix_backward(
+                _lib.ptr(p.estimate), _lib.ptr(p.target), _lib.ptr(p.meta), p.groups, p.inner, p.max_length, p.k,
+                p.est_stride, p.tgt_stride, _lib.ptr(ctx.stats), kind, flags, tau, reduction, _lib.ptr(g),
+                _lib.ptr(grad), _lib.stream_of(grad.device))
+        _lib.check(rc, 'b2s_pair_matrix_backward')
+        return grad, None, None, None, None, None
 
 
 def compute_pairwise_losses(
@@ -231,52 +311,27 @@ def compute_pairwise_losses(
         loss_fn=torch.nn.functional.mse_loss,
 ):
     """K x K matrix ``loss_fn(estimate[i], target[j])`` along `axis` (source_separation.py:127-241).
-    For ``mse_loss`` without autograd the matrix comes from one pass of the SSE kernel."""
-    sources = estimate.size()[axis]
-    assert sources < 30, f'Are you sure? sources={sources}'
-    if loss_fn in [torch.nn.functional.cross_entropy]:
-        import einops
 
-        assert axis % estimate.ndimension() == 1, axis
-        estimate_shape = list(estimate.shape)
-        del estimate_shape[1]
-        assert estimate_shape == list(target.shape), (
-            f'{estimate.shape} (N, K, ...) does not match {target.shape} (N, ...)'
-        )
+    For ``mse_loss`` and the regression losses every entry is a function of the pair statistics: one
+    read of the signals yields the whole matrix, with autograd w.r.t. the estimate.  Cross entropy uses
+    its closed form; any other callable is evaluated pair by pair.
+    """
+    sources = _check_pit_arguments(estimate, target, axis, loss_fn)
+    if loss_fn in _CROSS_ENTROPY:
         assert axis == 1, axis
-        return einops.reduce(torch.einsum(
-            'nc...,n...k->n...ck',
-            -torch.nn.LogSoftmax(dim=1)(estimate),
-            torch.nn.functional.one_hot(target, num_classes=sources).to(estimate.dtype)
-        ), 'n ... c k -> c k', reduction='mean')
+        return _cross_entropy_matrix(estimate, target, sources)
 
-    assert estimate.size() == target.size(), (
-        f'{estimate.size()} != {target.size()}'
-    )
-    needs_grad = torch.is_grad_enabled() and (estimate.requires_grad or target.requires_grad)
-    if (_FAST_PIT.get(loss_fn) == ('sse',) and sources <= _lib.MAX_SOURCES and not needs_grad
-            and estimate.is_cuda and estimate.dtype == torch.float32 and estimate.numel() > 0):
-        ax = axis % estimate.ndimension()
-        outer = 1
-        for s in estimate.shape[:ax]:
-            outer *= s
-        e3 = estimate.reshape(outer, sources, -1).contiguous()
-        t3 = target.reshape(outer, sources, -1).contiguous()
-        _, _, sse = _sse.dense_problem(e3, t3).forward()
-        return (sse[0, 0] / (outer * e3.shape[-1])).to(torch.float32)
+    spec = _fast_spec(loss_fn)
+    if (spec is not None and sources <= _lib.MAX_SOURCES and estimate.is_cuda and target.is_cuda
+            and estimate.dtype == torch.float32 and estimate.numel() > 0
+            and not (torch.is_grad_enabled() and target.requires_grad)):
+        rows, problem = _pair_rows(estimate, target, axis, spec)
+        kind, flags, reduction = _pair_args(spec)
+        return _PairMatrixFunction.apply(rows, problem, kind, flags, -1.0, reduction)[0]
 
-    indexer_e = [slice(None), ] * estimate.ndim
-    indexer_t = [slice(None), ] * target.ndim
-    pair_wise_loss_matrix = []
-    for i in range(sources):
-        indexer_e[axis] = i
-        for j in range(0, sources):
-            indexer_t[axis] = j
-            pair_wise_loss_matrix.append(loss_fn(
-                estimate[tuple(indexer_e)],
-                target[tuple(indexer_t)],
-            ))
-    return torch.stack(pair_wise_loss_matrix, 0).reshape(sources, sources)
+    e_slices = estimate.unbind(axis)
+    t_slices = target.unbind(axis)
+    return torch.stack([torch.stack([loss_fn(e, t) for t in t_slices]) for e in e_slices])
 
 
 def pit_loss_from_loss_matrix(
@@ -286,36 +341,49 @@ def pit_loss_from_loss_matrix(
         algorithm='optimal',
         return_permutation=False,
 ):
-    """PIT loss from a (K, K) pair-wise loss matrix (source_separation.py:244-312).  As in the
-    reference the assignment runs on the host (scipy's Hungarian solver)."""
-    import scipy.optimize
+    """PIT loss from a (K, K) pair-wise loss matrix (source_separation.py:244-312): the assignment
+    ``col_ind`` minimising ``sum_i matrix[i, col_ind[i]]``.
 
-    assert len(pair_wise_loss_matrix.shape) == 2, pair_wise_loss_matrix.shape
-    assert pair_wise_loss_matrix.shape[-2] == pair_wise_loss_matrix.shape[-1], pair_wise_loss_matrix.shape
-    sources = pair_wise_loss_matrix.shape[-1]
-    pair_wise_loss_np = pair_wise_loss_matrix.detach().cpu().numpy()
-
-    if algorithm in ('optimal', 'hungarian'):
-        row_ind, col_ind = scipy.optimize.linear_sum_assignment(pair_wise_loss_np)
-    elif algorithm in ('greedy', 'brute_force'):
-        from pb_bss.permutation_alignment import _mapping_from_score_matrix
-        if algorithm == 'brute_force':
-            algorithm = 'optimal'
-        col_ind = _mapping_from_score_matrix(-pair_wise_loss_np, algorithm=algorithm)
-        row_ind = range(sources)
-    else:
+    CUDA matrices with K <= 8 are solved on the device (b2s_assign: exhaustive, exact; the reference moves
+    the matrix to the host for scipy's Hungarian solver, :285-288) and the selected entries are gathered
+    with a device index, so the loss itself never leaves the GPU; larger or CPU matrices take the host
+    solver like the reference.  'greedy' takes the smallest remaining entry first.
+    """
+    shape = tuple(pair_wise_loss_matrix.shape)
+    assert len(shape) == 2, shape
+    assert shape[-2] == shape[-1], shape
+    sources = shape[-1]
+    if algorithm not in ('optimal', 'hungarian', 'greedy', 'brute_force'):
         raise ValueError(algorithm)
-
-    if reduction is None:
-        min_loss = pair_wise_loss_matrix[row_ind, col_ind]
-    elif reduction == 'mean':
-        min_loss = pair_wise_loss_matrix[row_ind, col_ind].mean()
-    elif reduction == 'sum':
-        min_loss = pair_wise_loss_matrix[row_ind, col_ind].sum()
-    else:
+    if reduction not in (None, 'mean', 'sum'):
         raise ValueError(reduction)
+    greedy = algorithm == 'greedy'
 
-    if return_permutation:
-        return min_loss, col_ind
+    if pair_wise_loss_matrix.is_cuda and sources <= _lib.MAX_SOURCES:
+        cols, _ = _first_minimum(pair_wise_loss_matrix[None], orientation=1, greedy=greedy)
+        col_index = cols[0].long()
+        col_ind = None
     else:
-        return min_loss
+        import numpy as np
+        import scipy.optimize
+        host = pair_wise_loss_matrix.detach().cpu().numpy()
+        if greedy:
+            work = host.astype(np.float64).copy()
+            col_ind = np.zeros(sources, dtype=np.int64)
+            for _ in range(sources):
+                i, j = np.unravel_index(np.argmin(work), work.shape)
+                col_ind[i] = j
+                work[i, :] = np.inf
+                work[:, j] = np.inf
+        else:
+            col_ind = scipy.optimize.linear_sum_assignment(host)[1]
+        col_index = torch.as_tensor(col_ind, dtype=torch.long, device=pair_wise_loss_matrix.device)
+
+    rows = torch.arange(sources, device=pair_wise_loss_matrix.device)
+    picked = pair_wise_loss_matrix[rows, col_index]
+    min_loss = picked if reduction is None else (picked.mean() if reduction == 'mean' else picked.sum())
+    if return_permutation:
+        if col_ind is None:
+            col_ind = col_index.cpu().numpy()
+        return min_loss, col_ind
+    return min_loss

@@ -16,21 +16,44 @@ _ORIGINALS = {}
 
 _LOSS_NAMES = ['mse_loss', 'log_mse_loss', 'sdr_loss', 'si_sdr_loss', 'log1p_mse_loss',
                'source_aggregated_sdr_loss', 'deep_clustering_loss', 'pit_loss',
-               'compute_pairwise_losses']
+               'compute_pairwise_losses', 'pit_loss_from_loss_matrix']
 
 
 def _on_device(*tensors):
     return all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 for t in tensors)
 
 
-def _route(ours, theirs):
+def _route(ours, theirs, handles=None):
+    """`ours` for float32 CUDA tensors (and, if given, when ``handles(*args, **kwargs)`` says the kernels cover
+    the case); everything else is the reference's own function object, untouched."""
     @functools.wraps(theirs)
     def routed(estimate, target, *args, **kwargs):
-        if _on_device(estimate, target):
+        if _on_device(estimate, target) and (handles is None or handles(*args, **kwargs)):
             return ours(estimate, target, *args, **kwargs)
         return theirs(estimate, target, *args, **kwargs)
     routed.__wrapped_reference__ = theirs
     return routed
+
+
+def _route_matrix(ours, theirs):
+    """pit_loss_from_loss_matrix: one positional argument (the K x K matrix)."""
+    @functools.wraps(theirs)
+    def routed(pair_wise_loss_matrix, **kwargs):
+        from . import _lib
+        if (_on_device(pair_wise_loss_matrix) and pair_wise_loss_matrix.dim() == 2
+                and pair_wise_loss_matrix.shape[-1] <= _lib.MAX_SOURCES
+                and kwargs.get('algorithm', 'optimal') in ('optimal', 'hungarian', 'brute_force')):
+            return ours(pair_wise_loss_matrix, **kwargs)
+        return theirs(pair_wise_loss_matrix, **kwargs)
+    routed.__wrapped_reference__ = theirs
+    return routed
+
+
+def _kernel_loss_fn(axis=None, loss_fn=torch.nn.functional.mse_loss, *args, **kwargs):
+    """pit_loss / compute_pairwise_losses: the kernels cover the loss functions registered in _FAST_PIT; an
+    opaque callable or cross entropy is the reference's business (its permutation loop, its einsum)."""
+    from .ops.losses import source_separation as our_ss
+    return our_ss._fast_spec(loss_fn) is not None
 
 
 def patch_padertorch(pt=None):
@@ -57,7 +80,11 @@ def patch_padertorch(pt=None):
         ours_fn = getattr(ours, name, None) or getattr(our_ss, name)
         home = ref_reg if hasattr(ref_reg, name) else ref_ss
         theirs_fn = getattr(home, name)
-        routed = _route(ours_fn, theirs_fn)
+        if name == 'pit_loss_from_loss_matrix':
+            routed = _route_matrix(ours_fn, theirs_fn)
+        else:
+            routed = _route(ours_fn, theirs_fn,
+                            _kernel_loss_fn if name in ('pit_loss', 'compute_pairwise_losses') else None)
         # the reference's own function objects (and our routed wrappers) take the kernel path when
         # they are passed to pit_loss as loss_fn
         if ours_fn in our_ss._FAST_PIT:

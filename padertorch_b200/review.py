@@ -93,6 +93,8 @@ def dc_losses_per_example(embeddings, target_masks, lengths=None):
     k = tgt.shape[2]
     assert tgt.shape == (batch, frames, k, bins), (emb.shape, tgt.shape)
     lengths = [frames] * batch if lengths is None else [int(v) for v in lengths]
+    assert len(lengths) == batch and max(lengths, default=0) <= frames and min(lengths, default=0) >= 0, \
+        (lengths, emb.shape)
     rows = [[lengths[b], b * frames * e_dim * bins, b * frames * k * bins, b * frames * e_dim * bins]
             for b in range(batch)]
     meta = meta_tensor(rows, emb.device, cache_key=('dc-padded', frames, e_dim, k, bins, tuple(lengths)))

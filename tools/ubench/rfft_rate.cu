@@ -3,6 +3,7 @@
 // in the loop, 2 CTAs x 4 warps per SM.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o rfft_rate rfft_rate.cu && ./rfft_rate
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <cmath>
 #include "../../padertorch_b200/csrc/rfft_packed.cuh"
@@ -11,7 +12,7 @@ using namespace b2s;
 constexpr int kWarps = 4;
 constexpr int kWarpFloats = 2 * rf::kSize + 4 * rf::kTile1;
 
-__global__ void __launch_bounds__(32 * kWarps, 2)
+__global__ void __launch_bounds__(32 * kWarps, 3)
 rfft_rate_kernel(const float* __restrict__ x, const float4* __restrict__ lane_table, float* __restrict__ out, int iters) {
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,8 +38,10 @@ rfft_rate_kernel(const float* __restrict__ x, const float4* __restrict__ lane_ta
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-int main() {
-  const int sms = 148, grid = sms * 2, iters = 200;
+int main(int argc, char** argv) {
+  // argv[1] = resident CTAs per SM wanted (2 or 3: dynamic shared memory is padded so that no more fit)
+  const int want = argc > 1 ? atoi(argv[1]) : 3;
+  const int sms = 148, grid = sms * want, iters = 200;
   std::vector<float> hx(2048), hw(1024);
   std::vector<float2> htab(1024);
   for (int i = 0; i < 2048; ++i) hx[i] = (float)rand() / RAND_MAX - 0.5f;
@@ -56,7 +59,8 @@ int main() {
   cudaMalloc(&x, 2048 * 4); cudaMalloc(&tab, table.size() * 16); cudaMalloc(&out, grid * 32 * kWarps * 4);
   cudaMemcpy(x, hx.data(), 2048 * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(tab, table.data(), table.size() * 16, cudaMemcpyHostToDevice);
-  const size_t smem = sizeof(float) * kWarps * kWarpFloats;
+  size_t smem = sizeof(float) * kWarps * kWarpFloats;
+  if (want == 2) smem = 100 * 1024;   // two CTAs of 100 KB fit, three do not
   cudaFuncSetAttribute(rfft_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rfft_rate_kernel, 32 * kWarps, smem);
