@@ -251,6 +251,18 @@ B2S_API int b2s_stft_pit_forward(const b2s_stft_plan* plan, const float* mixture
                          int64_t frames, int64_t pad_left, float* loss, int32_t* perm, double* sse,
                          void* workspace, b2s_stream stream);
 
+/* Backward of b2s_stft_pit_forward: grad_mask [B, frames, K, F] = grad_loss[b] * d loss[b] / d mask for the
+ * permutation the forward pass chose (perm [B, K] as written by it) -- what autograd derives for
+ * pit_loss(mask * Y_abs[:, None, :], X_abs, axis=-2) (pit/model.py:117-128, source_separation.py:112-119):
+ *     2 / (frames_b K F) * (mask |Y| - |X_j(i)|) * |Y|,   perm[j(i)] == i,
+ * with |X_k| recomputed from the waveforms in registers (no 4MFK read of materialised targets).  Frames beyond
+ * an example's length (meta) are not written: pass a zero-filled grad_mask for ragged batches.               */
+B2S_API int b2s_stft_pit_backward(const b2s_stft_plan* plan, const float* mixture,
+                          const float* observation_abs, const float* sources, const float* mask,
+                          const int64_t* meta, int64_t batch, int64_t samples, int sources_k,
+                          int64_t frames, int64_t pad_left, const int32_t* perm, const float* grad_loss,
+                          float* grad_mask, b2s_stream stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Batched target / feature preparation of the PIT example on the device:
  * pre_batch_transform, padertorch/contrib/examples/source_separation/pit/data.py:49-77, which runs per

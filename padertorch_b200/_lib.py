@@ -67,6 +67,8 @@ SIGNATURES = {
     'b2s_stft_pit_targets': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64, c_void, c_void,
                                      c_void, c_void]),
     'b2s_pit_targets': (c_int, [c_void, c_void, c_i64, c_int, c_i64, c_i64, c_void, c_void, c_void, c_void]),
+    'b2s_stft_pit_backward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64,
+                                      c_i64, c_void, c_void, c_void, c_void]),
     'b2s_stft_pit_workspace_bytes': (c_i64, [c_i64, c_i64, c_int]),
     'b2s_stft_pit_forward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64,
                                      c_int, c_i64, c_i64, c_void, c_void, c_void, c_void, c_void]),

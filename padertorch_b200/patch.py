@@ -56,9 +56,79 @@ def _kernel_loss_fn(axis=None, loss_fn=torch.nn.functional.mse_loss, *args, **kw
     return our_ss._fast_spec(loss_fn) is not None
 
 
-def patch_padertorch(pt=None):
-    """Replace the hot-path ops of the importable ``padertorch`` package by this package's.
-    Returns the list of patched attribute paths.  Idempotent."""
+def _all_on_device(items):
+    return len(items) > 0 and all(_on_device(t) for t in items)
+
+
+def _patch_models(pt, replace):
+    """Model-level drop-in: the per-example Python loops of the three
+    hot-path models become one or two launches for the whole minibatch.  Every method keeps its name,
+    arguments and return structure; CPU batches run the original method."""
+    import importlib
+    from . import review as ours
+
+    def module(name):
+        try:
+            return importlib.import_module(name)
+        except Exception:      # an example package whose own dependencies are missing stays untouched
+            return None
+
+    pit = module('padertorch.contrib.examples.source_separation.pit.model')
+    if pit is not None:
+        original_review = pit.PermutationInvariantTrainingModel.review
+
+        def pit_review(self, batch, model_out):
+            """pit/model.py:112-151 with the loop :117-135 replaced by review.pit_review_losses (the MSE and
+            the ideal-phase-sensitive loss of the whole list in one pass); `images` as in :142-147."""
+            if not (_all_on_device(model_out) and _all_on_device(batch['Y_abs'])):
+                return original_review(self, batch, model_out)
+            losses = ours.pit_review_losses(list(model_out), list(batch['Y_abs']), list(batch['X_abs']),
+                                            list(batch['cos_phase_difference']))
+            b = 0   # only the first example of a batch is rendered (:142)
+            images = {'observation': pit.stft_to_image(batch['Y_abs'][b])}
+            for i in range(model_out[b].shape[1]):
+                images[f'mask_{i}'] = pit.mask_to_image(model_out[b][:, i, :])
+                images[f'estimation_{i}'] = pit.stft_to_image(batch['X_abs'][b][:, 0, :])
+            return dict(losses=losses, images=images)
+
+        pit_review.__wrapped_reference__ = original_review
+        replace(pit.PermutationInvariantTrainingModel, 'review', pit_review)
+
+    dc = module('padertorch.contrib.tcl.dc')
+    if dc is not None:
+        original_dc = dc.DeepClusteringModel.review
+
+        def dc_review(self, batch, model_out):
+            """tcl/dc.py:76-84: the loop over (embedding, target_mask) pairs -> review.dc_review_loss on the
+            model's native 't e f' layout (no rearrange copies)."""
+            if not (_all_on_device(model_out) and _all_on_device(batch['target_mask'])):
+                return original_dc(self, batch, model_out)
+            return {'losses': {'dc_loss': ours.dc_review_loss(list(model_out), list(batch['target_mask']))}}
+
+        dc_review.__wrapped_reference__ = original_dc
+        replace(dc.DeepClusteringModel, 'review', dc_review)
+
+    tasnet = module('padertorch.contrib.examples.source_separation.tasnet.model')
+    if tasnet is not None:
+        original_loss = tasnet.TasNet.loss
+
+        def tasnet_loss(self, inputs, outputs):
+            """tasnet/model.py:154-176: 3 loss functions x B examples of pit_loss -> one statistics pass and
+            one loss-set launch (review.tasnet_losses)."""
+            s, x = inputs['s'], outputs['out']
+            if not (_on_device(x) and _on_device(s) and x.shape == s.shape):
+                return original_loss(self, inputs, outputs)
+            return ours.tasnet_losses(x, s, [int(n) for n in inputs['num_samples']])
+
+        tasnet_loss.__wrapped_reference__ = original_loss
+        replace(tasnet.TasNet, 'loss', tasnet_loss)
+
+
+def patch_padertorch(pt=None, models=True):
+    """Replace the hot-path ops of the importable ``padertorch`` package by this package's and, with
+    ``models=True``, the per-example loss loops of the three hot-path models (PIT ``review``, deep-clustering
+    ``review``, ``TasNet.loss``) by their batched forms.  Returns the list of patched attribute paths.
+    Idempotent."""
     if pt is None:
         import padertorch as pt
     from . import ops as ours
@@ -70,7 +140,7 @@ def patch_padertorch(pt=None):
     patched = {}
 
     def replace(module, name, value):
-        key = f'{module.__name__}.{name}'
+        key = f'{getattr(module, "__module__", None) and module.__module__ + "." + module.__name__ or module.__name__}.{name}'
         if hasattr(module, name):
             _ORIGINALS[key] = (module, name, getattr(module, name))
             setattr(module, name, value)
@@ -128,6 +198,21 @@ def patch_padertorch(pt=None):
     for module in (ref_stft_module, pt.ops):
         if getattr(module, 'STFT', None) is RefSTFT:
             replace(module, 'STFT', STFT)
+    if models:
+        _patch_models(pt, replace)
+    # modules that bound the names at import time (``from padertorch.ops import STFT`` in tasnet/tas_coders.py:5,
+    # ``from padertorch.ops.losses.regression import si_sdr_loss`` ...): rebind them as well
+    import sys
+    originals = {id(old): new for (module, name, old), new in
+                 ((entry, getattr(entry[0], entry[1])) for entry in list(_ORIGINALS.values()))
+                 if isinstance(module, type(sys)) }
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is None or not mod_name.startswith('padertorch.') or mod_name.startswith('padertorch_b200'):
+            continue
+        for attr, value in list(vars(mod).items()):
+            new = originals.get(id(value))
+            if new is not None and value is not new and f'{mod.__name__}.{attr}' not in _ORIGINALS:
+                replace(mod, attr, new)
     return sorted(patched)
 
 

@@ -162,43 +162,79 @@ def tasnet_losses(estimates, targets, num_samples, names=('si-sdr', 'log-mse', '
     return dict(zip(names, values))
 
 
+class _FusedStepFunction(torch.autograd.Function):
+    """masks -> (loss [B], permutation [B, K]) through b2s_stft_pit_forward; the gradient w.r.t. the masks
+    through b2s_stft_pit_backward (the target spectra are recomputed in registers in both directions)."""
+
+    @staticmethod
+    def forward(ctx, masks, mixture, observation_abs, sources, meta, stft, frames_call, pad_left, ragged):
+        lib = _lib.load()
+        batch, k, samples = sources.shape
+        device = sources.device
+        plan = stft._plan(device)
+        loss = torch.empty(batch, dtype=torch.float32, device=device)
+        perm = torch.empty((batch, k), dtype=torch.int32, device=device)
+        sse = torch.empty((batch, k, k), dtype=torch.float64, device=device)
+        ws = workspace(device, lib.b2s_stft_pit_workspace_bytes(batch, frames_call, k), 'fused')
+        with torch.cuda.device(device):
+            rc = lib.b2s_stft_pit_forward(
+                plan.handle, _lib.ptr(mixture), _lib.ptr(observation_abs), _lib.ptr(sources),
+                _lib.ptr(masks), _lib.ptr(meta), batch, samples, k, frames_call, pad_left, _lib.ptr(loss),
+                _lib.ptr(perm), _lib.ptr(sse), _lib.ptr(ws), _lib.stream_of(device))
+        _lib.check(rc, 'b2s_stft_pit_forward')
+        ctx.save_for_backward(masks, perm)
+        ctx.data = (mixture, observation_abs, sources, meta, stft, frames_call, pad_left, ragged)
+        ctx.mark_non_differentiable(perm)
+        return loss, perm
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_perm):
+        lib = _lib.load()
+        masks, perm = ctx.saved_tensors
+        mixture, observation_abs, sources, meta, stft, frames_call, pad_left, ragged = ctx.data
+        batch, k, samples = sources.shape
+        device = sources.device
+        plan = stft._plan(device)
+        # frames beyond an example's length are not written by the kernel
+        grad = (torch.zeros_like if ragged else torch.empty_like)(masks)
+        g = grad_loss.to(torch.float32).contiguous()
+        with torch.cuda.device(device):
+            rc = lib.b2s_stft_pit_backward(
+                plan.handle, _lib.ptr(mixture), _lib.ptr(observation_abs), _lib.ptr(sources), _lib.ptr(masks),
+                _lib.ptr(meta), batch, samples, k, frames_call, pad_left, _lib.ptr(perm), _lib.ptr(g),
+                _lib.ptr(grad), _lib.stream_of(device))
+        _lib.check(rc, 'b2s_stft_pit_backward')
+        return grad, None, None, None, None, None, None, None, None
+
+
 def stft_mask_pit_step(mixture, sources, masks, stft=None, observation_abs=None, num_samples=None):
     """The fused north-star step: per example ``pit_loss(mask * |STFT(y)|[:, None, :],
-    |STFT(s)|, axis=-2)`` with the target spectra recomputed in registers (b2s_stft_pit_forward).
+    |STFT(s)|, axis=-2)`` with the target spectra recomputed in registers (b2s_stft_pit_forward /
+    b2s_stft_pit_backward).
 
     mixture [B, T] (may be None when `observation_abs` [B, M, F] is given), sources [B, K, T],
-    masks [B, M, K, F].  Returns (loss [B], permutation [B, K] int32).  Forward only.
+    masks [B, M, K, F].  Returns (loss [B], permutation [B, K] int32); differentiable w.r.t. `masks`
+    (the waveforms and `observation_abs` are data on this path, as in pit/model.py:117-128).
     """
     stft = STFT(1024, 256) if stft is None else stft
-    lib = _lib.load()
-    sources = _lib.require_cuda_float(sources, 'sources').contiguous()
+    sources = _lib.require_cuda_float(sources, 'sources').detach().contiguous()
     masks = _lib.require_cuda_float(masks, 'masks').contiguous()
     batch, k, samples = sources.shape
     frames_call, pad_left = stft._frames_of_call(samples)
     assert masks.shape == (batch, frames_call, k, stft.size // 2 + 1), (masks.shape, frames_call)
     if mixture is not None:
-        mixture = _lib.require_cuda_float(mixture, 'mixture').contiguous()
+        mixture = _lib.require_cuda_float(mixture, 'mixture').detach().contiguous()
         assert mixture.shape == (batch, samples), (mixture.shape, sources.shape)
     if observation_abs is not None:
-        observation_abs = _lib.require_cuda_float(observation_abs, 'observation_abs').contiguous()
+        observation_abs = _lib.require_cuda_float(observation_abs, 'observation_abs').detach().contiguous()
         assert observation_abs.shape == (batch, frames_call, stft.size // 2 + 1)
     meta = None
     if num_samples is not None:
+        assert len(num_samples) == batch and max(int(n) for n in num_samples) <= samples, (num_samples, samples)
         rows = [[int(n), stft._frames_of_call(int(n))[0]] for n in num_samples]
         meta = meta_tensor(rows, sources.device, cache_key=('fused', tuple(map(tuple, rows))))
-    device = sources.device
-    plan = stft._plan(device)
-    loss = torch.empty(batch, dtype=torch.float32, device=device)
-    perm = torch.empty((batch, k), dtype=torch.int32, device=device)
-    sse = torch.empty((batch, k, k), dtype=torch.float64, device=device)
-    ws = workspace(device, lib.b2s_stft_pit_workspace_bytes(batch, frames_call, k), 'fused')
-    with torch.cuda.device(device):
-        rc = lib.b2s_stft_pit_forward(
-            plan.handle, _lib.ptr(mixture), _lib.ptr(observation_abs), _lib.ptr(sources),
-            _lib.ptr(masks), _lib.ptr(meta), batch, samples, k, frames_call, pad_left, _lib.ptr(loss),
-            _lib.ptr(perm), _lib.ptr(sse), _lib.ptr(ws), _lib.stream_of(device))
-    _lib.check(rc, 'b2s_stft_pit_forward')
-    return loss, perm
+    return _FusedStepFunction.apply(masks, mixture, observation_abs, sources, meta, stft, frames_call, pad_left,
+                                    num_samples is not None)
 
 
 def prepare_pit_targets(mixture, sources, stft=None):
