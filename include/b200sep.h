@@ -72,6 +72,7 @@ B2S_API int64_t b2s_stft_scratch_bytes(const b2s_stft_plan* plan, int64_t rows, 
 #define B2S_SPEC_CONCAT 1      /* [rows, frames, 2F]    real bins then imaginary bins ('concat')  */
 #define B2S_SPEC_ABS 2         /* [rows, frames, F]     |Y|          (fused magnitude epilogue)  */
 #define B2S_SPEC_LOG1P_ABS 3   /* [rows, frames, F]     log1p(|Y|)   (fused PIT-model feature)    */
+#define B2S_SPEC_FEATURE 4     /* internal: the parameterised feature epilogue of b2s_stft_features */
 
 /* STFT.__call__ (padertorch/ops/_stft.py:103-174).  signal [rows, samples] (row stride given in
  * floats); frame m covers padded samples m*shift .. m*shift+window_length-1 where padded index p
@@ -94,6 +95,26 @@ B2S_API int b2s_istft_forward(const b2s_stft_plan* plan, const float* spec, int6
 B2S_API int b2s_istft_backward(const b2s_stft_plan* plan, const float* grad_signal, int64_t rows,
                        int64_t samples_out, int64_t crop_left, int64_t frames, int layout,
                        float* grad_spec, b2s_stream stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature epilogues fused behind the transform, replacing the ATen chains of
+ * padertorch/contrib/mk/modules/features/timefreq.py:
+ *   to_spectrogram (:171-183)   x = |Y|^power * scale      (scale = 1/size for scale_spec, else 1)
+ *   Logarithm (:37-77)          log_b(max(eps, x)), b in {none, e, 10, 2}
+ *   MelTransform.forward (:398-470, :444)   x @ mel_basis before the logarithm.
+ * Without a filterbank features are [rows, frames, F]; with one [rows, frames, filters] (the spectrogram never
+ * reaches HBM: 4T + 4 M filters algorithmic bytes per utterance).  Fast plans only (size 1024).
+ * b2s_mel_create: basis = HOST float [bins][filters] row-major (MelTransform.mel_basis, :338).             */
+typedef struct b2s_mel b2s_mel;
+#define B2S_LOG_NONE 0
+#define B2S_LOG_E 1
+#define B2S_LOG_10 2
+#define B2S_LOG_2 3
+B2S_API int b2s_mel_create(b2s_mel** mel, int device, int bins, int filters, const float* basis);
+B2S_API int b2s_mel_destroy(b2s_mel* mel);
+B2S_API int b2s_stft_features(const b2s_stft_plan* plan, const float* signal, int64_t rows, int64_t samples,
+                      int64_t row_stride, int64_t pad_left, int64_t frames, float power, float scale,
+                      int log_kind, float eps, const b2s_mel* mel, float* features, b2s_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Permutation-invariant MSE over spectrogram-shaped data.

@@ -12,6 +12,7 @@ The compute lives in ``libb200sep.so`` (C ABI: include/b200sep.h); there is no C
 from . import _lib
 from . import ops
 from . import review
+from . import features
 from .ops import STFT
 from .patch import patch_padertorch, unpatch_padertorch
 

@@ -37,6 +37,10 @@ SIGNATURES = {
                                   c_void]),
     'b2s_istft_backward': (c_int, [c_void, c_void, c_i64, c_i64, c_i64, c_i64, c_int, c_void,
                                    c_void]),
+    'b2s_mel_create': (c_int, [ctypes.POINTER(c_void), c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float)]),
+    'b2s_mel_destroy': (c_int, [c_void]),
+    'b2s_stft_features': (c_int, [c_void, c_void, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
+                                  c_int, ctypes.c_float, c_void, c_void, c_void]),
     'b2s_pit_workspace_bytes': (c_i64, [c_i64, c_i64, c_i64, c_int, c_int]),
     'b2s_pit_sse_forward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int,
                                     c_i64, c_int, c_void, c_void, c_void, c_void, c_void]),

@@ -64,6 +64,35 @@ __device__ __forceinline__ void store_bin_t(float* __restrict__ out, int k, floa
   }
 }
 
+// Feature epilogue (layout B2S_SPEC_FEATURE): to_spectrogram + Logarithm + MelTransform of
+// padertorch/contrib/mk/modules/features/timefreq.py:37-77, 171-183, 398-470 behind the transform.
+struct FeatureArgs {
+  float half_power;   // |Y|^power = (re^2 + im^2)^(power / 2)
+  float scale;        // scale_spec: 1 / size, else 1
+  int log_kind;       // B2S_LOG_*
+  float eps;          // Logarithm: log(max(eps, x))
+  int filters;        // 0: no filterbank
+  const int* lo;      // [filters] first bin of filter m
+  const int* len;     // [filters] number of bins of its support
+  const int* woff;    // [filters] offset of its weights in `weights`
+  const float* weights;
+};
+__device__ __forceinline__ float feature_power(float2 y, const FeatureArgs& a) {
+  const float v = fmaf(y.x, y.x, y.y * y.y);
+  float r;
+  if (a.half_power == 0.5f) r = fft::sqrt_approx(v);
+  else if (a.half_power == 1.f) r = v;
+  else r = v > 0.f ? __powf(v, a.half_power) : 0.f;
+  return r * a.scale;
+}
+__device__ __forceinline__ float feature_log(float x, const FeatureArgs& a) {
+  if (a.log_kind == B2S_LOG_NONE) return x;
+  x = fmaxf(x, a.eps);
+  // lg2.approx: <= 2^-22 relative to |log2 x| plus the rounding of the factor
+  const float l2 = __log2f(x);
+  return a.log_kind == B2S_LOG_2 ? l2 : l2 * (a.log_kind == B2S_LOG_E ? 0.69314718055994530942f : 0.30102999566398119521f);
+}
+
 constexpr int kFwdWarps = 4;
 
 // One warp per frame, persistent over frames.  `win` is the (zero-extended) window the samples are
@@ -141,7 +170,7 @@ template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int NS = kPipeFrames,
 __global__ void __launch_bounds__(32 * kPipeWarps, CTAS)
 stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                      int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
-                     float* __restrict__ out, int ablate) {
+                     float* __restrict__ out, int ablate, FeatureArgs feat) {
   extern __shared__ __align__(16) float smem[];   // per warp: [STAGES][span] samples, NS exchange tiles, output rows
   __shared__ __align__(8) uint64_t bars[kPipeWarps][STAGES];
   constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
@@ -252,13 +281,30 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     // floats at either end from lanes): per-lane STG of rows that are only 4-byte aligned costs several LSU
     // cycles per touched line and blocks the shared-memory traffic of the whole SM behind it.
     const int nrows = min(NS, (int)frames - m0);
-    float* g = out + ((int64_t)row * frames + m0) * kOutPerFrame;
-    const int phase = (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
+    constexpr bool kFeature = LAYOUT == B2S_SPEC_FEATURE;
+    const bool mel = kFeature && feat.filters > 0;
+    float* g = out + ((int64_t)row * frames + m0) * (mel ? feat.filters : kOutPerFrame);
+    const int phase = mel ? 0 : (int)((reinterpret_cast<uintptr_t>(g) & 15) >> 2);
     if (lane == 0) tma::bulk_wait_read<0>();   // the previous unit's store has read the staging rows
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       float* o = obuf + phase + s * kOutPerFrame;
+      if (kFeature) {
+        // |Y|^power [/ size], and without a filterbank the logarithm, per bin
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float va = feature_power(ya[s][p], feat), vb = feature_power(yb[s][p], feat);
+          o[(p < 4 ? offa0 : offa4) + 64 * p] = mel ? va : feature_log(va, feat);
+          o[(p < 4 ? offb0 : offb4) - 64 * p] = mel ? vb : feature_log(vb, feat);
+        }
+        if (lane == 0) {
+          const float vd = feature_power(make_float2(ydc[s], 0.f), feat), vn = feature_power(make_float2(ynyq[s], 0.f), feat);
+          o[0] = mel ? vd : feature_log(vd, feat);
+          o[rf::kHalf] = mel ? vn : feature_log(vn, feat);
+        }
+        continue;
+      }
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         store_bin_t<LAYOUT>(o + (p < 4 ? offa0 : offa4) + kS * 64 * p, 0, ya[s][p]);
@@ -268,6 +314,23 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
         store_bin_t<LAYOUT>(o, 0, make_float2(ydc[s], 0.f));
         store_bin_t<LAYOUT>(o, rf::kHalf, make_float2(ynyq[s], 0.f));
       }
+    }
+    if (mel) {
+      // filterbank: filter m = sum over its (contiguous) support of weight * |Y|^power, then the logarithm; lanes
+      // own filters m = lane, lane + 32, ...; rows of `filters` floats leave with plain stores (80 floats per frame
+      // against 513: the output stream shrinks 6.4 x)
+      __syncwarp();
+      for (int s = 0; s < nrows; ++s) {
+        const float* o = obuf + s * kOutPerFrame;
+        for (int m = lane; m < feat.filters; m += 32) {
+          const int lo = __ldg(feat.lo + m), len = __ldg(feat.len + m);
+          const float* w = feat.weights + __ldg(feat.woff + m);
+          float acc = 0.f;
+          for (int j = 0; j < len; ++j) acc = fmaf(__ldg(w + j), o[lo + j], acc);
+          g[(int64_t)s * feat.filters + m] = feature_log(acc, feat);
+        }
+      }
+      continue;   // the next unit's bulk_wait_read / __syncwarp orders these reads before its writes
     }
     tma::fence_proxy_async();   // the rows were written through the generic proxy
     __syncwarp();
@@ -512,7 +575,7 @@ bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0;
 // launch of one instantiation of the warp-pipeline kernel
 struct PipeArgs {
   const float* x; int64_t rows, samples, row_stride, pad_left, frames; int shift; const float4* table; float* out;
-  int ablate, layout, device; cudaStream_t stream;
+  int ablate, layout, device; cudaStream_t stream; FeatureArgs feat;
 };
 template <int L, bool D, bool S, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm, bool COMPACT = false,
           int STAGES = kPipeStages>
@@ -540,7 +603,7 @@ int launch_pipe(const PipeArgs& a) {
     configured[a.device & 63] = true;
   }
   B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, a.x, a.rows, a.samples, a.row_stride, a.pad_left, a.frames, a.shift,
-                              a.table, a.out, a.ablate));
+                              a.table, a.out, a.ablate, a.feat));
   B2S_LAUNCH_CHECK("stft1024_warp_kernel");
   return B2S_OK;
 }
@@ -548,7 +611,7 @@ int launch_pipe(const PipeArgs& a) {
 // forward-type launch shared by b2s_stft_forward and b2s_istft_backward
 int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int64_t samples,
                    int64_t row_stride, int64_t pad_left, int64_t frames, int layout, const float* win,
-                   float interior_scale, float* out, cudaStream_t stream) {
+                   float interior_scale, float* out, cudaStream_t stream, const FeatureArgs* feat = nullptr) {
   const int64_t total = rows * frames;
   if (total == 0) return B2S_OK;
   if (plan->fast && plan->wlen == fft::kSize && plan->shift % 4 == 0 && plan->shift <= fft::kSize) {
@@ -561,7 +624,11 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                 "signal too large for the STFT warp kernel (%lld frames of %lld samples)", (long long)(rows * frames),
                 (long long)samples);
     const PipeArgs pa{x, rows, samples, row_stride, pad_left, frames, plan->shift, table, out, ablate, layout,
-                      plan->device, stream};
+                      plan->device, stream, feat ? *feat : FeatureArgs{}};
+    if (layout == B2S_SPEC_FEATURE) {
+      if (plan->shift == 256) return launch_pipe<B2S_SPEC_FEATURE, false, true>(pa);
+      return launch_pipe<B2S_SPEC_FEATURE, false, false>(pa);
+    }
     // tuning alternatives of the headline configuration (|Y| epilogue, shift 256): tools/hot_bench.py
     const char* ve = getenv("B2S_FWD_VARIANT");   // read per launch: one process can sweep the shapes
     const int variant = ve ? atoi(ve) : 0;
@@ -821,6 +888,73 @@ int b2s_stft_backward(const b2s_stft_plan* plan, const float* grad_spec, int64_t
   B2S_REQUIRE(rows * samples == 0 || (grad_spec || frames == 0) && grad_signal, "NULL device pointer");
   return launch_inverse(plan, grad_spec, rows, frames, layout, pad_left, samples, plan->awin, 1.f,
                         grad_signal, scratch, (cudaStream_t)stream);
+}
+
+// ---- feature epilogues ------------------------------------------------------------
+struct b2s_mel {
+  int device, bins, filters;
+  int *lo, *len, *woff;
+  float* weights;
+};
+
+int b2s_mel_create(b2s_mel** out, int device, int bins, int filters, const float* basis) {
+  B2S_REQUIRE(out && basis, "NULL pointer");
+  B2S_REQUIRE(bins >= 1 && filters >= 1 && filters <= 4096, "bad filterbank extents (%d bins, %d filters)", bins, filters);
+  B2S_ON_DEVICE(device);
+  // support of every filter (column of basis [bins][filters]): first .. last non-zero bin
+  std::vector<int> lo(filters, 0), len(filters, 0), woff(filters, 0);
+  std::vector<float> w;
+  for (int m = 0; m < filters; ++m) {
+    int first = -1, last = -1;
+    for (int f = 0; f < bins; ++f)
+      if (basis[(size_t)f * filters + m] != 0.f) { if (first < 0) first = f; last = f; }
+    woff[m] = (int)w.size();
+    if (first >= 0) {
+      lo[m] = first; len[m] = last - first + 1;
+      for (int f = first; f <= last; ++f) w.push_back(basis[(size_t)f * filters + m]);
+    }
+  }
+  if (w.empty()) w.push_back(0.f);
+  b2s_mel* mel = new b2s_mel();
+  mel->device = device; mel->bins = bins; mel->filters = filters;
+  B2S_CUDA(cudaMalloc(&mel->lo, sizeof(int) * filters));
+  B2S_CUDA(cudaMalloc(&mel->len, sizeof(int) * filters));
+  B2S_CUDA(cudaMalloc(&mel->woff, sizeof(int) * filters));
+  B2S_CUDA(cudaMalloc(&mel->weights, sizeof(float) * w.size()));
+  B2S_CUDA(cudaMemcpy(mel->lo, lo.data(), sizeof(int) * filters, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemcpy(mel->len, len.data(), sizeof(int) * filters, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemcpy(mel->woff, woff.data(), sizeof(int) * filters, cudaMemcpyHostToDevice));
+  B2S_CUDA(cudaMemcpy(mel->weights, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  *out = mel;
+  return B2S_OK;
+}
+
+int b2s_mel_destroy(b2s_mel* mel) {
+  if (!mel) return B2S_OK;
+  DeviceGuard guard(mel->device);
+  cudaFree(mel->lo); cudaFree(mel->len); cudaFree(mel->woff); cudaFree(mel->weights);
+  delete mel;
+  return B2S_OK;
+}
+
+int b2s_stft_features(const b2s_stft_plan* plan, const float* signal, int64_t rows, int64_t samples,
+                      int64_t row_stride, int64_t pad_left, int64_t frames, float power, float scale,
+                      int log_kind, float eps, const b2s_mel* mel, float* features, b2s_stream stream) {
+  if (int rc = check_plan(plan)) return rc;
+  B2S_REQUIRE(plan->fast && plan->wlen == fft::kSize && plan->shift % 4 == 0 && plan->shift <= fft::kSize,
+              "the fused feature epilogue exists for size 1024 / window_length 1024 / shift %% 4 == 0 plans only "
+              "(got size %d, window_length %d, shift %d)", plan->size, plan->wlen, plan->shift);
+  B2S_REQUIRE(power > 0.f, "power must be positive (got %g)", (double)power);
+  B2S_REQUIRE(log_kind >= B2S_LOG_NONE && log_kind <= B2S_LOG_2, "unknown logarithm %d", log_kind);
+  B2S_REQUIRE(!mel || (mel->bins == plan->bins && mel->device == plan->device),
+              "filterbank was built for %d bins on device %d", mel ? mel->bins : 0, mel ? mel->device : 0);
+  B2S_REQUIRE(rows >= 0 && samples >= 0 && frames >= 0 && pad_left >= 0, "negative extent");
+  B2S_REQUIRE(rows * frames == 0 || (signal && features), "NULL device pointer");
+  B2S_ON_DEVICE(plan->device);
+  FeatureArgs feat{0.5f * power, scale, log_kind, eps, mel ? mel->filters : 0, mel ? mel->lo : nullptr,
+                   mel ? mel->len : nullptr, mel ? mel->woff : nullptr, mel ? mel->weights : nullptr};
+  return launch_forward(plan, signal, rows, samples, row_stride, pad_left, frames, B2S_SPEC_FEATURE, plan->awin, 1.f,
+                        features, (cudaStream_t)stream, &feat);
 }
 
 }  // extern "C"

@@ -309,3 +309,70 @@ def test_near_tie_permutations(b2s, eps, capsys):
               f'float32 oracle (reference arithmetic) {int((swap32 != truth).sum())}/{B}')
     decided = gap > 1e-9
     np.testing.assert_array_equal(ours[decided], truth[decided])
+
+
+# ------------------------------------------------------------------------------------------------ features
+@pytest.mark.parametrize('power,scale_spec,log_base', [(1., False, False), (2., False, 10), (1., True, None),
+                                                        (0.6, False, 2), (2., True, False)])
+def test_feature_epilogues_against_reference_chain(b2s, power, scale_spec, log_base):
+    """to_spectrogram (timefreq.py:171-183) + Logarithm (:37-77) fused behind the STFT, against the same chain
+    of torch ops on the oracle's float64 spectrum.  Tolerance: 1e-4 of the largest value for linear features;
+    log features are compared where the argument is above the clamp (their absolute error is the relative
+    error of the argument)."""
+    from oracle.stft import ReferenceSTFT
+    rng = np.random.RandomState(17)
+    x = rng.randn(3, 2, 9000).astype(np.float32)
+    stft = b2s.features.SpectrogramSTFT(1024, 256, power=power, scale_spec=scale_spec, log_base=log_base,
+                                        sequence_last=False)
+    got, frames = stft(torch.from_numpy(x).to(dev()), sequence_lengths=[9000, 8000, 5000])
+    spec = ReferenceSTFT(1024, 256)(torch.from_numpy(x).double()).abs() ** power
+    if scale_spec:
+        spec = spec / 1024
+    assert got.shape == spec.shape
+    np.testing.assert_array_equal(frames, [stft.samples_to_frames(n) for n in (9000, 8000, 5000)])
+    got = got.cpu().double()
+    if log_base is False:
+        assert float((got - spec).abs().max()) <= 1e-4 * float(spec.abs().max())
+    else:
+        log_fn = {None: torch.log, 10: torch.log10, 2: torch.log2}[log_base]
+        want = log_fn(torch.clamp(spec, min=1e-5))
+        # d log(x) = dx / x: 1e-4 of the utterance maximum, seen from a value x, is 1e-4 max / x in log units
+        bound = 1e-4 * float(spec.max()) / torch.clamp(spec, min=1e-5) + 1e-5
+        scale = {None: 1.0, 10: 1 / np.log(10), 2: 1 / np.log(2)}[log_base]
+        assert bool(((got - want).abs() <= bound * scale).all())
+    # sequence_last=True transposes
+    stft.sequence_last = True
+    got_t, _ = stft(torch.from_numpy(x).to(dev()))
+    assert got_t.shape == spec.transpose(-2, -1).shape
+
+
+@pytest.mark.parametrize('filters,log_base', [(80, 10), (40, None), (23, False)])
+def test_log_mel_against_matmul(b2s, filters, log_base):
+    """MelTransform.forward (timefreq.py:398-470): (|Y|^power) @ mel_basis, then the logarithm -- the fused kernel
+    against torch.matmul with the SAME basis on the oracle's float64 spectrum (this pins the kernel; the basis
+    itself is paderbox's get_fbanks restated, parity unpinned)."""
+    from oracle.stft import ReferenceSTFT
+    rng = np.random.RandomState(5)
+    x = (0.3 * rng.randn(4, 12000)).astype(np.float32)
+    mel = b2s.features.MelTransform(16000, 1024, number_of_filters=filters, lowest_frequency=80,
+                                    highest_frequency=7600, log_base=log_base, sequence_last=False)
+    got, _ = mel(torch.from_numpy(x).to(dev()))
+    spec = ReferenceSTFT(1024, 256)(torch.from_numpy(x).double()).abs()
+    want = spec @ torch.from_numpy(mel.mel_basis).double()
+    assert got.shape == want.shape == (4, spec.shape[1], filters)
+    got = got.cpu().double()
+    if log_base is False:
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    else:
+        log_fn = {None: torch.log, 10: torch.log10}[log_base]
+        ref = log_fn(torch.clamp(want, min=1e-5))
+        bound = (1e-4 * float(want.max()) / torch.clamp(want, min=1e-5) + 1e-5) * (1.0 if log_base is None else 1 / np.log(10))
+        assert bool(((got - ref).abs() <= bound).all())
+    # an arbitrary dense basis (no triangular structure): still exact
+    dense = rng.rand(513, 7).astype(np.float32)
+    mel2 = b2s.features.MelTransform(16000, 1024, mel_basis=dense, log_base=False, sequence_last=False)
+    got2, _ = mel2(torch.from_numpy(x).to(dev()))
+    want2 = spec @ torch.from_numpy(dense).double()
+    assert float((got2.cpu().double() - want2).abs().max()) <= 1e-4 * float(want2.abs().max())
+    with pytest.raises(NotImplementedError):
+        b2s.features.stft_features(b2s.ops.STFT(512, 128), torch.from_numpy(x).to(dev()))
