@@ -296,6 +296,12 @@ B2S_API int b2s_pit_targets(const float* spec_mixture, const float* spec_sources
                     int64_t frames, int64_t bins, float* y_abs, float* x_abs,
                     float* cos_phase_difference, b2s_stream stream);
 
+/* Masked spectra of the evaluation path (padertorch/contrib/examples/source_separation/pit/evaluate.py:147-152):
+ * masked [B, K, frames, F, 2] = mask [B, frames, K, F] * spec_mixture [B, frames, F, 2] -- the rows b2s_istft_forward
+ * consumes ('t k f -> k t f' included).                                                                       */
+B2S_API int b2s_mask_spectrum(const float* mask, const float* spec_mixture, int64_t batch, int sources,
+                      int64_t frames, int64_t bins, float* masked, b2s_stream stream);
+
 /* The same preparation straight from the waveforms, the complex spectra never leaving the registers (fast
  * plans: size 1024 / window_length 1024 / shift % 4 == 0; 1..3 sources; all examples full length):
  * mixture [B, samples], sources [B, K, samples] -> y_abs [B, frames, F], x_abs / cos_phase_difference

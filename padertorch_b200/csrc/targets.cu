@@ -86,6 +86,36 @@ pit_targets_kernel(const float2* __restrict__ spec_y, const float2* __restrict__
   }
 }
 
+
+// Z[b, k, m, f] = mask[b, m, k, f] * Y[b, m, f]: the masked spectra of the evaluation path
+// (padertorch/contrib/examples/source_separation/pit/evaluate.py:147-152: Z = mask * Y[:, None, :], then
+// 't k f -> k t f' for the inverse transform), written in the row layout b2s_istft_forward consumes
+// ([B * K] rows of [M, F] complex bins).  Thread = 2 consecutive complex outputs (one 16-byte store).
+__global__ void __launch_bounds__(kTargetThreads)
+mask_spectrum_kernel(const float* __restrict__ mask, const float2* __restrict__ spec_y, int64_t batch, int K,
+                     int64_t M, int F, float2* __restrict__ out) {
+  const int64_t n = batch * K * M * F;
+  const int64_t i0 = ((int64_t)blockIdx.x * kTargetThreads + threadIdx.x) * 2;
+  if (i0 >= n) return;
+  float2 z[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t i = i0 + e;
+    if (i >= n) { z[e] = make_float2(0.f, 0.f); continue; }
+    const int64_t row = i / F;            // (b * K + k) * M + m
+    const int f = (int)(i - row * F);
+    const int64_t bk = row / M;
+    const int64_t m = row - bk * M;
+    const int64_t b = bk / K;
+    const int k = (int)(bk - b * K);
+    const float w = __ldg(mask + ((b * M + m) * K + k) * F + f);
+    const float2 y = __ldg(spec_y + (b * M + m) * F + f);
+    z[e] = make_float2(w * y.x, w * y.y);
+  }
+  if (i0 + 2 <= n) *reinterpret_cast<float4*>(out + i0) = make_float4(z[0].x, z[0].y, z[1].x, z[1].y);
+  else out[i0] = z[0];
+}
+
 }  // namespace
 
 extern "C" {
@@ -110,6 +140,23 @@ int b2s_pit_targets(const float* spec_mixture, const float* spec_sources, int64_
       reinterpret_cast<const float2*>(spec_mixture), reinterpret_cast<const float2*>(spec_sources), batch, sources,
       frames, (int)bins, blocks_y, y_abs, x_abs, cos_phase_difference);
   B2S_LAUNCH_CHECK("pit_targets_kernel");
+  return B2S_OK;
+}
+
+int b2s_mask_spectrum(const float* mask, const float* spec_mixture, int64_t batch, int sources, int64_t frames,
+                      int64_t bins, float* masked, b2s_stream stream) {
+  B2S_REQUIRE(batch >= 0 && frames >= 0 && bins >= 1 && bins < ((int64_t)1 << 30), "bad extents");
+  B2S_REQUIRE(sources >= 1, "sources=%d", sources);
+  if (batch * frames == 0) return B2S_OK;
+  B2S_REQUIRE(mask && spec_mixture && masked, "NULL device pointer");
+  B2S_REQUIRE(((reinterpret_cast<uintptr_t>(spec_mixture) & 7) | (reinterpret_cast<uintptr_t>(masked) & 15)) == 0,
+              "b2s_mask_spectrum needs an 8-byte aligned spectrum and a 16-byte aligned output");
+  const int64_t blocks = ceil_div(batch * sources * frames * bins, (int64_t)kTargetThreads * 2);
+  B2S_REQUIRE(blocks < ((int64_t)1 << 31), "too many elements for one launch");
+  mask_spectrum_kernel<<<(unsigned)blocks, kTargetThreads, 0, (cudaStream_t)stream>>>(
+      mask, reinterpret_cast<const float2*>(spec_mixture), batch, sources, frames, (int)bins,
+      reinterpret_cast<float2*>(masked));
+  B2S_LAUNCH_CHECK("mask_spectrum_kernel");
   return B2S_OK;
 }
 

@@ -290,6 +290,10 @@ class STFT:
             raise ValueError(
                 f'Please choose one of the predefined output_types'
                 f'{self.possible_out_types} not {self.complex_representation}')
+        return self._inverse_layout(spec, layout)
+
+    def _inverse_layout(self, spec, layout):
+        """iSTFT of a real-view spectrum in a kernel layout ([..., frames, F, 2] or [..., frames, 2F])."""
         _lib.require_cuda_float(spec, 'stft_signal')
         bins = self.size // 2 + 1
         if layout == _lib.SPEC_INTERLEAVED:

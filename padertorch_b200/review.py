@@ -281,3 +281,76 @@ def prepare_pit_targets(mixture, sources, stft=None):
                                  _lib.ptr(y_abs), _lib.ptr(x_abs), _lib.ptr(cpd), _lib.stream_of(device))
     _lib.check(rc, 'b2s_pit_targets')
     return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=frames)
+
+
+# ---------------------------------------------------------------------------------------------- evaluation path
+def separate(masks, mixture_spectrum, stft, num_samples=None):
+    """``z = istft(mask * Y[:, None, :])`` of the evaluation loop (pit/evaluate.py:147-152) for a whole batch on
+    the device: masks [B, M, K, F], mixture_spectrum [B, M, F] complex64 (or [B, M, F, 2]) -> estimates
+    [B, K, samples].  Two launches (b2s_mask_spectrum, b2s_istft_forward)."""
+    lib = _lib.load()
+    masks = _lib.require_cuda_float(masks, 'masks').detach().contiguous()
+    spec = torch.view_as_real(mixture_spectrum) if torch.is_complex(mixture_spectrum) else mixture_spectrum
+    spec = _lib.require_cuda_float(spec, 'mixture_spectrum').detach().contiguous()
+    batch, frames, k, bins = masks.shape
+    assert spec.shape == (batch, frames, bins, 2), (spec.shape, masks.shape)
+    masked = torch.empty((batch, k, frames, bins, 2), dtype=torch.float32, device=masks.device)
+    with torch.cuda.device(masks.device):
+        rc = lib.b2s_mask_spectrum(_lib.ptr(masks), _lib.ptr(spec), batch, k, frames, bins, _lib.ptr(masked),
+                                   _lib.stream_of(masks.device))
+    _lib.check(rc, 'b2s_mask_spectrum')
+    estimates = stft._inverse_layout(masked, _lib.SPEC_INTERLEAVED)      # [B, K, samples]
+    if num_samples is not None:
+        estimates = estimates[..., :max(int(n) for n in num_samples)]
+    return estimates
+
+
+def evaluate_separation(masks, mixture, sources, stft=None, num_samples=None):
+    """Batched evaluation (pit/evaluate.py:144-176 with the metrics of this package
+    in place of pb_bss / mir_eval): mask * STFT(y) -> iSTFT -> K x K SI-SDR / SDR matrices from ONE statistics
+    pass -> assignment on the device.
+
+    masks [B, M, K, F], mixture [B, T], sources [B, K, T].  Returns a dict of device tensors:
+    ``estimates`` [B, K, T], ``permutation`` [B, K] (estimate matched with source k, chosen by SI-SDR),
+    ``si_sdr`` / ``sdr`` [B, K] of the matched pairs in dB, ``input_si_sdr`` / ``input_sdr`` [B, K] (the
+    mixture as the estimate of every source) and their ``*_improvement``."""
+    from .ops.losses import source_separation as ss
+    stft = STFT(1024, 256) if stft is None else stft
+    lib = _lib.load()
+    mixture = _lib.require_cuda_float(mixture, 'mixture').detach().contiguous()
+    sources = _lib.require_cuda_float(sources, 'sources').detach().contiguous()
+    batch, k, samples = sources.shape
+    spectrum = stft._spectrum(mixture, _lib.SPEC_INTERLEAVED)            # [B, M, F, 2]
+    estimates = separate(masks, spectrum, stft)[..., :samples].contiguous()
+    if estimates.shape[-1] < samples:                                    # pad=False crops the tail
+        sources = sources[..., :estimates.shape[-1]].contiguous()
+        mixture = mixture[..., :estimates.shape[-1]].contiguous()
+        samples = estimates.shape[-1]
+    lengths = [samples] * batch if num_samples is None else [min(int(n), samples) for n in num_samples]
+
+    def matrices(est):
+        rows = [[lengths[b], b * k * samples, b * k * samples] for b in range(batch)]
+        meta = meta_tensor(rows, est.device, cache_key=('eval', k, samples, tuple(lengths)))
+        problem = _pairs.PairProblem(est, sources, meta, batch, 1, k, max(lengths), samples, samples)
+        stats = problem.stats()
+        out = []
+        for kind in (_lib.LOSS_SI_SDR, _lib.LOSS_SDR):
+            m = torch.empty((batch, k, k), dtype=torch.float32, device=est.device)
+            with torch.cuda.device(est.device):
+                rc = lib.b2s_pair_loss_matrix(_lib.ptr(stats), _lib.ptr(meta), batch, 1, k, kind, 0, -1.0,
+                                              _lib.REDUCE_SUM, _lib.ptr(m), _lib.stream_of(est.device))
+            _lib.check(rc, 'b2s_pair_loss_matrix')
+            out.append(m)
+        return out
+
+    loss_si, loss_sdr = matrices(estimates)                  # entries are losses = -dB
+    perm, _ = ss._first_minimum(loss_si, orientation=0)      # perm[b, k] = estimate matched with source k
+    index = perm.long()[:, None, :]                          # gather rows perm[k] of column k
+    si_sdr = -torch.gather(loss_si, 1, index)[:, 0, :]
+    sdr = -torch.gather(loss_sdr, 1, index)[:, 0, :]
+    observation = mixture[:, None, :].expand(batch, k, samples).contiguous()
+    in_si, in_sdr = matrices(observation)
+    diag = torch.arange(k, device=sources.device)
+    input_si_sdr, input_sdr = -in_si[:, diag, diag], -in_sdr[:, diag, diag]
+    return dict(estimates=estimates, permutation=perm, si_sdr=si_sdr, sdr=sdr, input_si_sdr=input_si_sdr,
+                input_sdr=input_sdr, si_sdr_improvement=si_sdr - input_si_sdr, sdr_improvement=sdr - input_sdr)

@@ -376,3 +376,43 @@ def test_log_mel_against_matmul(b2s, filters, log_base):
     assert float((got2.cpu().double() - want2).abs().max()) <= 1e-4 * float(want2.abs().max())
     with pytest.raises(NotImplementedError):
         b2s.features.stft_features(b2s.ops.STFT(512, 128), torch.from_numpy(x).to(dev()))
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+@pytest.mark.parametrize('k', [2, 3, 5])
+def test_evaluation_path_against_oracle(b2s, k):
+    """review.evaluate_separation (pit/evaluate.py:144-176 on the device): mask * STFT(y) -> iSTFT -> SI-SDR /
+    SDR of the best assignment, against the same chain through the oracle (reference iSTFT, regression losses,
+    brute-force assignment by SI-SDR)."""
+    from oracle import losses as ol
+    from oracle.stft import ReferenceSTFT
+    rng = np.random.RandomState(40 + k)
+    B, T = 3, 12000
+    s = (0.1 * rng.randn(B, k, T)).astype(np.float32)
+    y = s.sum(1)
+    stft = b2s.ops.STFT(1024, 256)
+    ref = ReferenceSTFT(1024, 256)
+    M = stft.samples_to_frames(T)
+    # oracle-like masks: ideal ratio masks of a random permutation of the speakers + noise
+    S = ref(torch.from_numpy(s).double()).abs()                       # [B, K, M, F]
+    order = [rng.permutation(k) for _ in range(B)]
+    irm = torch.stack([S[b, order[b]] for b in range(B)]) / (S.sum(1, keepdim=True) + 1e-9)
+    masks = (irm.permute(0, 2, 1, 3) + 0.05 * torch.from_numpy(rng.rand(B, M, k, 513))).float().contiguous()
+    out = b2s.review.evaluate_separation(masks.to(dev()), torch.from_numpy(y).to(dev()), torch.from_numpy(s).to(dev()),
+                                         stft=stft)
+    Y = ref(torch.from_numpy(y).double())                              # [B, M, F] complex
+    Z = masks.double().permute(0, 2, 1, 3) * Y[:, None]               # [B, K, M, F]
+    z = ref.inverse(Z)[..., :T]
+    assert float((out['estimates'].cpu().double() - z).abs().max()) <= 1e-4 * float(z.abs().max())
+    for b in range(B):
+        pair = torch.stack([torch.stack([ol.si_sdr_loss(z[b, i], torch.from_numpy(s[b, j]).double()) for j in range(k)])
+                            for i in range(k)])
+        best = min(itertools.permutations(range(k)), key=lambda p: (sum(float(pair[p[j], j]) for j in range(k)), p))
+        assert tuple(out['permutation'][b].tolist()) == best
+        for j in range(k):
+            e, t = z[b, best[j]], torch.from_numpy(s[b, j]).double()
+            np.testing.assert_allclose(float(out['si_sdr'][b, j]), -float(ol.si_sdr_loss(e, t)), rtol=1e-3, atol=2e-3)
+            np.testing.assert_allclose(float(out['sdr'][b, j]), -float(ol.sdr_loss(e, t)), rtol=1e-3, atol=2e-3)
+            obs = torch.from_numpy(y[b]).double()
+            np.testing.assert_allclose(float(out['input_si_sdr'][b, j]), -float(ol.si_sdr_loss(obs, t)), rtol=1e-3, atol=2e-3)
+    assert bool((out['si_sdr_improvement'] > 0).all())      # ratio masks do separate
