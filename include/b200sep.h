@@ -310,6 +310,26 @@ B2S_API int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture
                          int64_t batch, int64_t samples, int sources_k, int64_t frames, int64_t pad_left,
                          float* y_abs, float* x_abs, float* cos_phase_difference, b2s_stream stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense projections of the mask networks on the tcgen05 tensor cores:
+ *     c [m, n] = act(a [m, k] . weight [n, k]^T + bias [n])            == torch.nn.functional.linear
+ * for Linear(1200, 1200) + ReLU, Linear(1200, F K) + sigmoid and the LSTM input projections of
+ * padertorch/contrib/examples/source_separation/pit/model.py:60-73, 96-102, and the 1 x 1 convolutions of
+ * padertorch/modules/convnet.py:120-167.  TMA tensor maps -> shared memory -> tcgen05.mma.kind::tf32 with the
+ * accumulator in tensor memory -> tcgen05.ld -> bias / activation -> global.
+ * a_lo / weight_lo: x - tf32(x) of the operands (b2s_tf32_split, or `c_lo` of the preceding projection): with
+ * them the kernel evaluates a_hi w_hi + a_hi w_lo + a_lo w_hi (fp32-faithful: ~2^-21 relative per product,
+ * the reference runs these GEMMs in fp32); without them (both NULL) one TF32 product (~1e-3).
+ * Row strides in floats, multiples of 4 (TMA: 16-byte pitches); base pointers 16-byte aligned.
+ * c_lo (may be NULL): additionally writes c - tf32(c) for a following projection.                           */
+#define B2S_ACT_NONE 0
+#define B2S_ACT_RELU 1
+#define B2S_ACT_SIGMOID 2
+B2S_API int b2s_tf32_split(const float* x, int64_t count, float* lo, b2s_stream stream);
+B2S_API int b2s_linear_forward(const float* a, const float* a_lo, const float* weight, const float* weight_lo,
+                       const float* bias, int64_t m, int64_t n, int64_t k, int64_t a_row_stride,
+                       int64_t weight_row_stride, int activation, float* c, float* c_lo, b2s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,9 @@ SIGNATURES = {
     'b2s_pair_matrix_backward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
                                          c_void, c_int, c_int, c_dbl, c_int, c_void, c_void, c_void]),
     'b2s_assign': (c_int, [c_void, c_i64, c_int, c_int, c_int, c_void, c_void, c_void]),
+    'b2s_tf32_split': (c_int, [c_void, c_i64, c_void, c_void]),
+    'b2s_linear_forward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
+                                   c_void, c_void, c_void]),
     'b2s_dc_workspace_bytes': (c_i64, [c_i64, c_i64, c_i64, c_int]),
     'b2s_dc_forward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_int,
                                ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_void,
@@ -83,6 +86,7 @@ SIGNATURES = {
 SPEC_INTERLEAVED, SPEC_CONCAT, SPEC_ABS, SPEC_LOG1P_ABS = 0, 1, 2, 3
 PIT_META, PAIR_META, DC_META = 6, 3, 4
 MAX_SOURCES, DC_MAX_CHANNELS = 8, 64
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 LOSS_MSE, LOSS_LOG_MSE, LOSS_LOG1P_MSE, LOSS_SDR, LOSS_SI_SDR, LOSS_SA_SDR = range(6)
 FLAG_OFFSET_INVARIANT, FLAG_GRAD_STOP = 1, 2
 REDUCE_NONE, REDUCE_SUM, REDUCE_MEAN = 0, 1, 2

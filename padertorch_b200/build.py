@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, 'build')
 LIB = os.path.join(HERE, 'libb200sep.so')
-SOURCES = ['capi.cu', 'stft.cu', 'pit.cu', 'pairstats.cu', 'dc.cu', 'fused.cu', 'fused_bwd.cu', 'targets.cu', 'targets_fused.cu']
+SOURCES = ['capi.cu', 'stft.cu', 'pit.cu', 'pairstats.cu', 'dc.cu', 'fused.cu', 'fused_bwd.cu', 'targets.cu', 'targets_fused.cu', 'gemm_umma.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

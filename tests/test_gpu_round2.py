@@ -416,3 +416,56 @@ def test_evaluation_path_against_oracle(b2s, k):
             obs = torch.from_numpy(y[b]).double()
             np.testing.assert_allclose(float(out['input_si_sdr'][b, j]), -float(ol.si_sdr_loss(obs, t)), rtol=1e-3, atol=2e-3)
     assert bool((out['si_sdr_improvement'] > 0).all())      # ratio masks do separate
+
+
+# ------------------------------------------------------------------------------------------------ projections
+@pytest.mark.parametrize('m,n,k', [(1, 8, 4), (77, 130, 36), (253, 1026, 1200), (640, 2400, 513), (1000, 1200, 1200)])
+def test_tcgen05_linear_against_float64(b2s, m, n, k):
+    """b2s_linear_forward (tcgen05 / TMEM / TMA) == activation(F.linear(x, w, b)) of pit/model.py:96-102.
+    precision='fp32' (3-term TF32 split) must be as close to the float64 result as cuBLAS fp32 is, within a small
+    factor -- the reference runs these GEMMs in fp32; precision='tf32' is held to 2e-3 of the largest output."""
+    torch.manual_seed(m + n + k)
+    x = torch.randn(m, k, device=dev())
+    w = torch.randn(n, k, device=dev()) / k ** 0.5
+    b = torch.randn(n, device=dev())
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    scale = float(ref.abs().max())
+    err_cublas = float((torch.nn.functional.linear(x, w, b).double() - ref).abs().max())
+    for act, fn in ((None, lambda t: t), ('relu', torch.relu), ('sigmoid', torch.sigmoid)):
+        want = fn(ref)
+        got = b2s.ops.linear(x, w, b, activation=act)
+        err = float((got.double() - want).abs().max())
+        assert err <= max(10 * err_cublas, 2e-6 * scale), (act, err, err_cublas, scale)
+        got_tf32 = b2s.ops.linear(x, w, b, activation=act, precision='tf32')
+        assert float((got_tf32.double() - want).abs().max()) <= 2e-3 * max(scale, 1.0)
+    # no bias, leading axes, chained lo output
+    got = b2s.ops.linear(x.view(1, m, k), w)
+    assert got.shape == (1, m, n)
+    assert float((got[0].double() - (ref - b.double())).abs().max()) <= max(10 * err_cublas, 2e-6 * scale)
+
+
+def test_tcgen05_linear_autograd_and_chaining(b2s):
+    """Gradients (cuBLAS backward around the tensor-core forward) equal torch's; the `c_lo` output of one
+    projection is a valid lo operand of the next (Linear + ReLU -> Linear + sigmoid, pit/model.py:98-102)."""
+    from padertorch_b200.ops.linear import linear_forward, tf32_split
+    torch.manual_seed(0)
+    x = torch.randn(300, 1200, device=dev(), requires_grad=True)
+    l1 = torch.nn.Linear(1200, 1200).to(dev())
+    l2 = torch.nn.Linear(1200, 1026).to(dev())
+    y = b2s.ops.linear(b2s.ops.linear(x, l1.weight, l1.bias, 'relu'), l2.weight, l2.bias, 'sigmoid')
+    y.square().mean().backward()
+    grads = [x.grad.clone(), l1.weight.grad.clone(), l2.bias.grad.clone()]
+    x.grad = None; l1.zero_grad(); l2.zero_grad()
+    y_ref = torch.sigmoid(l2(torch.relu(l1(x))))
+    y_ref.square().mean().backward()
+    torch.testing.assert_close(y, y_ref, rtol=1e-4, atol=1e-5)
+    for g, r in zip(grads, [x.grad, l1.weight.grad, l2.bias.grad]):
+        torch.testing.assert_close(g, r, rtol=1e-3, atol=1e-5 * float(r.abs().max()) + 1e-9)
+    with torch.no_grad():
+        h, h_lo = linear_forward(x.detach(), l1.weight, l1.bias, 'relu', want_lo=True)
+        torch.testing.assert_close(h_lo, tf32_split(h), rtol=0, atol=0)
+        out, _ = linear_forward(h, l2.weight, l2.bias, 'sigmoid', x_lo=h_lo)
+        torch.testing.assert_close(out, y_ref, rtol=1e-4, atol=1e-5)
+    m = b2s.ops.FusedLinear(1200, 600, activation='relu').to(dev())
+    torch.testing.assert_close(m(x.detach()), torch.relu(torch.nn.functional.linear(x.detach(), m.weight, m.bias)),
+                               rtol=1e-4, atol=1e-5)
