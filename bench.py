@@ -1,8 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- utterances/s of the STFT -> mask -> PIT hot path (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
+                    [--config pit|pit3|dc|tasnet|train]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+--config selects the workload: `pit` (default) is BASELINE.json's headline, described below; the others are
+BASELINE.json's configs 2-5 (bench_configs.py): `pit3` K = 3 / 8 s, `dc` deep-clustering loss on a ragged batch,
+`tasnet` time-domain PIT losses + the gradient all-reduce of a ConvTasNet, `train` one full training step of the
+BLSTM mask estimator (cuDNN LSTM + tcgen05 projections + fused loss + overlapped NCCL gradient exchange).
+--impl reference-gpu times the unmodified reference ops on the same GPU (its ATen composition).
 
 One "step" = one pass of the hot path over one batch of synthetic 4 s / 16 kHz 2-speaker mixtures:
   kernel 1  |Y| = |STFT(y)|                      (front-end feature, b2s_stft_forward, ABS epilogue)
@@ -46,6 +53,22 @@ WORKLOAD = ('fused STFT->mask->PIT-loss path, batch 64 x 4 s x 16 kHz, 2 speaker
 BYTES_FRONT = 4 * SAMPLES + 4 * FRAMES * BINS                                  # y -> |Y|
 BYTES_LOSS = 4 * SAMPLES * (1 + SOURCES) + 4 * FRAMES * BINS * SOURCES         # mask, y, s -> loss, perm
 BYTES_PATH = BYTES_FRONT + BYTES_LOSS                                          # 2 581 468 B/utt
+FUSED_WARP_INSTRUCTIONS = 24.14e6   # smsp__inst_executed.sum of one fused launch at this shape (ncu, profiles/)
+
+
+def headline_config(world):
+    """Identical in every arm (ours / reference / reference-gpu): the workload, not how an arm runs it."""
+    return {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'samples': SAMPLES, 'sources': SOURCES,
+            'frames': FRAMES, 'bins': BINS,
+            'l2': f'inputs larger than L2: {ROTATE} rotating input sets of 215 MB each',
+            'parallelism': f'{world} independent shard(s), no data-path collective'}
+
+
+def nccl_info_to_stderr():
+    """NCCL's INFO log (ranks, rings / trees / NVLS) goes to stderr, stdout stays the one JSON line."""
+    os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2S_NCCL_DEBUG', 'INFO'))
+    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 
 def measured_peaks():
@@ -207,7 +230,7 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'l2': 'n/a (CPU)'},
+        'data': 'synthetic', 'config': headline_config(world),
         'cpu_baseline': {'value': value, 'unit': 'utt/s', 'cores': cores, 'kind': kind,
                          'sample': f'{args.steps} x one full batch of {BATCH} utterances through '
                                    + ('the unmodified reference (baseline/_ref): ' if kind == 'reference'
@@ -217,6 +240,40 @@ def run_reference(args, rank, world):
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args, rank, world, local_rank):
+    """The reference's own ATen composition on the B200: the unmodified
+    pt.ops.STFT (dense DFT convolution) + per-example pit_loss loop on CUDA tensors, device-timed."""
+    if rank != 0:
+        return
+    pt = import_reference()
+    if pt is None:
+        print(json.dumps({'impl': 'reference-gpu', 'unavailable': 'reference not installed in baseline/_ref'}), flush=True)
+        return
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    stft = pt.ops.STFT(SIZE, SHIFT)
+    sets = [synthetic_batch(i, device=device) for i in range(ROTATE)]
+    for i in range(max(args.warmup, 3)):
+        reference_step(pt, sets[i % ROTATE], stft, BATCH)
+    torch.cuda.synchronize()
+    steps = max(3, min(args.steps, 20))
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        reference_step(pt, sets[i % ROTATE], stft, BATCH)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / steps
+    value = BATCH / (ms * 1e-3)
+    print(json.dumps({'impl': 'reference-gpu', 'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s', 'n_gpus': 1,
+                      'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
+                      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': headline_config(1),
+                      'note': 'unmodified reference ops (pt.ops.STFT = conv1d with the dense DFT matrix, per-example '
+                              'pit_loss loop with int(idx) syncs) on CUDA tensors, python eager as the reference runs them',
+                      'gpu_launches': 0}), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -229,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
-        os.environ['NCCL_DEBUG'] = os.environ.get('B2S_NCCL_DEBUG', 'ERROR')   # keep stdout to the one JSON line
+        nccl_info_to_stderr()
         dist.init_process_group('nccl', device_id=device)
 
     stft = b2s.ops.STFT(SIZE, SHIFT)
@@ -390,21 +447,41 @@ def run_ours(args, rank, world, local_rank):
     out_perm = torch.empty((BATCH, SOURCES), dtype=torch.int32).pin_memory()
     d2h = out_loss.numel() * 4 + out_perm.numel() * 4
 
-    def e2e_step(host):
-        data = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        loss, perm = step(data)
-        out_loss.copy_(loss, non_blocking=True)
-        out_perm.copy_(perm, non_blocking=True)
+    # double buffered: the host -> device copies of step i + 1 run on a copy stream while step i computes; every step
+    # still moves its own inputs over PCIe and reads its own results back inside the timed region
+    copy_stream = torch.cuda.Stream(device)
+    slots = [dict(data={k: torch.empty_like(v, device=device) for k, v in host_sets[0].items()},
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+
+    def upload(i):
+        slot = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot['free'])          # the step that last used this slot is done with it
+            for k, v in host_sets[i % 2].items():
+                slot['data'][k].copy_(v, non_blocking=True)
+            slot['ready'].record(copy_stream)
+
+    def e2e_loop(n):
+        for slot in slots:
+            slot['free'].record(torch.cuda.current_stream())
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            slot = slots[i % 2]
+            torch.cuda.current_stream().wait_event(slot['ready'])
+            loss, perm = step(slot['data'])
+            out_loss.copy_(loss, non_blocking=True)
+            out_perm.copy_(perm, non_blocking=True)
+            slot['free'].record(torch.cuda.current_stream())
 
     e2e_steps = max(5, min(args.steps, 30))
-    for i in range(3):
-        e2e_step(host_sets[i % 2])
+    e2e_loop(3)
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(host_sets[i % 2])
+    e2e_loop(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if distributed:
@@ -424,10 +501,8 @@ def run_ours(args, rank, world, local_rank):
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'samples': SAMPLES, 'sources': SOURCES,
-                       'l2': f'inputs larger than L2: {ROTATE} rotating input sets of 215 MB each',
-                       'parallelism': f'{world} independent shard(s), no data-path collective',
-                       'launch': 'python eager' if args.eager else ('CUDA graph replay (2 kernel nodes per step)' if args.single_step_graphs else f'CUDA graph replay ({GRAPH_STEPS} steps = {2 * GRAPH_STEPS} kernel nodes per graph, 2 kernel nodes per step' + ('' if args.single_stream else '; front-end kernels captured on a second stream: front-end of step n + 1 overlaps the tail of the loss kernel of step n') + ')')},
+            'config': headline_config(world),
+            'launch': 'python eager' if args.eager else ('CUDA graph replay (2 kernel nodes per step)' if args.single_step_graphs else f'CUDA graph replay ({GRAPH_STEPS} steps = {2 * GRAPH_STEPS} kernel nodes per graph, 2 kernel nodes per step' + ('' if args.single_stream else '; front-end kernels captured on a second stream: front-end of step n + 1 overlaps the tail of the loss kernel of step n') + ')'),
             'e2e': {'value': world * BATCH * e2e_steps / e2e_s, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
             'gpu_launches': 2 * args.steps,
@@ -435,6 +510,13 @@ def run_ours(args, rank, world, local_rank):
             'roofline': {'bound': 'hbm', 'kernel': 'stft_pit_fused_kernel', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind,
                          'algorithmic_bytes_per_launch': BYTES_LOSS * BATCH, 'kernel_ms': loss_ms},
+            'roofline_issue': {'bound': 'fp32-issue', 'kernel': 'stft_pit_fused_kernel',
+                               'achieved': FUSED_WARP_INSTRUCTIONS / (loss_ms * 1e-3) / 1e9,
+                               'peak': 148 * 4 * 1.965, 'unit': 'G warp-instructions/s',
+                               'frac': FUSED_WARP_INSTRUCTIONS / (loss_ms * 1e-3) / 1e9 / (148 * 4 * 1.965),
+                               'note': 'issue slots: 148 SMs x 4 sub-partitions x 1.965 GHz; instructions per launch '
+                                       'from ncu smsp__inst_executed.sum (profiles/r2_ncu_summary.txt); the kernel is '
+                                       'bound by shared-memory + FP32-pipe work per frame, not by HBM (DESIGN.md 6)'},
             'path_roofline': {'achieved': path_gbs, 'frac': path_gbs / peak, 'unit': 'GB/s',
                               'algorithmic_bytes_per_step': BYTES_PATH * BATCH,
                               'front_end_kernel_ms': front_ms,
@@ -459,7 +541,9 @@ def main():
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--steps', type=int, default=1000)
     parser.add_argument('--warmup', type=int, default=10)
-    parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    parser.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-gpu'])
+    parser.add_argument('--config', default='pit', choices=['pit', 'pit3', 'dc', 'tasnet', 'train'],
+                        help="workload: BASELINE.json's headline (pit) or one of its configs 2-5")
     parser.add_argument('--eager', action='store_true', help='launch from Python instead of CUDA graphs')
     parser.add_argument('--single-stream', action='store_true', help='capture the multi-step graph on one stream (no overlap of the next front-end with the running loss kernel)')
     parser.add_argument('--single-step-graphs', action='store_true', help='one CUDA graph per step instead of one per round of input sets')
@@ -467,11 +551,18 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.config != 'pit':
+        import bench_configs
+        bench_configs.run(args, rank, world, local_rank)
+        return
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: padertorch_b200 has no CPU fallback')
+    if args.impl == 'reference-gpu':
+        run_reference_gpu(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

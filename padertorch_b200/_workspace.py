@@ -23,18 +23,18 @@ def workspace(device, nbytes, tag):
 
 
 def meta_tensor(rows, device, cache_key=None):
-    """int64 [len(rows), width] table on `device`.  Tables that depend only on shapes are cached
-    (cache_key), tables holding pointer differences are uploaded per call."""
+    """int64 [len(rows), width] table on `device`, cached: by `cache_key` for tables that depend only on shapes,
+    by content otherwise (tables of pointer differences repeat as long as the caching allocator hands the same
+    blocks back, which is the steady state of a training loop -- and what makes the calls CUDA-graph capturable:
+    an upload from pageable memory is not)."""
     device = torch.device(device)
-    if cache_key is not None:
-        key = (device.index, cache_key)
-        hit = _meta_cache.get(key)
-        if hit is not None:
-            return hit
+    key = (device.index, cache_key if cache_key is not None else ('rows', tuple(tuple(int(v) for v in r) for r in rows)))
+    hit = _meta_cache.get(key)
+    if hit is not None:
+        return hit
     table = torch.tensor(rows, dtype=torch.int64).to(device)
-    if cache_key is not None:
-        with _lock:
-            if len(_meta_cache) >= _META_CACHE_LIMIT:
-                _meta_cache.clear()
-            _meta_cache[key] = table
+    with _lock:
+        if len(_meta_cache) >= _META_CACHE_LIMIT:
+            _meta_cache.clear()
+        _meta_cache[key] = table
     return table
