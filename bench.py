@@ -36,6 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL reads its environment when the library is loaded (import torch): ask for the INFO log (ranks, rings / trees /
+# NVLS) before that; main() points file descriptor 1 at stderr, so the log never mixes with the JSON line on stdout
+os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2S_NCCL_DEBUG', 'INFO'))
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -64,11 +68,32 @@ def headline_config(world):
             'parallelism': f'{world} independent shard(s), no data-path collective'}
 
 
+_JSON_OUT = None
+
+
+def reserve_stdout_for_json():
+    """From here on file descriptor 1 points at stderr: whatever libraries print (NCCL's INFO log goes to stdout)
+    lands in stderr, and emit() writes the one JSON line to the ORIGINAL stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _JSON_OUT is not None:
+        _JSON_OUT.write(text + '\n')
+        _JSON_OUT.flush()
+    else:
+        print(text, flush=True)
+
+
 def nccl_info_to_stderr():
-    """NCCL's INFO log (ranks, rings / trees / NVLS) goes to stderr, stdout stays the one JSON line."""
-    os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2S_NCCL_DEBUG', 'INFO'))
-    os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    """NCCL's INFO log (ranks, rings / trees / NVLS) is kept, not silenced (NCCL_DEBUG is set at the top of this file,
+    before torch is imported); it reaches stderr through reserve_stdout_for_json()."""
+    assert _JSON_OUT is not None, 'call reserve_stdout_for_json() first'
 
 
 def measured_peaks():
@@ -239,7 +264,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_gpu(args, rank, world, local_rank):
@@ -249,7 +274,7 @@ def run_reference_gpu(args, rank, world, local_rank):
         return
     pt = import_reference()
     if pt is None:
-        print(json.dumps({'impl': 'reference-gpu', 'unavailable': 'reference not installed in baseline/_ref'}), flush=True)
+        emit({'impl': 'reference-gpu', 'unavailable': 'reference not installed in baseline/_ref'})
         return
     device = torch.device('cuda', local_rank)
     torch.cuda.set_device(device)
@@ -267,13 +292,13 @@ def run_reference_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     ms = start.elapsed_time(end) / steps
     value = BATCH / (ms * 1e-3)
-    print(json.dumps({'impl': 'reference-gpu', 'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s', 'n_gpus': 1,
+    emit({'impl': 'reference-gpu', 'metric': 'utterances/sec', 'value': value, 'unit': 'utt/s', 'n_gpus': 1,
                       'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
                       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                       'config': headline_config(1),
                       'note': 'unmodified reference ops (pt.ops.STFT = conv1d with the dense DFT matrix, per-example '
                               'pit_loss loop with int(idx) syncs) on CUDA tensors, python eager as the reference runs them',
-                      'gpu_launches': 0}), flush=True)
+                      'gpu_launches': 0})
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -531,7 +556,7 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(traffic_file):
             with open(traffic_file) as fd:
                 line['roofline']['traffic'] = json.load(fd).get('stft_pit_fused_kernel')
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.destroy_process_group()
 
@@ -551,7 +576,9 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    reserve_stdout_for_json()
     if args.config != 'pit':
+        sys.modules.setdefault('bench', sys.modules[__name__])   # bench_configs shares this module's state (emit)
         import bench_configs
         bench_configs.run(args, rank, world, local_rank)
         return

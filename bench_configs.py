@@ -108,7 +108,7 @@ def _cpu_model():
 
 
 def _emit(line):
-    print(json.dumps(line), flush=True)
+    B.emit(line)
 
 
 def _base_line(args, world, value, ms_per_step, config, **extra):

@@ -23,6 +23,63 @@ import padertorch_b200 as b2s  # noqa: E402
 from padertorch_b200 import parallel  # noqa: E402
 
 
+def real_trainer_check(rank, world, dev):
+    import tempfile
+    import warnings
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'padertorch')):
+        if rank == 0:
+            print('[nccl_probe] reference not installed in baseline/_ref: real-Trainer check skipped', flush=True)
+        return
+    for path in (os.path.join(ROOT, 'oracle', 'ref_standins'), ref):
+        if path not in sys.path:
+            sys.path.insert(0, path)
+    warnings.filterwarnings('ignore')
+    import padertorch as pt
+    from padertorch.contrib.examples.source_separation.pit.model import PermutationInvariantTrainingModel
+    b2s.patch_padertorch(pt)
+    stft = pt.ops.STFT(1024, 256)
+
+    def examples(n):
+        out = []
+        g = torch.Generator().manual_seed(7)
+        for i in range(n):
+            T = 16000 - 800 * (i % 3)
+            s = 0.1 * torch.randn(2, T, generator=g)
+            Y = stft(s.sum(0).to(dev))
+            X = stft(s.to(dev)).transpose(0, 1)
+            out.append(dict(Y_abs=[Y.abs().cpu()], X_abs=[X.abs().cpu()],
+                            cos_phase_difference=[torch.cos(torch.angle(Y[:, None, :]) - torch.angle(X)).cpu()]))
+        return out
+
+    def model():
+        torch.manual_seed(3)
+        return PermutationInvariantTrainingModel(F=513, recurrent_layers=1, units=32, K=2, dropout_input=0.,
+                                                 dropout_hidden=0., dropout_linear=0.)
+
+    data = examples(2 * world + 1)           # not divisible by the world size: the tail group is dropped
+    steps = 2
+    kwargs = dict(optimizer=pt.optimizer.SGD(lr=0.05), loss_weights={'pit_mse_loss': 1.0, 'pit_ips_loss': 0.5},
+                  stop_trigger=(steps, 'iteration'), summary_trigger=(1, 'iteration'), checkpoint_trigger=(1000, 'iteration'))
+    Trainer = parallel.distributed_trainer_class(pt.Trainer)
+    with tempfile.TemporaryDirectory() as tmp:
+        mine = model()
+        trainer = Trainer(mine, os.path.join(parallel.rank_storage_dir(tmp), 'dist'),
+                          virtual_minibatch_size=parallel.rounds_per_rank(world), **kwargs)
+        trainer.train(parallel.ShardedDataset(data), device=dev.index, progress_bar=False)
+        if rank == 0:
+            single = model()
+            reference_trainer = pt.Trainer(single, os.path.join(tmp, 'single'), virtual_minibatch_size=world, **kwargs)
+            reference_trainer.train(data[:2 * world], device=dev.index, progress_bar=False)
+            worst = max(float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
+                        for p, q in zip(mine.parameters(), single.parameters()))
+            print(f'[nccl_probe] real padertorch.Trainer, {world} GPU(s) x 1 round vs 1 GPU x virtual_minibatch_size {world}, '
+                  f'{steps} optimizer steps: max relative parameter difference {worst:.2e}; summed loss of the last step '
+                  f'{trainer.last_loss_sum:.6f}', flush=True)
+            assert worst < 1e-4, worst
+    b2s.unpatch_padertorch()
+
+
 def main():
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', rank)))
@@ -65,6 +122,10 @@ def main():
         print(f'[nccl_probe] world {world}: summed loss {float(total):.6f} vs single-process {float(want):.6f}; '
               f'max relative gradient difference {worst:.2e}', flush=True)
         assert abs(float(total) - float(want)) <= 1e-5 * abs(float(want)) and worst < 1e-5
+
+    # ---- 1b. the REAL padertorch.Trainer (baseline/_ref) under DistributedTrainer: G GPUs x 1 round per step must equal
+    # the unmodified Trainer on one GPU with virtual_minibatch_size = G on the same examples
+    real_trainer_check(rank, world, dev)
 
     # ---- cost of the exchange step
     numel = 25_324_626                       # PIT BLSTM (F = 513), SURVEY.md appendix B
