@@ -123,7 +123,13 @@ __device__ __forceinline__ void warp_search_permutations(const double* cost, int
 
 // One frame position = (K [+1]) transforms whose magnitudes stay in registers as packed (A side, B side)
 // pairs, then the K x K SSE of 9 packed bin pairs per lane (slot 8 = DC / Nyquist, live in lane 0 only).
-template <int K, bool RECOMPUTE_Y, int WARPS, int CTAS, int NS>
+// RING (shift 256 only): the frames of a position are not copied whole.  Every transform keeps a ring of five hops
+// of 256 samples; a warp walks consecutive positions of an utterance, so position m + 1 needs ONE new hop per
+// signal (1 KB instead of 4 KB: a quarter of the L2 -> shared-memory traffic and no re-fetch of overlapping frames
+// from DRAM), and that hop's slot is not part of the frame being transformed: it is requested a whole position
+// ahead.  Only the first position of a range / an utterance fills four hops.
+constexpr int kHop = 256, kRingHops = 5;
+template <int K, bool RECOMPUTE_Y, int WARPS, int CTAS, int NS, bool RING>
 __global__ void __launch_bounds__(32 * WARPS, CTAS)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
                       const float* __restrict__ sources, const float* __restrict__ mask,
@@ -136,7 +142,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   constexpr int F = rf::kBins;
   constexpr int kFusedWarps = WARPS;
   constexpr int NT = RECOMPUTE_Y ? K + 1 : K;   // transforms per position; with RECOMPUTE_Y the mixture is first
-  constexpr int kWarpFloats = NT * rf::kSize + 2 * NS * rf::kTile1 + row_area_floats(K);
+  constexpr int kSig = RING ? kRingHops * kHop : rf::kSize;   // floats per staged signal
+  constexpr int kWarpFloats = NT * kSig + 2 * NS * rf::kTile1 + row_area_floats(K);
   extern __shared__ __align__(16) float smem[];   // per warp: [NT][1024] frames, NS exchange tiles, mask / |Y| rows
   __shared__ __align__(8) uint64_t bars[kFusedWarps][2];
   __shared__ double totals_sm[kFusedWarps][NV];
@@ -156,8 +163,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     trace[((size_t)blockIdx.x * kFusedWarps + warp) * 8 + 6] = smid;
   }
   float* sig = smem + warp * kWarpFloats;                          // frame of transform t at sig + t * 1024
-  float2* tile = reinterpret_cast<float2*>(sig + NT * rf::kSize);
-  float* rows_area = sig + NT * rf::kSize + 2 * NS * rf::kTile1;
+  float2* tile = reinterpret_cast<float2*>(sig + NT * kSig);
+  float* rows_area = sig + NT * kSig + 2 * NS * rf::kTile1;
   uint64_t* bar_sig = &bars[warp][0];
   uint64_t* bar_rows = &bars[warp][1];
   if (lane == 0) {
@@ -182,7 +189,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   const int64_t p_begin = range_start(gw, total, nwarps), p_end = range_start(gw + 1, total, nwarps);
 
   unsigned sig_phase = 0, rows_phase = 0;
-  bool sig_by_tma = false;
+  bool sig_by_tma = false, sig_async = false;
   int off_m = 0, off_y = 0;     // float offset of a row inside its landing area (source misalignment / 4)
 
   auto frames_of = [&](int64_t b) { return meta ? meta[2 * b + 1] : frames; };
@@ -216,11 +223,63 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   const int pad = (int)pad_left;
   // start the copy of the NT frames of position q = (b, m) (TMA, or zero-filling cp.async for frames that touch
   // the zero padding at the signal's ends or are not 16-byte aligned)
+  int64_t ring_b = -1;   // RING: the position whose four hops the rings hold (or will hold once the copies land)
+  int ring_m = -2;
   auto start_signals = [&](int64_t q, int64_t b, int m) {
     if (q >= p_end) return;
     set_ctx(b);
     if (m >= ctx_M) { sig_by_tma = false; return; }
     if ((ablate & 8) && q != p_begin) { sig_by_tma = false; return; }
+    if (RING) {
+      // hops m .. m + 3 of example b must be resident; a continuation needs only hop m + 3
+      const bool cont = b == ring_b && m == ring_m + 1;
+      const int h0 = cont ? m + 3 : m, h1 = m + 4;
+      ring_b = b; ring_m = m;
+      sig_async = false;
+      {   // the steady state: one hop, inside the signal, 16-byte aligned (pad_left % 4 == 0: launcher)
+        const int s0 = h0 * kHop - pad;
+        if (cont && ctx_a16 && s0 >= 0 && s0 + kHop <= ctx_T) {
+          sig_by_tma = true;
+          if (lane == 0) {
+            float* dst = sig + ((unsigned)h0 % kRingHops) * kHop;
+            mbar_expect_tx(bar_sig, (unsigned)(NT * kHop * 4));
+#pragma unroll
+            for (int t = 0; t < NT; ++t) bulk_g2s(dst + t * kSig, ctx_row[t] + s0, kHop * 4u, bar_sig);
+          }
+          return;
+        }
+      }
+      sig_async = true;
+      int nbulk = 0;
+      for (int h = h0; h < h1; ++h) {
+        const int s0 = h * kHop - pad;
+        nbulk += (ctx_a16 && (s0 & 3) == 0 && s0 >= 0 && s0 + kHop <= ctx_T) ? 1 : 0;
+      }
+      sig_by_tma = nbulk > 0;
+      if (nbulk > 0 && lane == 0) mbar_expect_tx(bar_sig, (unsigned)(nbulk * NT * kHop * 4));
+      for (int h = h0; h < h1; ++h) {
+        const int s0 = h * kHop - pad;
+        float* dst = sig + (h % kRingHops) * kHop;
+        if (ctx_a16 && (s0 & 3) == 0 && s0 >= 0 && s0 + kHop <= ctx_T) {
+          if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) bulk_g2s(dst + t * kSig, ctx_row[t] + s0, kHop * 4u, bar_sig);
+          }
+        } else {   // hop touches the zero padding / the signal's end, or is not 16-byte aligned: zero-filling cp.async
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const float* xr = ctx_row[t];
+            for (int i = lane; i < kHop; i += 32) {
+              const int n = s0 + i;
+              const bool ok = n >= 0 && n < ctx_T;
+              fft::cp_async_4_zfill(dst + t * kSig + i, ok ? xr + n : xr, ok ? 4 : 0);
+            }
+          }
+        }
+      }
+      fft::cp_async_commit();
+      return;
+    }
     const int s0 = m * shift - pad;
     const bool a16 = ctx_a16 && (s0 & 3) == 0;
     const bool bulk = a16 && s0 >= 0 && s0 + rf::kSize <= ctx_T;
@@ -231,7 +290,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
         // before the __syncwarp() that precedes this call, and the copy's writes arrive a memory latency later)
         mbar_expect_tx(bar_sig, NT * rf::kSize * 4u);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * rf::kSize, ctx_row[t] + s0, rf::kSize * 4u, bar_sig);
+        for (int t = 0; t < NT; ++t) bulk_g2s(sig + t * kSig, ctx_row[t] + s0, rf::kSize * 4u, bar_sig);
       }
     } else {
       // just as asynchronous as the bulk copy (cp.async.wait_group before pass 1); 16-byte units when possible
@@ -242,13 +301,13 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
           for (int c = lane; c < rf::kSize / 4; c += 32) {
             const int n = s0 + 4 * c;
             const int bytes = n < 0 ? 0 : max(0, min(4, ctx_T - n)) * 4;
-            fft::cp_async_16(sig + t * rf::kSize + 4 * c, bytes ? xr + n : xr, bytes);
+            fft::cp_async_16(sig + t * kSig + 4 * c, bytes ? xr + n : xr, bytes);
           }
         } else {
           for (int i = lane; i < rf::kSize; i += 32) {
             const int n = s0 + i;
             const bool ok = n >= 0 && n < ctx_T;
-            fft::cp_async_4_zfill(sig + t * rf::kSize + i, ok ? xr + n : xr, ok ? 4 : 0);
+            fft::cp_async_4_zfill(sig + t * kSig + i, ok ? xr + n : xr, ok ? 4 : 0);
           }
         }
       }
@@ -378,10 +437,21 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     if (sig_by_tma) {
       mbar_wait(bar_sig, sig_phase);
       sig_phase ^= 1;
-    } else {
+    }
+    if (RING ? sig_async : !sig_by_tma) {   // a ring fill may mix bulk copies and zero-filling cp.async
       fft::cp_async_wait_all();
       __syncwarp();
     }
+    // RING: the hop the NEXT position adds lies outside the frame being transformed: request it now, a whole position
+    // ahead; a position that starts another utterance (or follows a skipped one) refills from the hook below
+    int hop_off[4];
+    {
+      const int base = (int)((unsigned)m % kRingHops);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hop_off[j] = (base + j >= kRingHops ? base + j - kRingHops : base + j) * kHop;
+    }
+    const bool cont_next = RING && bn == b && mn < ctx_M && q + 1 < p_end;
+    if (cont_next) start_signals(q + 1, bn, mn);
     // magnitudes as (A side, B side) pairs; slot 8 = (|DC|, |Nyquist|), zero outside lane 0; lane 0's slot 7
     // holds bin 256 on both sides: its B copy is zeroed (and so is the matching mask load)
     auto magnitudes = [&](const float2 (&ya)[8], const float2 (&yb)[8], float ydc, float ynyq, float2 (&x)[9]) {
@@ -396,8 +466,9 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
       float2 ya[2][8], yb[2][8];
       float ydc[2], ynyq[2];
       // the frames of the LAST transforms are in registers after pass 1: start the next position's copy
-      auto next_copy = [&]() { if (t + 2 >= NT) start_signals(q + 1, bn, mn); };
-      rf::rfft_streams<2, false, false>(sig + t * rf::kSize, rf::kSize, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
+      auto next_copy = [&]() { if (t + 2 >= NT && !cont_next) start_signals(q + 1, bn, mn); };
+      rf::rfft_streams<2, false, false>(sig + t * kSig, kSig, tile, k, ya, yb, ydc, ynyq, 0, next_copy,
+                                        RING ? hop_off : nullptr);
       magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
       magnitudes(ya[1], yb[1], ydc[1], ynyq[1], x[t + 1]);
     }
@@ -406,8 +477,9 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     for (int t = (NS == 2 ? (NT & ~1) : 0); t < NT; ++t) {
       float2 ya[1][8], yb[1][8];
       float ydc[1], ynyq[1];
-      auto next_copy = [&]() { if (t == NT - 1) start_signals(q + 1, bn, mn); };
-      rf::rfft_streams<1, false, false>(sig + t * rf::kSize, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
+      auto next_copy = [&]() { if (t == NT - 1 && !cont_next) start_signals(q + 1, bn, mn); };
+      rf::rfft_streams<1, false, false>(sig + t * kSig, 0, tile, k, ya, yb, ydc, ynyq, 0, next_copy,
+                                        RING ? hop_off : nullptr);
       magnitudes(ya[0], yb[0], ydc[0], ynyq[0], x[t]);
     }
     constexpr int XS = RECOMPUTE_Y ? 1 : 0;   // x[XS + j] = |STFT(s_j)|
@@ -470,13 +542,22 @@ int launch_fused_shape(const b2s_stft_plan* plan, const float* mixture, const fl
   B2S_REQUIRE(samples < ((int64_t)1 << 30) && frames < ((int64_t)1 << 20) && pad_left < ((int64_t)1 << 30),
               "signal too long for the fused STFT->PIT kernel (%lld samples)", (long long)samples);
   constexpr int nt = RECOMPUTE ? K + 1 : K;
-  constexpr size_t smem = sizeof(float) * kFusedWarps * (nt * rf::kSize + 2 * shape.ns * rf::kTile1 + row_area_floats(K));
-  static_assert(smem <= 227 * 1024, "pipeline shape exceeds the shared memory of an SM");
-  auto kernel = stft_pit_fused_kernel<K, RECOMPUTE, shape.warps, shape.ctas, shape.ns>;
-  static bool configured[64] = {};   // per device (one static per instantiation)
-  if (!configured[plan->device & 63]) {
+  // the hop ring (shift 256, opt-in with B2S_FUSED_RING=1) where its 25 % larger signal area still fits.  Measured on
+  // B200 at the north-star shape (profiles/r2_fused_ring.txt): bit-identical results, 11 % fewer shared-memory
+  // wavefronts, 26 % less L2 -> SM traffic, 6 % more instructions -- and the same 51.4 us; DRAM traffic is unchanged
+  // (139 MB: the overlapping frames of the plain copies hit L2), so it stays off by default.
+  constexpr bool kRingFits = sizeof(float) * kFusedWarps * (nt * kRingHops * kHop + 2 * shape.ns * rf::kTile1 + row_area_floats(K)) * shape.ctas
+                             + 2048 * shape.ctas <= 228 * 1024;
+  const char* re = getenv("B2S_FUSED_RING");
+  const bool ring = kRingFits && plan->shift == kHop && pad_left % 4 == 0 && re && atoi(re) != 0;
+  const size_t smem = sizeof(float) * kFusedWarps * (nt * (ring ? kRingHops * kHop : rf::kSize) + 2 * shape.ns * rf::kTile1 + row_area_floats(K));
+  B2S_REQUIRE(smem <= 227 * 1024, "internal: pipeline shape exceeds the shared memory of an SM");
+  auto kernel = ring ? stft_pit_fused_kernel<K, RECOMPUTE, shape.warps, shape.ctas, shape.ns, kRingFits>
+                     : stft_pit_fused_kernel<K, RECOMPUTE, shape.warps, shape.ctas, shape.ns, false>;
+  static bool configured[2][64] = {};   // per (ring, device) (one static per instantiation)
+  if (!configured[ring][plan->device & 63]) {
     B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[plan->device & 63] = true;
+    configured[ring][plan->device & 63] = true;
   }
   static const bool want_trace = getenv("B2S_FUSED_TRACE") != nullptr;
   unsigned long long* trace = nullptr;

@@ -266,6 +266,13 @@ B2S_HD void load_frame(const float* frame, int lane, float4* x, int count = 8) {
   for (int n2 = 0; n2 < 8; ++n2)
     if (n2 < count) x[n2] = src[32 * n2];
 }
+// The same loads from a ring of hops: the frame's four hops of 256 samples sit at float offsets hop_off[0..3] of
+// `ring` (a consecutive frame shares three of them with its predecessor: only the new hop is copied)
+B2S_HD void load_frame_ring(const float* ring, const int* hop_off, int lane, float4* x) {
+#pragma unroll
+  for (int n2 = 0; n2 < 8; ++n2)
+    x[n2] = *reinterpret_cast<const float4*>(ring + hop_off[n2 >> 1] + (n2 & 1) * 128 + 4 * lane);
+}
 // window + radix-8 over n2 of the lane's two neighbouring butterflies (x[n2] = z[2l + 64 n2], z[2l + 1 + 64 n2])
 B2S_HD void pass1_regs(const float4* x, const LaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
   float2 a[4], d[4];
@@ -533,7 +540,8 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 template <int NS, bool CONSECUTIVE, bool DOUBLE_INTERIOR, class Consts, class Hook = NoHook>
 __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, float2* tile, const Consts& consts,
                                              float2 (&ya)[NS][8], float2 (&yb)[NS][8], float (&y_dc)[NS],
-                                             float (&y_nyq)[NS], int ablate = 0, Hook input_consumed = Hook()) {
+                                             float (&y_nyq)[NS], int ablate = 0, Hook input_consumed = Hook(),
+                                             const int* hop_off = nullptr) {
   // ablate (kernel-tuning experiments only): 2 = skip the shared-memory exchanges, 4 = skip the arithmetic
   const int lane = consts.lane;
   LaneConsts k;   // fields are materialised right before the pass that uses them
@@ -556,7 +564,10 @@ __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, fl
   } else {
     float4 x[NS][8];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) load_frame(frame0 + s * stride, lane, x[s]);
+    for (int s = 0; s < NS; ++s) {
+      if (hop_off) load_frame_ring(frame0 + s * stride, hop_off, lane, x[s]);   // `stride` = floats per ring
+      else load_frame(frame0 + s * stride, lane, x[s]);
+    }
     if (!(ablate & 4)) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) pass1_regs(x[s], k, va[s], vb[s]);
