@@ -129,6 +129,12 @@ __device__ __forceinline__ void warp_search_permutations(const double* cost, int
 // from DRAM), and that hop's slot is not part of the frame being transformed: it is requested a whole position
 // ahead.  Only the first position of a range / an utterance fills four hops.
 constexpr int kHop = 256, kRingHops = 5;
+// Tuning aids (per-warp trace stamps, ablation bits) are compiled in only with -DB2S_TUNING=1 (B2S_TUNING=1 python -m
+// padertorch_b200.build --force): in the production kernel they cost ~3 % (branches inside the position loop).
+#ifndef B2S_TUNING
+#define B2S_TUNING 0
+#endif
+constexpr bool kTuning = B2S_TUNING != 0;
 template <int K, bool RECOMPUTE_Y, int WARPS, int CTAS, int NS, bool RING>
 __global__ void __launch_bounds__(32 * WARPS, CTAS)
 stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict__ yabs,
@@ -137,7 +143,9 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
                       int shift, int64_t pad_left, const float4* __restrict__ lane_table, int slots,
                       double* __restrict__ partial, int* __restrict__ counters, float* __restrict__ loss,
                       int32_t* __restrict__ perm, double* __restrict__ sse, unsigned long long* __restrict__ trace,
-                      int ablate /* tuning only: 1 no SSE, 2 no square roots, 4 no row copies, 8 no frame copies */) {
+                      int ablate_arg /* tuning only: 1 no SSE, 2 no square roots, 4 no row copies, 8 no frame copies */) {
+  const int ablate = kTuning ? ablate_arg : 0;
+  if (!kTuning) trace = nullptr;
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
   constexpr int kFusedWarps = WARPS;
