@@ -16,6 +16,7 @@ LIB = os.path.join(HERE, 'libb200sep.so')
 SOURCES = ['capi.cu', 'stft.cu', 'pit.cu', 'pairstats.cu', 'dc.cu', 'fused.cu', 'fused_bwd.cu', 'targets.cu', 'targets_fused.cu', 'gemm_umma.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+NVCC_FLAGS += os.environ.get('B2S_NVCC_EXTRA', '').split()   # A/B builds of compile-time alternatives (tools/)
 if os.environ.get('B2S_TUNING', '0') not in ('', '0'):      # per-warp trace stamps / ablation bits of the fused kernel
     NVCC_FLAGS.append('-DB2S_TUNING=1')
 

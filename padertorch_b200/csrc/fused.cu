@@ -68,8 +68,10 @@ struct FusedGrid {
 FusedGrid fused_grid(int64_t batch, int64_t frames, FusedShape shape) {
   FusedGrid g;
   g.total = batch * std::max<int64_t>(1, frames);
+  // B2S_FUSED_SMS (tuning aid): use fewer SMs -- separates per-SM limits from chip-wide contention
+  static const int sms = [] { const char* e = getenv("B2S_FUSED_SMS"); const int v = e ? atoi(e) : 0; return v > 0 && v < kNumSMs ? v : kNumSMs; }();
   g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.total, shape.warps),
-                                                       (int64_t)kNumSMs * shape.ctas));
+                                                       (int64_t)sms * shape.ctas));
   g.warps = std::min<int64_t>((int64_t)g.grid * shape.warps, g.total);   // surplus warps of the last CTA idle
   g.slots = (int)(ceil_div(std::max<int64_t>(1, frames) * g.warps, g.total) + 2);
   return g;
@@ -493,6 +495,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
     constexpr int XS = RECOMPUTE_Y ? 1 : 0;   // x[XS + j] = |STFT(s_j)|
 
     // ---- SSE of this frame: e_i = mask_i * |Y| against every source magnitude
+    // (waiting for the rows earlier -- inside the last transform, before its pass 3, so that the row loads could be
+    // scheduled into the pass-3 arithmetic -- was measured slower: 49.4 against 48.1 us, profiles/r2_fused_experiments.txt)
     if (!(ablate & 4) || q == p_begin) {
       mbar_wait(bar_rows, rows_phase);   // the rows of this frame have landed
       rows_phase ^= 1;
@@ -532,6 +536,8 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
   if (b_cur >= 0) flush(b_cur);
   stamp(5);
 }
+
+#include "fused_ws.cuh"
 
 template <int K, bool RECOMPUTE, int VARIANT>
 int launch_fused_shape(const b2s_stft_plan* plan, const float* mixture, const float* yabs, const float* sources,
@@ -674,6 +680,12 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  cudaStream_t stream) {
 #define B2S_FUSED_ARGS plan, mixture, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse, workspace, stream
   if (!yabs) return launch_fused_shape<K, true, 0>(B2S_FUSED_ARGS);
+  if constexpr (K <= 2) {   // warp-specialised kernel (fused_ws.cuh): opt-in with B2S_FUSED_WS=1 -- measured slower
+    const char* e = getenv("B2S_FUSED_WS");   // (54.2 us against 47.6 us, profiles/r2_fused_ws.txt)
+    if (e && atoi(e) != 0)
+      return launch_fused_ws<K>(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse,
+                                workspace, stream);
+  }
   if (K == 2) {   // tuning alternatives of the headline configuration (tools/hot_bench.py)
     const char* e = getenv("B2S_FUSED_VARIANT");   // read per launch: one process can sweep the shapes
     const int variant = e ? atoi(e) : 0;

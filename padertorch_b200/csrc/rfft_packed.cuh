@@ -537,11 +537,13 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 // `input_consumed()` is called (by the whole warp) once every lane holds its input samples in registers: the
 // staged frames may be overwritten from then on (a single-slot pipeline starts its next copy there).
-template <int NS, bool CONSECUTIVE, bool DOUBLE_INTERIOR, class Consts, class Hook = NoHook>
+// `before_pass3()` is called (by the whole warp) after the exchange-2 stores, i.e. when ~2/3 of the transform are done:
+// a caller waits there for operands of its epilogue, so that their loads can be scheduled into pass 3.
+template <int NS, bool CONSECUTIVE, bool DOUBLE_INTERIOR, class Consts, class Hook = NoHook, class Hook3 = NoHook>
 __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, float2* tile, const Consts& consts,
                                              float2 (&ya)[NS][8], float2 (&yb)[NS][8], float (&y_dc)[NS],
                                              float (&y_nyq)[NS], int ablate = 0, Hook input_consumed = Hook(),
-                                             const int* hop_off = nullptr) {
+                                             const int* hop_off = nullptr, Hook3 before_pass3 = Hook3()) {
   // ablate (kernel-tuning experiments only): 2 = skip the shared-memory exchanges, 4 = skip the arithmetic
   const int lane = consts.lane;
   LaneConsts k;   // fields are materialised right before the pass that uses them
@@ -599,6 +601,7 @@ __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, fl
 #pragma unroll
     for (int s = 0; s < NS; ++s) store_ex2(tile + s * kTile1, lane, va[s], vb[s]);
   }
+  before_pass3();
   __syncwarp();
   if (!(ablate & 2)) {
 #pragma unroll

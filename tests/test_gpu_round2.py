@@ -273,6 +273,41 @@ def test_fused_step_full_size_against_oracle(b2s, B, K, T):
     assert float((md.grad.cpu() - mo.grad).abs().max()) <= 1e-4 * float(mo.grad.abs().max())
 
 
+@pytest.mark.parametrize('B,K,T,ragged', [(5, 2, 16000, False), (7, 2, 24000, True), (3, 1, 9000, False),
+                                          (64, 2, 64000, False)])
+def test_warp_specialised_fused_kernel_against_oracle(b2s, B, K, T, ragged, monkeypatch):
+    """The opt-in warp-specialised form of the fused kernel (csrc/fused_ws.cuh, B2S_FUSED_WS=1: transform warps and
+    SSE warps with re-split register file) against the oracle and against the default one-role kernel: permutations
+    bit exact, losses within 1e-4; ragged batches; bit-identical reruns."""
+    from oracle import path as OP
+    y, s, rng = _step_inputs(B, K, T, 11)
+    stft = b2s.ops.STFT(1024, 256)
+    M = stft.samples_to_frames(T)
+    masks = rng.rand(B, M, K, 513).astype(np.float32)
+    lengths = [int(T - 1000 * (b % 4) - 3 * b) for b in range(B)] if ragged else None
+    yd, sd = torch.from_numpy(y).to(dev()), torch.from_numpy(s).to(dev())
+    md = torch.from_numpy(masks).to(dev())
+    y_abs = stft.magnitude(yd)
+    monkeypatch.delenv('B2S_FUSED_WS', raising=False)
+    loss0, perm0 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
+    monkeypatch.setenv('B2S_FUSED_WS', '1')
+    loss1, perm1 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
+    loss2, perm2 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
+    torch.cuda.synchronize()
+    assert torch.equal(loss1, loss2) and torch.equal(perm1, perm2)
+    np.testing.assert_array_equal(perm1.cpu().numpy(), perm0.cpu().numpy())
+    np.testing.assert_allclose(loss1.cpu().numpy(), loss0.cpu().numpy(), rtol=1e-5)
+    if B <= 8:
+        for b in range(B):
+            n = lengths[b] if ragged else T
+            m_b = stft.samples_to_frames(n)
+            want_loss, want_perm, _ = OP.stft_mask_pit_step(torch.from_numpy(y[b:b + 1, :n]),
+                                                           torch.from_numpy(s[b:b + 1, :, :n]),
+                                                           torch.from_numpy(masks[b:b + 1, :m_b]))
+            np.testing.assert_array_equal(perm1[b].cpu().numpy(), np.asarray(want_perm)[0])
+            np.testing.assert_allclose(float(loss1[b]), float(want_loss[0]), rtol=LOSS_RTOL)
+
+
 @pytest.mark.parametrize('eps', [1e-3, 1e-5])
 def test_near_tie_permutations(b2s, eps, capsys):
     """SURVEY.md section 8(d) near-tie stress: s_2 = s_1 + eps N(0, 1).  The two candidate losses then differ by
