@@ -285,6 +285,10 @@ def test_warp_specialised_fused_kernel_against_oracle(b2s, B, K, T, ragged, monk
     M = stft.samples_to_frames(T)
     masks = rng.rand(B, M, K, 513).astype(np.float32)
     lengths = [int(T - 1000 * (b % 4) - 3 * b) for b in range(B)] if ragged else None
+    if ragged:   # |Y| comes from the padded batch: the padding must be silence, as in a collated batch
+        for b, n in enumerate(lengths):
+            y[b, n:] = 0
+            s[b, :, n:] = 0
     yd, sd = torch.from_numpy(y).to(dev()), torch.from_numpy(s).to(dev())
     md = torch.from_numpy(masks).to(dev())
     y_abs = stft.magnitude(yd)
