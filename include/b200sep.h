@@ -303,12 +303,16 @@ B2S_API int b2s_mask_spectrum(const float* mask, const float* spec_mixture, int6
                       int64_t frames, int64_t bins, float* masked, b2s_stream stream);
 
 /* The same preparation straight from the waveforms, the complex spectra never leaving the registers (fast
- * plans: size 1024 / window_length 1024 / shift % 4 == 0; 1..3 sources; all examples full length):
+ * plans: size 1024 / window_length 1024 / shift % 4 == 0; 1..4 sources):
  * mixture [B, samples], sources [B, K, samples] -> y_abs [B, frames, F], x_abs / cos_phase_difference
- * [B, frames, K, F].  frames / pad_left as for b2s_stft_forward.                                      */
+ * [B, frames, K, F].  frames / pad_left as for b2s_stft_forward.
+ * meta: NULL (all examples full length) or device int64 [B][2] = {samples_b, frames_b} of a padded batch: samples
+ * beyond samples_b are never read, rows of frames >= frames_b are written as zeros (what collating the
+ * per-example results of pit/data.py:49-77 with zero padding gives).                                          */
 B2S_API int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources,
-                         int64_t batch, int64_t samples, int sources_k, int64_t frames, int64_t pad_left,
-                         float* y_abs, float* x_abs, float* cos_phase_difference, b2s_stream stream);
+                         const int64_t* meta, int64_t batch, int64_t samples, int sources_k, int64_t frames,
+                         int64_t pad_left, float* y_abs, float* x_abs, float* cos_phase_difference,
+                         b2s_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense projections of the mask networks on the tcgen05 tensor cores:

@@ -72,8 +72,8 @@ SIGNATURES = {
                                 ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_void,
                                 c_void]),
     'b2s_mask_spectrum': (c_int, [c_void, c_void, c_i64, c_int, c_i64, c_i64, c_void, c_void]),
-    'b2s_stft_pit_targets': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64, c_void, c_void,
-                                     c_void, c_void]),
+    'b2s_stft_pit_targets': (c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64, c_void,
+                                     c_void, c_void, c_void]),
     'b2s_pit_targets': (c_int, [c_void, c_void, c_i64, c_int, c_i64, c_i64, c_void, c_void, c_void, c_void]),
     'b2s_stft_pit_backward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64,
                                       c_i64, c_void, c_void, c_void, c_void]),

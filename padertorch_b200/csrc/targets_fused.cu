@@ -25,7 +25,7 @@ namespace {
 // warps per CTA: shared memory per warp (K + 1 frames, exchange tiles, 1 + 2K staged rows) grows with K; ONE CTA
 // per SM with as many warps as fit in 227 KB (7 x 31.8 KB at K = 2; two CTAs of 3 warps would leave a seventh
 // pipeline's worth of shared memory unused)
-__host__ __device__ constexpr int tgt_warps(int K) { return K <= 1 ? 8 : (K == 2 ? 7 : 5); }
+__host__ __device__ constexpr int tgt_warps(int K) { return K <= 1 ? 8 : (K == 2 ? 7 : (K == 3 ? 5 : 4)); }
 constexpr int kTgtCtasPerSm = 1;
 constexpr int F = rf::kBins;
 
@@ -47,7 +47,8 @@ __device__ __forceinline__ float2 unit_phasor(float2 y, float ay) {
 
 template <int K>
 __global__ void __launch_bounds__(32 * tgt_warps(K), kTgtCtasPerSm)
-stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__ sources, int64_t batch,
+stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__ sources,
+                    const int64_t* __restrict__ meta /* NULL or [B][2] = {samples_b, frames_b} */, int64_t batch,
                     int64_t samples, int64_t frames, int shift, int64_t pad_left,
                     const float4* __restrict__ lane_table, float* __restrict__ y_abs, float* __restrict__ x_abs,
                     float* __restrict__ cpd) {
@@ -79,16 +80,18 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
   const int64_t gw = (int64_t)blockIdx.x * kTgtWarps + warp;
   if (gw >= nwarps) return;
   const int64_t p_begin = gw * total / nwarps, p_end = (gw + 1) * total / nwarps;
-  const int T = (int)samples, pad = (int)pad_left, frames_i = (int)frames;
+  const int pad = (int)pad_left, frames_i = (int)frames;
 
   unsigned sig_phase = 0;
   bool sig_by_tma = false;
   int64_t ctx_b = -1;
+  int T = (int)samples, ctx_M = frames_i;   // of the context's example (ragged batches: meta)
   bool ctx_a16 = false;
   const float* ctx_row[NT];
   auto set_ctx = [&](int64_t b) {
     if (b == ctx_b) return;
     ctx_b = b;
+    if (meta) { T = (int)meta[2 * b]; ctx_M = (int)meta[2 * b + 1]; }
     ctx_a16 = true;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
@@ -101,6 +104,7 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
   auto start_signals = [&](bool valid, int64_t b, int m) {
     if (!valid) return;
     set_ctx(b);
+    if (m >= ctx_M) { sig_by_tma = false; return; }   // padding row of a shorter example: nothing to transform
     const int s0 = m * shift - pad;
     const bool a16 = ctx_a16 && (s0 & 3) == 0;
     const bool bulk = a16 && s0 >= 0 && s0 + rf::kSize <= T;
@@ -146,6 +150,8 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
     int64_t bn = b;
     int mn = m + 1;
     if (mn == frames_i) { mn = 0; ++bn; }
+    set_ctx(b);
+    const bool live = m < ctx_M;
     if (sig_by_tma) {
       mbar_wait(bar_sig, sig_phase);
       sig_phase ^= 1;
@@ -215,8 +221,14 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
         }
       }
     };
+    if (!live) {   // a frame beyond this example's length: the padded tensors hold zeros there (as a collated batch)
+      free_stage();
+      for (int i = lane; i < F; i += 32) sy[i] = 0.f;
+      for (int i = lane; i < K * F; i += 32) { sx[i] = 0.f; sc[i] = 0.f; }
+      start_signals(has_next, bn, mn);
+    }
 #pragma unroll
-    for (int t = 0; t + 1 < NT; t += 2) {
+    for (int t = 0; live && t + 1 < NT; t += 2) {
       float2 ya[2][8], yb[2][8];
       float ydc[2], ynyq[2];
       auto next_copy = [&]() { if (t + 2 >= NT) start_signals(has_next, bn, mn); };
@@ -224,7 +236,7 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
       emit(t, ya[0], yb[0], ydc[0], ynyq[0]);
       emit(t + 1, ya[1], yb[1], ydc[1], ynyq[1]);
     }
-    if (NT & 1) {
+    if (live && (NT & 1)) {
       float2 ya[1][8], yb[1][8];
       float ydc[1], ynyq[1];
       auto next_copy = [&]() { start_signals(has_next, bn, mn); };
@@ -250,7 +262,7 @@ stft_targets_kernel(const float* __restrict__ mixture, const float* __restrict__
 }
 
 template <int K>
-int launch_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources, int64_t batch,
+int launch_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources, const int64_t* meta, int64_t batch,
                    int64_t samples, int64_t frames, int64_t pad_left, float* y_abs, float* x_abs, float* cpd,
                    cudaStream_t stream) {
   constexpr int kTgtWarps = tgt_warps(K);
@@ -276,8 +288,8 @@ int launch_targets(const b2s_stft_plan* plan, const float* mixture, const float*
   cfg.numAttrs = 1;
   const int shift = plan->shift;
   const float4* table = plan->lane_fwd;
-  B2S_CUDA(cudaLaunchKernelEx(&cfg, stft_targets_kernel<K>, mixture, sources, batch, samples, frames, shift, pad_left,
-                              table, y_abs, x_abs, cpd));
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, stft_targets_kernel<K>, mixture, sources, meta, batch, samples, frames, shift,
+                              pad_left, table, y_abs, x_abs, cpd));
   B2S_LAUNCH_CHECK("stft_targets_kernel");
   return B2S_OK;
 }
@@ -286,14 +298,14 @@ int launch_targets(const b2s_stft_plan* plan, const float* mixture, const float*
 
 extern "C" {
 
-int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources, int64_t batch,
-                         int64_t samples, int sources_k, int64_t frames, int64_t pad_left, float* y_abs,
+int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const float* sources,
+                         const int64_t* meta, int64_t batch, int64_t samples, int sources_k, int64_t frames, int64_t pad_left, float* y_abs,
                          float* x_abs, float* cos_phase_difference, b2s_stream stream) {
   B2S_REQUIRE(plan != nullptr, "stft plan is NULL");
   B2S_REQUIRE(plan->fast && plan->wlen == fft::kSize && plan->shift <= fft::kSize && plan->shift % 4 == 0,
               "the fused target preparation exists for size 1024 / window_length 1024 / shift %% 4 == 0 plans only "
               "(got size %d, window_length %d, shift %d)", plan->size, plan->wlen, plan->shift);
-  B2S_REQUIRE(sources_k >= 1 && sources_k <= 3, "fused target preparation supports 1..3 sources (got %d)", sources_k);
+  B2S_REQUIRE(sources_k >= 1 && sources_k <= 4, "fused target preparation supports 1..4 sources (got %d)", sources_k);
   B2S_REQUIRE(batch >= 0 && samples >= 0 && frames >= 0 && pad_left >= 0, "bad extents");
   B2S_REQUIRE(samples < ((int64_t)1 << 30) && frames < ((int64_t)1 << 20) && pad_left < ((int64_t)1 << 30),
               "signal too long for the fused target preparation (%lld samples)", (long long)samples);
@@ -302,9 +314,10 @@ int b2s_stft_pit_targets(const b2s_stft_plan* plan, const float* mixture, const 
   B2S_ON_DEVICE(plan->device);
   cudaStream_t st = (cudaStream_t)stream;
   switch (sources_k) {
-    case 1: return launch_targets<1>(plan, mixture, sources, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
-    case 2: return launch_targets<2>(plan, mixture, sources, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
-    default: return launch_targets<3>(plan, mixture, sources, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
+    case 1: return launch_targets<1>(plan, mixture, sources, meta, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
+    case 2: return launch_targets<2>(plan, mixture, sources, meta, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
+    case 3: return launch_targets<3>(plan, mixture, sources, meta, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
+    default: return launch_targets<4>(plan, mixture, sources, meta, batch, samples, frames, pad_left, y_abs, x_abs, cos_phase_difference, st);
   }
 }
 

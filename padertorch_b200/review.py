@@ -237,7 +237,7 @@ def stft_mask_pit_step(mixture, sources, masks, stft=None, observation_abs=None,
                                     num_samples is not None)
 
 
-def prepare_pit_targets(mixture, sources, stft=None):
+def prepare_pit_targets(mixture, sources, stft=None, num_samples=None):
     """Batched ``pre_batch_transform`` of the PIT example on the device
     (contrib/examples/source_separation/pit/data.py:49-77): from raw waveforms
     mixture [B, T] and sources [B, K, T] to the tensors the model's review consumes,
@@ -246,6 +246,10 @@ def prepare_pit_targets(mixture, sources, stft=None):
 
     (the reference computes them per example with numpy on the data-loader workers and ships
     4 M F (1 + 2 K) bytes per utterance over PCIe instead of 4 T (1 + K)).  Forward only.
+
+    `num_samples` (one length per example of a zero-padded batch): samples beyond an example's length are not read
+    and the rows of frames beyond its own frame count are zeros -- the tensors equal the zero-padded collation of
+    the per-example results; `num_frames` is then the list of frame counts.
     """
     stft = STFT(1024, 256) if stft is None else stft
     lib = _lib.load()
@@ -257,19 +261,29 @@ def prepare_pit_targets(mixture, sources, stft=None):
     device = mixture.device
     plan = stft._plan(device)
     frames_call, pad_left = stft._frames_of_call(samples)
+    meta, num_frames = None, frames_call
+    if num_samples is not None:
+        assert len(num_samples) == batch and max(int(n) for n in num_samples) <= samples, (num_samples, samples)
+        rows = [[int(n), stft._frames_of_call(int(n))[0]] for n in num_samples]
+        num_frames = [r[1] for r in rows]
+        meta = meta_tensor(rows, device, cache_key=('targets', tuple(map(tuple, rows))))
     if (lib.b2s_stft_plan_is_fast(plan.handle) and stft.window_length == 1024 and stft.shift % 4 == 0
-            and stft.shift <= 1024 and k <= 3 and batch * frames_call > 0):
+            and stft.shift <= 1024 and k <= 4 and batch * frames_call > 0):
         # one kernel: transforms, magnitudes and phase term in registers (b2s_stft_pit_targets)
         bins = stft.size // 2 + 1
         y_abs = torch.empty((batch, frames_call, bins), dtype=torch.float32, device=device)
         x_abs = torch.empty((batch, frames_call, k, bins), dtype=torch.float32, device=device)
         cpd = torch.empty((batch, frames_call, k, bins), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
-            rc = lib.b2s_stft_pit_targets(plan.handle, _lib.ptr(mixture), _lib.ptr(sources), batch, samples, k,
-                                          frames_call, pad_left, _lib.ptr(y_abs), _lib.ptr(x_abs), _lib.ptr(cpd),
-                                          _lib.stream_of(device))
+            rc = lib.b2s_stft_pit_targets(plan.handle, _lib.ptr(mixture), _lib.ptr(sources), _lib.ptr(meta), batch,
+                                          samples, k, frames_call, pad_left, _lib.ptr(y_abs), _lib.ptr(x_abs),
+                                          _lib.ptr(cpd), _lib.stream_of(device))
         _lib.check(rc, 'b2s_stft_pit_targets')
-        return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=frames_call)
+        return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=num_frames)
+    if num_samples is not None:   # other plans: silence beyond each example's length, rows beyond its frames zeroed
+        keep = torch.arange(samples, device=device)[None, :] < torch.as_tensor(num_samples, device=device)[:, None]
+        mixture = torch.where(keep, mixture, torch.zeros_like(mixture))
+        sources = torch.where(keep[:, None, :], sources, torch.zeros_like(sources))
     spec_y = stft._spectrum(mixture, _lib.SPEC_INTERLEAVED)       # [B, M, F, 2]
     spec_x = stft._spectrum(sources, _lib.SPEC_INTERLEAVED)       # [B, K, M, F, 2]
     frames, bins = spec_y.shape[1], spec_y.shape[2]
@@ -280,6 +294,12 @@ def prepare_pit_targets(mixture, sources, stft=None):
         rc = lib.b2s_pit_targets(_lib.ptr(spec_y), _lib.ptr(spec_x), batch, k, frames, bins,
                                  _lib.ptr(y_abs), _lib.ptr(x_abs), _lib.ptr(cpd), _lib.stream_of(device))
     _lib.check(rc, 'b2s_pit_targets')
+    if num_samples is not None:
+        live = torch.arange(frames, device=device)[None, :] < torch.as_tensor(num_frames, device=device)[:, None]
+        y_abs = y_abs * live[:, :, None]
+        x_abs = x_abs * live[:, :, None, None]
+        cpd = cpd * live[:, :, None, None]
+        return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=num_frames)
     return dict(Y_abs=y_abs, X_abs=x_abs, cos_phase_difference=cpd, num_frames=frames)
 
 

@@ -488,6 +488,42 @@ def test_prepare_pit_targets(b2s, size, shift, T, K):
     assert_loss_close(got['pit_ips_loss'].cpu().numpy(), want['pit_ips_loss'].numpy())
 
 
+@pytest.mark.parametrize('size,shift,T,K', [(1024, 256, 9000, 2), (1024, 256, 7001, 4), (1024, 256, 6000, 3),
+                                           (512, 128, 3001, 2)])
+def test_prepare_pit_targets_ragged(b2s, size, shift, T, K):
+    """Ragged batches (num_samples) and K = 4 through the one-kernel target preparation (b2s_stft_pit_targets with a
+    meta table; the two-transform path for other plans): every example equals the oracle on its own length, rows of
+    frames beyond an example's frame count are zeros, and garbage beyond an example's samples is never read."""
+    from oracle import path as oracle_path
+    from oracle.stft import ReferenceSTFT
+    rng = np.random.RandomState(size + 7 * K)
+    B = 4
+    s = (0.1 * rng.randn(B, K, T)).astype(np.float32)
+    lengths = [T, T - 1234, T // 2 + 3, 2048]
+    y = s.sum(1)
+    s_dirty, y_dirty = s.copy(), y.copy()
+    for b, n in enumerate(lengths):       # NaN beyond the lengths: must not reach the outputs
+        s_dirty[b, :, n:] = np.nan
+        y_dirty[b, n:] = np.nan
+    stft = b2s.ops.STFT(size, shift)
+    out = b2s.review.prepare_pit_targets(cuda(y_dirty), cuda(s_dirty), stft=stft, num_samples=lengths)
+    ref = ReferenceSTFT(size, shift)
+    assert len(out['num_frames']) == B
+    for b, n in enumerate(lengths):
+        y_abs, x_abs, cpd = oracle_path.prepare_pit_example(torch.from_numpy(y[b, :n]).double(),
+                                                            torch.from_numpy(s[b, :, :n]).double(), ref)
+        m_b = y_abs.shape[0]
+        assert out['num_frames'][b] == m_b
+        assert_spec_close(out['Y_abs'][b, :m_b].cpu().numpy(), y_abs.numpy(), what='Y_abs')
+        assert_spec_close(out['X_abs'][b, :m_b].cpu().numpy(), x_abs.numpy(), what='X_abs')
+        got = out['cos_phase_difference'][b, :m_b].cpu().numpy()
+        strong = ((y_abs[:, None, :] > 1e-2 * y_abs.max()) & (x_abs > 1e-2 * x_abs.max().clamp_min(1e-30))).numpy()
+        np.testing.assert_allclose(got[strong], cpd.numpy()[strong], atol=2e-4)
+        for name in ('Y_abs', 'X_abs', 'cos_phase_difference'):
+            tail = out[name][b, m_b:]
+            assert tail.numel() == 0 or float(tail.abs().max()) == 0.0, name
+
+
 def test_tasnet_losses_golden(b2s, golden):
     num_samples = golden.index['models']['tasnet']['num_samples']
     s = cuda(golden('models/tasnet/s'))
