@@ -64,7 +64,11 @@ B2S_API int b2s_stft_plan_create(b2s_stft_plan** plan, int device, int size, int
 B2S_API int b2s_stft_plan_destroy(b2s_stft_plan* plan);
 /* 1 if the plan runs the register-resident warp FFT (size 1024), 0 for the table-driven DFT.    */
 B2S_API int b2s_stft_plan_is_fast(const b2s_stft_plan* plan);
-/* bytes of scratch the inverse-type calls need for (rows, frames); 0 when overlap-add is fused.  */
+/* bytes of scratch the inverse-type calls (b2s_istft_forward, b2s_stft_backward) need for (rows, frames).
+ * Fast plans with shift 256 (the ring kernel): [ticket counters | partial sums of the chunk boundaries] -- the
+ * buffer must be ZERO-FILLED ONCE before its first use; every call leaves the counters at zero, so one buffer
+ * serves all later calls of any geometry on the same stream (not two calls that run concurrently).  Other fast
+ * plans: 0.  Generic plans: the windowed frames [rows][frames][window_length], no initialisation needed.      */
 B2S_API int64_t b2s_stft_scratch_bytes(const b2s_stft_plan* plan, int64_t rows, int64_t frames);
 
 /* spectrum layouts (last axes of the output), F = size/2 + 1 */

@@ -495,7 +495,10 @@ B2S_HD int inv_pos_b(int lane, int q) { return (lane ? 64 - lane : 32) + 64 * ((
 // 2 l + e + 64 n2 and their mirrors, i.e. consecutive positions (conflict free) instead of every other one.
 B2S_HD int inv_bin_pos(int k) { return (k >> 1) + (k & 1) * 264; }
 
-// inverse split + radix-8 over n2; Y = the frame's 513 bins (re, im) in shared memory at inv_bin_pos(k)
+// inverse split + radix-8 over n2; Y = the frame's 513 bins (re, im) in shared memory at inv_bin_pos(k), or -- NATURAL
+// -- in bin order as they lie in global memory (a row landed by one bulk copy: every 8-byte load then has a lane
+// stride of 16 bytes, i.e. four instead of two wavefronts, against 17 staging copies per lane and frame)
+template <bool NATURAL = false>
 B2S_HD void inv_pass1_regs(const float2* Y, const InvLaneConsts& k, float2 (&va)[8], float2 (&vb)[8]) {
   const int lane = k.lane;
 #pragma unroll
@@ -504,7 +507,8 @@ B2S_HD void inv_pass1_regs(const float2* Y, const InvLaneConsts& k, float2 (&va)
     for (int e = 0; e < 2; ++e) {
       const int kk = 2 * lane + e + 64 * n2;
       // kk and 512 - kk have the same parity: positions lane + 32 n2 (+264) and 256 - lane - 32 n2 - e (+264)
-      float2 A = conj(Y[lane + 32 * n2 + 264 * e]), B = Y[256 - lane - 32 * n2 - e + 264 * e];
+      float2 A = conj(NATURAL ? Y[kk] : Y[lane + 32 * n2 + 264 * e]);
+      float2 B = NATURAL ? Y[kHalf - kk] : Y[256 - lane - 32 * n2 - e + 264 * e];
       if (n2 == 0 && e == 0 && lane == 0) { A.y = 0.f; B.y = 0.f; }
       const float2 s = add2(A, B), d = sub2(A, B);
       float2 u = add2(s, cmul(d, k.tin[2 * n2 + e]));
@@ -630,12 +634,13 @@ __device__ __forceinline__ void rfft_streams(const float* frame0, int stride, fl
 // NS inverse transforms per warp.  `tile` = NS regions of kTile1 float2; on entry region s holds the 513 bins of
 // stream s (it becomes the exchange buffer once every lane has its inputs); on return a[s][p] / b[s][q] are the
 // windowed sample pairs of positions lane + 64 p / inv_pos_b(lane, q).
-template <int NS>
+// NATURAL: the spectrum of stream s starts at tile + s * kTile1 + spec_off[s] in bin order (see inv_pass1_regs).
+template <int NS, bool NATURAL = false>
 __device__ __forceinline__ void irfft_streams(float2* tile, const InvLaneConsts& k, float2 (&a)[NS][8],
-                                              float2 (&b)[NS][8]) {
+                                              float2 (&b)[NS][8], const int* spec_off = nullptr) {
   const int lane = k.lane;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) inv_pass1_regs(tile + s * kTile1, k, a[s], b[s]);
+  for (int s = 0; s < NS; ++s) inv_pass1_regs<NATURAL>(tile + s * kTile1 + (NATURAL ? spec_off[s] : 0), k, a[s], b[s]);
   __syncwarp();   // every lane holds its bins: the regions become exchange buffers
 #pragma unroll
   for (int s = 0; s < NS; ++s) store_ex1(tile + s * kTile1, lane, a[s], b[s]);

@@ -396,8 +396,12 @@ __host__ __device__ constexpr int inv_slots(int ns) { return ns == 1 ? 16 : 24; 
 template <int LAYOUT>
 __device__ __forceinline__ void stage_spectrum(float2* slot, const float* __restrict__ spec, int64_t fr, int lane) {
   if (LAYOUT == B2S_SPEC_INTERLEAVED) {
-    const float2* src = reinterpret_cast<const float2*>(spec) + fr * rf::kBins;
-    for (int c = lane; c < rf::kBins; c += 32) fft::cp_async_8(slot + rf::inv_bin_pos(c), src + c);
+    // bin lane + 32 i lands at inv_bin_pos(lane) + 16 i: one base per side and immediates (16 copies + bin 512 from lane 0)
+    const float2* src = reinterpret_cast<const float2*>(spec) + fr * rf::kBins + lane;
+    float2* dst = slot + rf::inv_bin_pos(lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fft::cp_async_8(dst + 16 * i, src + 32 * i);
+    if (lane == 0) fft::cp_async_8(dst + 256, src + 512);
   } else {   // 'concat': a row of real parts, then a row of imaginary parts
     const float* re = spec + fr * 2 * rf::kBins;
     float* dst = reinterpret_cast<float*>(slot);
@@ -505,6 +509,235 @@ istft1024_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, i
         orow[n] = acc;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- ring inverse
+// Halo-free overlap-add for shift 256 (four hops per frame): every row is cut into chunks of consecutive frames
+// (at least four), one chunk = one unit of a persistent grid of independent WARPS.  A warp walks its chunk NS
+// frames at a time: the spectra of the next step travel into the other half of its double buffer (cp.async)
+// while rf::irfft_streams transforms the current ones in place.  The overlap-add never touches shared memory: a
+// lane's windowed samples fall on the SAME four 8-byte positions of whichever hop they belong to (a side: sample
+// pairs lane and 64 + lane of the hop, b side: 64 - lane and 128 - lane), so the sums of the hops in flight live
+// in registers (a shift register of 3 + NS hops x 4 float2), contributions arrive in increasing frame order (the
+// sums equal the sequential overlap-add), and a completed hop leaves as four warp-wide contiguous 256-byte stores.
+// No block barrier, no frame is transformed twice.  The three hops on either side of a chunk boundary receive
+// contributions from both neighbours: each side writes its partial sums to the workspace and takes a ticket;
+// whoever comes second adds the two (a + b is commutative: the result does not depend on who that is) and writes
+// the output -- nobody waits.
+// workspace = [kMaxTickets ints, zero between calls][boundaries][2 sides][3 hops][4][32 lanes] float2.
+constexpr int kRingHop = 256, kRingWarps = 4;
+__host__ __device__ constexpr int ring_ctas(int ns) { return ns == 1 ? 3 : 2; }
+__host__ __device__ constexpr int ring_warp_floats(int ns) { return 2 * ns * 2 * rf::kTile1; }   // double-buffered spectra
+constexpr int kBoundaryFloats = 2 * 3 * kRingHop;
+struct RingGeometry { int64_t chunks_per_row, units, boundaries; int grid; };
+RingGeometry ring_geometry(int64_t rows, int64_t frames, int ns) {
+  RingGeometry g;
+  const int64_t warps = (int64_t)kNumSMs * ring_ctas(ns) * kRingWarps;
+  g.chunks_per_row = std::max<int64_t>(1, std::min<int64_t>(warps / std::max<int64_t>(1, rows), frames / 4));
+  g.units = rows * g.chunks_per_row;
+  g.boundaries = rows * (g.chunks_per_row - 1);
+  g.grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(g.units, kRingWarps), (int64_t)kNumSMs * ring_ctas(ns)));
+  return g;
+}
+
+template <int LAYOUT, int NS>
+__global__ void __launch_bounds__(32 * kRingWarps, ring_ctas(NS))
+istft_ring_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int64_t chunks_per_row,
+                  int64_t crop_left, int64_t samples_out, const float4* __restrict__ lane_table,
+                  float interior_in_scale, float* __restrict__ out, int* __restrict__ tickets,
+                  float* __restrict__ partials) {
+  extern __shared__ __align__(16) float ring_smem[];
+  __shared__ __align__(8) uint64_t ring_bars[kRingWarps][2];
+  // interleaved complex rows (4104 contiguous bytes, 8-byte aligned) travel by ONE bulk copy each and are read in bin
+  // order; 'concat' rows are staged bin by bin with cp.async
+  constexpr bool kBulk = LAYOUT == B2S_SPEC_INTERLEAVED;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* bufs = reinterpret_cast<float2*>(ring_smem + warp * ring_warp_floats(NS));   // [2][NS][kTile1]
+  if (kBulk && lane == 0) {
+    tma::mbar_init(&ring_bars[warp][0], 1);
+    tma::mbar_init(&ring_bars[warp][1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+  unsigned phase_bits = 0;   // bit `which`: parity the next wait on that buffer's barrier expects
+  unsigned off_bits = 0;     // bit which * NS + s: float2 offset (0 or 1) of bin 0 inside its landing region
+  rf::InvLaneConsts k;
+  k.load(lane_table, lane, interior_in_scale);
+  const int64_t units = rows * chunks_per_row;
+  const int64_t nwarps = (int64_t)gridDim.x * kRingWarps;
+  const int64_t total_hops = (crop_left + samples_out + kRingHop - 1) / kRingHop;   // hops that can receive output
+  // sample-pair positions of a lane inside a hop: v[0] lane, v[1] 64 + lane, v[2] 64 - lane (lane 0: 32), v[3] 64 + that
+  const int qb = lane ? 64 - lane : 32;
+  auto store_hop = [&](float* orow, int64_t h, const float2 (&v)[4]) {
+    if (h >= total_hops) return;
+    const int64_t n0 = h * kRingHop - crop_left;
+    if (n0 >= 0 && n0 + kRingHop <= samples_out) {   // warp-uniform: the whole hop lies inside the output row
+      float2* o = reinterpret_cast<float2*>(orow + n0);
+      o[lane] = v[0];
+      o[64 + lane] = v[1];
+      o[qb] = v[2];
+      o[64 + qb] = v[3];
+      return;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t n = n0 + 2 * ((q & 1) * 64 + (q < 2 ? lane : qb));
+      if (n >= 0 && n < samples_out) orow[n] = v[q].x;
+      if (n + 1 >= 0 && n + 1 < samples_out) orow[n + 1] = v[q].y;
+    }
+  };
+  auto park_hop = [&](int64_t bid, int side, int j, const float2 (&v)[4]) {
+    float2* dst = reinterpret_cast<float2*>(partials + bid * kBoundaryFloats) + ((side * 3 + j) * 4) * 32 + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * 32] = v[q];
+  };
+  // Publish the parked boundary hops of a chunk -- its leading ones (boundary bid_lead, if any) and its trailing ones
+  // (bid_trail, if any) -- with ONE fence and one round of tickets (lanes 0 and 1), then combine wherever the
+  // neighbour was first.
+  auto publish = [&](bool lead, bool trail, int64_t bid_lead, int64_t bid_trail, int64_t row, int64_t f0, int64_t f1) {
+    if (!lead && !trail) return;
+    __threadfence();
+    __syncwarp();
+    int old = 0;
+    if (lane == 0 && lead) old = atomicAdd(tickets + bid_lead, 1);
+    if (lane == 1 && trail) old = atomicAdd(tickets + bid_trail, 1);
+    const int old_lead = __shfl_sync(0xffffffffu, old, 0), old_trail = __shfl_sync(0xffffffffu, old, 1);
+    const bool second_lead = lead && old_lead == 1, second_trail = trail && old_trail == 1;
+    if (!second_lead && !second_trail) return;   // warp-uniform
+    __threadfence();
+    float* orow = out + row * samples_out;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (!(w == 0 ? second_lead : second_trail)) continue;
+      const int64_t bid = w == 0 ? bid_lead : bid_trail, h_first = w == 0 ? f0 : f1;
+      const float2* e = reinterpret_cast<const float2*>(partials + bid * kBoundaryFloats) + lane;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float2 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = __ldcg(e + (j * 4 + q) * 32), b = __ldcg(e + ((3 + j) * 4 + q) * 32);
+          v[q] = make_float2(a.x + b.x, a.y + b.y);
+        }
+        store_hop(orow, h_first + j, v);
+      }
+      if (lane == 0) tickets[bid] = 0;
+    }
+  };
+  for (int64_t u = (int64_t)blockIdx.x * kRingWarps + warp; u < units; u += nwarps) {
+    const int64_t row = u / chunks_per_row, c = u - row * chunks_per_row;
+    const int64_t f0 = frames * c / chunks_per_row, f1 = frames * (c + 1) / chunks_per_row;
+    float* orow = out + row * samples_out;
+    const bool lead_partial = f0 > 0, trail_partial = f1 < frames;
+    const int64_t bid_lead = row * (chunks_per_row - 1) + (c - 1), bid_trail = bid_lead + 1;
+    auto stage_step = [&](int which, int64_t m) {
+      if (kBulk) {
+        unsigned bytes[NS], total = 0;
+        uintptr_t from[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const uintptr_t addr = reinterpret_cast<uintptr_t>(spec) + (uintptr_t)(row * frames + m + s) * (rf::kBins * 8);
+          off_bits = (off_bits & ~(1u << (which * NS + s))) | ((unsigned)((addr >> 3) & 1) << (which * NS + s));
+          from[s] = addr & ~(uintptr_t)15;
+          bytes[s] = m + s < f1 ? (unsigned)(((addr & 15) + rf::kBins * 8 + 15) & ~15u) : 0u;
+          total += bytes[s];
+        }
+        if (lane == 0) {
+          // the region was the exchange buffer of the transform before last (generic-proxy stores and loads, all
+          // finished before the __syncwarp() that ended it): order them before the copy's async-proxy writes
+          tma::fence_proxy_async();
+          tma::mbar_expect_tx(&ring_bars[warp][which], total);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            if (bytes[s]) tma::bulk_g2s(bufs + (which * NS + s) * rf::kTile1, reinterpret_cast<const void*>(from[s]), bytes[s], &ring_bars[warp][which]);
+        }
+        return;
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (m + s < f1) stage_spectrum<LAYOUT>(bufs + (which * NS + s) * rf::kTile1, spec, row * frames + m + s, lane);
+      fft::cp_async_commit();
+    };
+    stage_step(0, f0);
+    float2 acc[3 + NS][4];   // hop m + t of the current step; slots 0..2 carry sums of earlier frames
+#pragma unroll
+    for (int t = 0; t < 3 + NS; ++t)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[t][q] = make_float2(0.f, 0.f);
+    int which = 0;
+    for (int64_t m = f0; m < f1; m += NS, which ^= 1) {
+      const bool more = m + NS < f1;
+      if (more) stage_step(which ^ 1, m + NS);
+      if (kBulk) {
+        tma::mbar_wait(&ring_bars[warp][which], (phase_bits >> which) & 1u);
+        phase_bits ^= 1u << which;
+      } else {
+        if (more) fft::cp_async_wait_group<1>(); else fft::cp_async_wait_group<0>();
+        __syncwarp();
+      }
+      float2 a[NS][8], b[NS][8];
+      int spec_off[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) spec_off[s] = (int)((off_bits >> (which * NS + s)) & 1u);
+      if (NS == 2 && m + 1 >= f1) {   // warp-uniform: an odd chunk's last frame is transformed alone (60 % of a pair's time)
+        float2 a1[1][8], b1[1][8];
+        rf::irfft_streams<1, kBulk>(bufs + which * NS * rf::kTile1, k, a1, b1, spec_off);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) { a[0][p] = a1[0][p]; b[0][p] = b1[0][p]; }
+      } else {
+        rf::irfft_streams<NS, kBulk>(bufs + which * NS * rf::kTile1, k, a, b, spec_off);
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (m + s < f1) {   // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // hop j of the frame: a-side pairs 2 j, 2 j + 1; b-side slots whose r = (p + 7) & 7 is 2 j, 2 j + 1
+            const float2 c0 = a[s][2 * j], c1 = a[s][2 * j + 1], c2 = b[s][(2 * j + 1) & 7], c3 = b[s][(2 * j + 2) & 7];
+            float2 (&dst)[4] = acc[s + j];
+            if (j == 3) { dst[0] = c0; dst[1] = c1; dst[2] = c2; dst[3] = c3; }   // first contribution to that hop
+            else { dst[0] = rf::add2(dst[0], c0); dst[1] = rf::add2(dst[1], c1); dst[2] = rf::add2(dst[2], c2); dst[3] = rf::add2(dst[3], c3); }
+          }
+        }
+      }
+      // hops m .. m + NS - 1 are complete as far as this chunk is concerned
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int64_t h = m + s;
+        if (h < f1) {
+          if (lead_partial && h < f0 + 3) {
+            park_hop(bid_lead, 1, (int)(h - f0), acc[s]);   // published together with the trailing hops
+          } else {
+            store_hop(orow, h, acc[s]);
+          }
+        }
+      }
+      if (m + NS <= f1) {   // shift the register ring by NS hops (a short last step keeps its slots: see below)
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[t][q] = acc[t + NS][q];
+      }
+    }
+    // the three hops after the last frame: slots 0..2 after a full last step, slots 1..3 after a short one (NS = 2, odd count)
+    const bool short_last = NS == 2 && ((f1 - f0) & 1);
+    float2 tail[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tail[j][q] = short_last ? acc[(j + 1) % (3 + NS)][q] : acc[j][q];
+    if (trail_partial) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) park_hop(bid_trail, 0, j, tail[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) store_hop(orow, f1 + j, tail[j]);
+      // positions no frame reaches (a requested length beyond the frames' support) are zeros
+      const float2 z[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      for (int64_t h = f1 + 3; h < total_hops; ++h) store_hop(orow, h, z);
+    }
+    publish(lead_partial, trail_partial, bid_lead, bid_trail, row, f0, f1);
   }
 }
 
@@ -682,6 +915,17 @@ bool fused_inverse_ok(const b2s_stft_plan* plan) {
   return plan->fast && overlap <= 8;   // hops = slots - overlap + 1 >= 9
 }
 
+// the ring kernel: shift 256 (four hops per zero-extended frame) and 16-byte stores of whole hop quarters
+bool ring_inverse_ok(const b2s_stft_plan* plan, int64_t crop_left, int64_t samples_out, const float* out) {
+  return plan->fast && plan->shift == kRingHop && (crop_left & 3) == 0 && (samples_out & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+int64_t ring_workspace_bytes(int64_t rows, int64_t frames) {
+  int64_t most = 0;
+  for (int ns = 1; ns <= 2; ++ns) most = std::max(most, ring_geometry(rows, frames, ns).boundaries);
+  return kTicketBytes + most * (int64_t)sizeof(float) * kBoundaryFloats;
+}
+
 // inverse-type launch shared by b2s_istft_forward and b2s_stft_backward
 int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, int64_t frames,
                    int layout, int64_t crop_left, int64_t samples_out, const float* win,
@@ -692,7 +936,30 @@ int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, i
     B2S_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * rows * samples_out, stream));
     return B2S_OK;
   }
-  if (fused_inverse_ok(plan)) {
+  // B2S_INV_RING: 0 = chunked kernel with halo frames, 1 / 2 = ring kernel with one / two frames per step (default 2)
+  const int ring_ns = [] { const char* e = getenv("B2S_INV_RING"); const int v = e ? atoi(e) : 2; return v < 0 || v > 2 ? 2 : v; }();   // per call: tests switch it
+  if (fused_inverse_ok(plan) && ring_ns > 0 && ring_inverse_ok(plan, crop_left, samples_out, out) && scratch) {
+    B2S_REQUIRE((reinterpret_cast<uintptr_t>(spec) & 7) == 0, "spectrum pointer must be 8-byte aligned");
+    const RingGeometry g = ring_geometry(rows, frames, ring_ns);
+    B2S_REQUIRE(g.boundaries <= kMaxTickets, "too many rows for the inverse transform's workspace");
+    const size_t smem = sizeof(float) * kRingWarps * ring_warp_floats(ring_ns);
+    const int variant = (layout == B2S_SPEC_INTERLEAVED ? 0 : 1) + (ring_ns == 2 ? 2 : 0);
+    auto kernel = ring_ns == 2
+        ? (layout == B2S_SPEC_INTERLEAVED ? istft_ring_kernel<B2S_SPEC_INTERLEAVED, 2> : istft_ring_kernel<B2S_SPEC_CONCAT, 2>)
+        : (layout == B2S_SPEC_INTERLEAVED ? istft_ring_kernel<B2S_SPEC_INTERLEAVED, 1> : istft_ring_kernel<B2S_SPEC_CONCAT, 1>);
+    static bool configured[4][64] = {};
+    if (!configured[variant][plan->device & 63]) {
+      B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[variant][plan->device & 63] = true;
+    }
+    const bool adjoint = interior_scale == 1.f;
+    B2S_REQUIRE(win == (adjoint ? plan->awin : plan->swin), "internal: window / table mismatch");
+    int* tickets = reinterpret_cast<int*>(scratch);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + kTicketBytes);
+    kernel<<<g.grid, 32 * kRingWarps, smem, stream>>>(spec, rows, frames, g.chunks_per_row, crop_left, samples_out,
+        adjoint ? plan->lane_inv_ana : plan->lane_inv_syn, 0.5f * interior_scale, out, tickets, partials);
+    B2S_LAUNCH_CHECK("istft_ring_kernel");
+  } else if (fused_inverse_ok(plan)) {
     B2S_REQUIRE((reinterpret_cast<uintptr_t>(spec) & 7) == 0, "spectrum pointer must be 8-byte aligned");
     static const int ns = [] { const char* e = getenv("B2S_INV_NS"); return e && atoi(e) == 2 ? 2 : 1; }();
     const int overlap = (plan->wlen + plan->shift - 1) / plan->shift;
@@ -840,7 +1107,8 @@ int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
 int b2s_stft_plan_is_fast(const b2s_stft_plan* plan) { return plan && plan->fast; }
 
 int64_t b2s_stft_scratch_bytes(const b2s_stft_plan* plan, int64_t rows, int64_t frames) {
-  if (!plan || fused_inverse_ok(plan)) return 0;
+  if (!plan) return 0;
+  if (fused_inverse_ok(plan)) return plan->shift == kRingHop ? ring_workspace_bytes(rows, frames) : 0;
   return (int64_t)sizeof(float) * rows * frames * plan->wlen;
 }
 

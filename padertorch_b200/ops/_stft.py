@@ -11,6 +11,8 @@ from math import ceil
 import numpy as np
 import torch
 
+from .._workspace import workspace
+
 from .. import _lib
 
 _LEGAL_FADING = [None, True, False, 'full', 'half']
@@ -162,9 +164,14 @@ class _ISTFTForward(torch.autograd.Function):
 
 
 def _scratch(plan, rows, frames, device):
-    nbytes = _lib.load().b2s_stft_scratch_bytes(plan.handle, rows, frames)
+    lib = _lib.load()
+    nbytes = lib.b2s_stft_scratch_bytes(plan.handle, rows, frames)
     if nbytes == 0:
         return None
+    if lib.b2s_stft_plan_is_fast(plan.handle):
+        # the ring inverse keeps ticket counters in its workspace: zero-filled once per (device, stream), every call
+        # leaves them at zero (include/b200sep.h)
+        return workspace(device, nbytes, 'stft-inverse')
     return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
 
 

@@ -508,3 +508,39 @@ def test_tcgen05_linear_autograd_and_chaining(b2s):
     m = b2s.ops.FusedLinear(1200, 600, activation='relu').to(dev())
     torch.testing.assert_close(m(x.detach()), torch.relu(torch.nn.functional.linear(x.detach(), m.weight, m.bias)),
                                rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('rows,T', [(1, 256), (1, 700), (2, 1024), (3, 5000), (5, 17001), (130, 9000), (1300, 2100),
+                                    (64, 64000)])
+@pytest.mark.parametrize('layout', ['complex', 'concat'])
+def test_ring_inverse_against_chunked_kernel_and_oracle(b2s, rows, T, layout, monkeypatch):
+    """The halo-free ring inverse (istft_ring_kernel: per-warp chunks, register overlap-add, ticketed chunk boundaries)
+    against the chunked kernel it replaces (B2S_INV_RING=0) and against the oracle's iSTFT; also as the adjoint of the
+    STFT (autograd of the forward transform).  Rows beyond the warp count (several units per warp), rows with fewer
+    than four frames (one chunk), odd chunk lengths, both spectrum layouts; bit-identical reruns."""
+    from oracle.stft import ReferenceSTFT
+    torch.manual_seed(rows + T)
+    stft = b2s.ops.STFT(1024, 256, complex_representation=layout)
+    x = 0.1 * torch.randn(rows, T, device=dev())
+    xr = x.clone().requires_grad_(True)
+    spec = stft(xr)
+    g = torch.randn_like(spec) if not spec.is_complex() else torch.randn_like(torch.view_as_real(spec))
+    monkeypatch.setenv('B2S_INV_RING', '2')
+    z1 = stft.inverse(spec.detach())
+    z1b = stft.inverse(spec.detach())
+    (grad1,) = torch.autograd.grad(spec if not spec.is_complex() else torch.view_as_real(spec), xr, g, retain_graph=True)
+    monkeypatch.setenv('B2S_INV_RING', '1')
+    z2 = stft.inverse(spec.detach())
+    monkeypatch.setenv('B2S_INV_RING', '0')
+    z0 = stft.inverse(spec.detach())
+    (grad0,) = torch.autograd.grad(spec if not spec.is_complex() else torch.view_as_real(spec), xr, g)
+    torch.cuda.synchronize()
+    assert torch.equal(z1, z1b)
+    scale = float(z0.abs().max())
+    assert float((z1 - z0).abs().max()) <= 2e-6 * scale and float((z2 - z0).abs().max()) <= 2e-6 * scale
+    assert float((grad1 - grad0).abs().max()) <= 2e-6 * float(grad0.abs().max())
+    assert float((z1[..., :T] - x).abs().max()) <= 1e-4 * float(x.abs().max())     # round trip
+    if rows <= 5:
+        ref = ReferenceSTFT(1024, 256, complex_representation=layout)
+        want = ref.inverse(spec.detach().cpu())
+        assert float((z1.cpu() - want).abs().max()) <= 1e-4 * float(want.abs().max())

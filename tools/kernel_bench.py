@@ -90,8 +90,8 @@ def main():
     def stft_bwd(i):
         out = torch.empty(B, T, device=dev)
         def run():
-            rc = _lib.load().b2s_stft_backward(plan.handle, gspec[i].data_ptr(), B, M, 0, 768, T, out.data_ptr(), None,
-                                               _lib.stream_of(dev))
+            rc = _lib.load().b2s_stft_backward(plan.handle, gspec[i].data_ptr(), B, M, 0, 768, T, out.data_ptr(),
+                                               _lib.ptr(S._scratch(plan, B, M, dev)), _lib.stream_of(dev))
             assert rc == 0
         return run
     record('stft backward (adjoint)', time_graph(stft_bwd, n), B * (4 * T + 8 * M * F))
