@@ -38,7 +38,8 @@ if ROOT not in sys.path:
 
 # NCCL reads its environment when the library is loaded (import torch): ask for the INFO log (ranks, rings / trees /
 # NVLS) before that; main() points file descriptor 1 at stderr, so the log never mixes with the JSON line on stdout
-os.environ.setdefault('NCCL_DEBUG', os.environ.get('B2S_NCCL_DEBUG', 'INFO'))
+# (the GPU boxes export NCCL_DEBUG=VERSION: override it, B2S_NCCL_DEBUG selects another level)
+os.environ['NCCL_DEBUG'] = os.environ.get('B2S_NCCL_DEBUG', 'INFO')
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -514,6 +515,37 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
+    # The headline path has no data-path collective (utterances are independent).  What a data-parallel TRAINING step on
+    # it exchanges is the mask network's gradient: measured here, outside every timed region, as the bucketed sum
+    # all-reduce of the PIT BLSTM model's 101.3 MB of gradients (padertorch_b200.parallel's exchange; --config train
+    # measures it inside a real training step).
+    probe = None
+    if distributed:
+        nbytes, bucket = 101298508, 32 << 20
+        flat = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+        chunks = list(flat.split(bucket // 4))
+        for _ in range(3):
+            for c in chunks:
+                dist.all_reduce(c)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            for c in chunks:
+                dist.all_reduce(c)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        probe = {'op': 'all_reduce(sum), fp32, 32 MiB buckets', 'bytes': nbytes, 'ranks': world, 'ms': ms,
+                 'algbw_gbs': nbytes / (ms * 1e-3) / 1e9, 'busbw_gbs': nbytes / (ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+                 'note': 'gradient exchange of the PIT BLSTM mask estimator (25.3 M parameters); device-timed, max over '
+                         'ranks, outside the timed region of `value` and `e2e`'}
+        del flat, chunks
+
     if rank == 0:
         peak, peak_kind = measured_peaks()
         ms_per_step = elapsed_ms / args.steps
@@ -556,6 +588,8 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(traffic_file):
             with open(traffic_file) as fd:
                 line['roofline']['traffic'] = json.load(fd).get('stft_pit_fused_kernel')
+        if probe is not None:
+            line['collective_probe'] = probe
         emit(line)
     if distributed:
         dist.destroy_process_group()
