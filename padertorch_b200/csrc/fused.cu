@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "fft1024.cuh"
 #include "rfft_packed.cuh"
+#include "cfft_pair.cuh"
 #include "tma.cuh"
 #include "stft_plan.cuh"
 #include "perm.cuh"
@@ -538,6 +539,7 @@ stft_pit_fused_kernel(const float* __restrict__ mixture, const float* __restrict
 }
 
 #include "fused_ws.cuh"
+#include "fused_pair.cuh"
 
 template <int K, bool RECOMPUTE, int VARIANT>
 int launch_fused_shape(const b2s_stft_plan* plan, const float* mixture, const float* yabs, const float* sources,
@@ -680,6 +682,13 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
                  cudaStream_t stream) {
 #define B2S_FUSED_ARGS plan, mixture, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse, workspace, stream
   if (!yabs) return launch_fused_shape<K, true, 0>(B2S_FUSED_ARGS);
+  if constexpr (K == 2) {   // two sources: the pair-transform kernel (fused_pair.cuh); B2S_FUSED_PAIR=0 = the 8 x 8 x 8 pipeline
+    const char* e = getenv("B2S_FUSED_PAIR");
+    const char* w = getenv("B2S_FUSED_WS");
+    if (!(e && atoi(e) == 0) && !getenv("B2S_FUSED_VARIANT") && !(w && atoi(w) != 0) && !getenv("B2S_FUSED_RING"))
+      return launch_fused_pair(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse,
+                               workspace, stream);
+  }
   if constexpr (K <= 2) {   // warp-specialised kernel (fused_ws.cuh): opt-in with B2S_FUSED_WS=1 -- measured slower
     const char* e = getenv("B2S_FUSED_WS");   // (54.2 us against 47.6 us, profiles/r2_fused_ws.txt)
     if (e && atoi(e) != 0)

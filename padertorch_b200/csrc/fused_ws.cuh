@@ -5,7 +5,9 @@
 // north-star shape (profiles/r2_fused_experiments.txt): the magnitudes cross shared memory (76 more wavefronts per
 // position on a pipe that is already ~70 % busy), which costs more than the serial SSE it removes from the transform
 // warps.  Kept as the measured record of that design (parity-green: tests/test_gpu_round2.py) and as the working
-// example of register-file re-splitting with setmaxnreg.
+// example of register-file re-splitting with setmaxnreg.  compute-sanitizer: memcheck clean; racecheck reports two
+// WARNINGS for this kernel only (frame-buffer refill against the same warp's pass-1 loads -- the sequence the tool
+// accepts in the one-role kernels, profiles/r2_sanitizer.txt).
 //
 // Idea: the one-role pipeline of stft_pit_fused_kernel executes transform, magnitudes, row copies, K x K SSE and the
 // example bookkeeping serially in every warp, at two resident warps per SM sub-partition (240 registers).  Without the

@@ -1,4 +1,4 @@
-// Host emulation of tools/prototypes/cfft_pair.cuh: two real frames through one 1024-point complex FFT, the 32
+// Host emulation of padertorch_b200/csrc/cfft_pair.cuh: two real frames through one 1024-point complex FFT, the 32
 // lanes of a warp run pass by pass on the CPU (shared memory = a plain array, the mirror shuffle = an array
 // lookup); both spectra are compared with a double-precision DFT.  Prints "max_rel_err <value>".
 #include <cmath>
@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../../tools/prototypes/cfft_pair.cuh"
+#include "../../padertorch_b200/csrc/cfft_pair.cuh"
 
 using namespace b2s::cp;
 
@@ -42,7 +42,7 @@ int main() {
         const int bin = l + 32 * r;
         are[bin] = sa[r].x; aim[bin] = sa[r].y; bre[bin] = sb[r].x; bim[bin] = sb[r].y;
       }
-      if (l == 0) { are[512] = z[0][16].x; aim[512] = 0; bre[512] = z[0][16].y; bim[512] = 0; }
+      if (l == 0) { are[512] = 2 * z[0][16].x; aim[512] = 0; bre[512] = 2 * z[0][16].y; bim[512] = 0; }   // (window halved)
     }
     double maxref = 0.0, maxerr = 0.0;
     for (int f = 0; f <= 512; ++f) {

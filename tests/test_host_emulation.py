@@ -31,7 +31,7 @@ def test_packed_rfft_host_emulation(tmp_path):
 
 @pytest.mark.skipif(shutil.which('g++') is None or _cuda_include() is None, reason='needs g++ and the CUDA headers')
 def test_pair_transform_prototype_host_emulation(tmp_path):
-    """tools/prototypes/cfft_pair.cuh (two real frames per 1024-point complex FFT, one exchange): both spectra
+    """csrc/cfft_pair.cuh (two real frames per 1024-point complex FFT, one exchange): both spectra
     against a double-precision DFT, lane by lane on the CPU."""
     exe = tmp_path / 'cfft_pair_emulate'
     subprocess.run(['g++', '-O1', '-std=c++17', '-I', _cuda_include(), '-o', str(exe),

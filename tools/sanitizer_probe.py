@@ -43,3 +43,34 @@ out = b2s.review.tasnet_losses(est, s, [4001, 3000, 4001])
 prep = b2s.review.prepare_pit_targets(s.sum(1), s, stft=stft)
 torch.cuda.synchronize()
 print('ok losses', float(out['si-sdr']), prep['X_abs'].shape)
+
+# ---- round 2: pair-transform fused kernel (default, K = 2), 8 x 8 x 8 pipeline and warp-specialised form (opt-in), fused
+# backward, ragged batches; ring inverse with several chunks per row, chunk boundaries, both layouts; ragged targets, K = 4
+import os
+B, K, T = 5, 2, 20000
+s = (0.1 * rng.randn(B, K, T)).astype(np.float32); y = s.sum(1)
+M = stft.samples_to_frames(T)
+lengths = [T, T - 999, T // 2, 4096, T - 4]
+yd, sd = torch.from_numpy(y).to(dev), torch.from_numpy(s).to(dev)
+ya = stft.magnitude(yd)
+ref = None
+for env in ({}, {'B2S_FUSED_PAIR': '0'}, {'B2S_FUSED_WS': '1'}):
+    os.environ.update(env)
+    md = torch.rand(B, M, K, 513, device=dev, requires_grad=True)
+    for ns in (None, lengths):
+        loss, perm = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=ya, num_samples=ns)
+        loss.sum().backward()
+    for k in env:
+        os.environ.pop(k)
+torch.cuda.synchronize()
+for rows, T2 in ((3, 5000), (70, 9000), (1300, 1500)):
+    for rep in ('complex', 'concat'):
+        st = b2s.ops.STFT(1024, 256, complex_representation=rep)
+        x = (0.1 * torch.randn(rows, T2, device=dev)).requires_grad_(True)
+        spec = st(x)
+        z = st.inverse(spec)
+        z.sum().backward()
+prep = b2s.review.prepare_pit_targets(torch.randn(3, 7001, device=dev), torch.randn(3, 4, 7001, device=dev), stft=stft,
+                                      num_samples=[7001, 5000, 2048])
+torch.cuda.synchronize()
+print('ok round 2', float(loss.sum()), float(z.abs().max()), prep['X_abs'].shape)

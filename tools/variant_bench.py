@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--fused', default='0,1,2,3,4')
     ap.add_argument('--fwd', default='0,1,2,3')
     ap.add_argument('--ring', default='', help='B2S_FUSED_RING values to time (default shape), e.g. 0,1')
+    ap.add_argument('--pair', default='', help='B2S_FUSED_PAIR values to time (1 = pair-transform kernel), e.g. 0,1,0,1')
     ap.add_argument('--ws', default='', help='B2S_FUSED_WS values to time (1 = warp-specialised kernel), e.g. 0,1,0,1')
     ap.add_argument('--ablate', default='', help='B2S_FUSED_ABLATE values to time (default shape)')
     ap.add_argument('--iters', type=int, default=240)
@@ -79,6 +80,20 @@ def main():
                                                                      observation_abs=yabs[i])), n, iters=args.iters)
         show(f'fused hop ring = {r}', ms, B * (4 * T * (1 + K) + 4 * M * F * K), f'bit-identical to the first variant: {same}')
     os.environ.pop('B2S_FUSED_RING', None)
+    pair_ref = None
+    for r in [int(t) for t in args.pair.split(',') if t != '']:
+        os.environ['B2S_FUSED_PAIR'] = str(r)
+        loss, perm = review.stft_mask_pit_step(None, ss[0], masks[0], stft=stft, observation_abs=yabs[0])
+        torch.cuda.synchronize()
+        if pair_ref is None:
+            pair_ref = (loss.clone(), perm.clone())
+        dl = float(((loss - pair_ref[0]).abs() / pair_ref[0].abs()).max())
+        same = bool((perm == pair_ref[1]).all())
+        ms = time_graph(lambda i: (lambda: review.stft_mask_pit_step(None, ss[i], masks[i], stft=stft,
+                                                                     observation_abs=yabs[i])), n, iters=args.iters)
+        show(f'fused pair transform = {r}', ms, B * (4 * T * (1 + K) + 4 * M * F * K),
+             f'loss dev from first {dl:.1e}, permutations equal: {same}')
+    os.environ.pop('B2S_FUSED_PAIR', None)
     ws_ref = None
     for r in [int(t) for t in args.ws.split(',') if t != '']:
         os.environ['B2S_FUSED_WS'] = str(r)
