@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "fft1024.cuh"
 #include "rfft_packed.cuh"
+#include "cfft_pair.cuh"
 #include "stft_plan.cuh"
 #include "tma.cuh"
 
@@ -165,12 +166,16 @@ constexpr int kPipeStages = 2;     // ring slots per warp
 // shared-memory wavefronts + FP32 pipe cycles per frame): 3 CTAs/SM with 48-register
 // compact constants (rf::CompactConsts), one frame per unit at 4 CTAs/SM, a single ring slot refilled from
 // rfft_streams' input_consumed hook.
+// PAIR (NS == 2): the unit's two frames go through ONE 1024-point complex transform (cfft_pair.cuh: z = frame_0 +
+// i frame_1, one exchange, mirror shuffle, addition-only separation); lane j then holds bins j + 32 r of both frames.
 template <int LAYOUT, bool DOUBLE_INTERIOR, bool SHIFT256, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm,
-          bool COMPACT = false, int STAGES = kPipeStages>
+          bool COMPACT = false, int STAGES = kPipeStages, bool PAIR = false>
 __global__ void __launch_bounds__(32 * kPipeWarps, CTAS)
 stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples, int64_t row_stride,
                      int64_t pad_left, int64_t frames, int shift, const float4* __restrict__ lane_table,
-                     float* __restrict__ out, int ablate, FeatureArgs feat) {
+                     float* __restrict__ out, int ablate, FeatureArgs feat, const float* __restrict__ window,
+                     const float2* __restrict__ tab) {
+  static_assert(!PAIR || NS == 2, "the pair transform takes the two frames of a unit");
   extern __shared__ __align__(16) float smem[];   // per warp: [STAGES][span] samples, NS exchange tiles, output rows
   __shared__ __align__(8) uint64_t bars[kPipeWarps][STAGES];
   constexpr int kOutPerFrame = LAYOUT <= B2S_SPEC_CONCAT ? 2 * rf::kBins : rf::kBins;
@@ -189,7 +194,18 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
   }
   __syncwarp();
   typename std::conditional<COMPACT, rf::CompactConsts, rf::LaneConsts>::type k;
-  k.load(lane_table, lane);   // immutable plan data: may be read before the preceding kernel has finished
+  cp::PairConsts kp;
+  if (PAIR) {   // immutable plan data: may be read before the preceding kernel has finished
+    kp.lane = lane;
+    // the separation's factor 1/2 is part of the window; DOUBLE_INTERIOR (adjoint of the iSTFT) wants the interior
+    // bins doubled: the window stays whole and the two edge bins are halved instead
+#pragma unroll
+    for (int p = 0; p < 32; ++p) kp.w[p] = (DOUBLE_INTERIOR ? 1.f : 0.5f) * __ldg(window + lane + 32 * p);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + ((lane * q) & 1023));
+  } else {
+    k.load(lane_table, lane);
+  }
   // Launched with programmatic stream serialization: barriers and constants above overlap the tail of the
   // preceding kernel; nothing of the caller's data is touched before this wait.  Only then may a kernel launched
   // the same way behind this one (the fused loss) start -- it reads its own inputs before ITS wait and must not
@@ -274,7 +290,57 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     float2 ya[NS][8], yb[NS][8];
     float ydc[NS], ynyq[NS];
     auto next_copy = [&]() { if (STAGES == 1) issue(nxt, 0); };
-    rf::rfft_streams<NS, SHIFT256 && (NS > 1), DOUBLE_INTERIOR>(buf, shift, tile, k, ya, yb, ydc, ynyq, ablate, next_copy);
+    float2 pa[PAIR ? 16 : 1], pb[PAIR ? 16 : 1];   // PAIR: spectra of frame 0 / frame 1 at bins lane + 32 r
+    float2 pn = make_float2(0.f, 0.f);             // PAIR, lane 0: (Y_0[512], Y_1[512]), both real
+    if (PAIR) {
+      float2 v[32];
+      {
+        const float* fa = buf + lane;
+        if (SHIFT256) {   // frame 1 = frame 0 shifted by eight of the lane's strides: 40 loads instead of 64
+          float xs[40];
+#pragma unroll
+          for (int p = 0; p < 40; ++p) xs[p] = fa[32 * p];
+#pragma unroll
+          for (int p = 0; p < 32; ++p) v[p] = make_float2(kp.w[p] * xs[p], kp.w[p] * xs[p + 8]);
+        } else {
+          const float* fb = fa + shift;
+#pragma unroll
+          for (int p = 0; p < 32; ++p) v[p] = make_float2(kp.w[p] * fa[32 * p], kp.w[p] * fb[32 * p]);
+        }
+      }
+      __syncwarp();   // every lane holds its samples; the previous unit's column reads of the tile are done
+      next_copy();
+      cp::radix32(v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float2 u = v[cp::out_pos(q)];
+        tile[lane * cp::kPitch + q] = q == 0 ? u : rf::cmul(u, kp.t[cp::out_pos(q)]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int l = 0; l < 32; ++l) v[l] = tile[l * cp::kPitch + lane];
+      cp::radix32(v);
+      const int partner = (32 - lane) & 31;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 z = v[cp::out_pos(r)];
+        const float2 hi = v[cp::out_pos(31 - r)], lo = v[cp::out_pos((32 - r) & 31)];
+        const float2 send = lane == 0 ? lo : hi;
+        float2 mm;
+        mm.x = __shfl_sync(0xffffffffu, send.x, partner);
+        mm.y = __shfl_sync(0xffffffffu, send.y, partner);
+        const float2 cm = make_float2(mm.x, -mm.y);
+        const float2 sa = rf::add2(z, cm), d = rf::sub2(z, cm);
+        pa[r] = sa;                          // Y_0[k] = (Z[k] + conj Z[1024 - k]) / 2
+        pb[r] = make_float2(d.y, -d.x);      // Y_1[k] = (Z[k] - conj Z[1024 - k]) / 2i
+      }
+      const float2 zn = v[cp::out_pos(16)];
+      // bin 512 (lane 0): Z[512] = (Y_0 + i Y_1) / 2 resp. Y_0 + i Y_1 with the whole window
+      pn = DOUBLE_INTERIOR ? zn : make_float2(2.f * zn.x, 2.f * zn.y);
+      if (DOUBLE_INTERIOR && lane == 0) { pa[0] = make_float2(0.5f * pa[0].x, 0.f); pb[0] = make_float2(0.5f * pb[0].x, 0.f); }
+    } else {
+      rf::rfft_streams<NS, SHIFT256 && (NS > 1), DOUBLE_INTERIOR>(buf, shift, tile, k, ya, yb, ydc, ynyq, ablate, next_copy);
+    }
     if (ablate & 1) continue;   // experiments: no output at all
     // The spectrum rows of the unit are adjacent in global memory.  They are assembled in shared memory at
     // the global address's phase within 16 bytes and leave as ONE asynchronous TMA bulk store (plus at most 3
@@ -290,6 +356,29 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       float* o = obuf + phase + s * kOutPerFrame;
+      if (PAIR) {   // bins lane + 32 r: unit-stride, conflict-free staging stores with immediates
+        float* ol = o + kS * lane;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float2 y = s == 0 ? pa[r] : pb[r];
+          if (kFeature) {
+            const float va = feature_power(y, feat);
+            ol[32 * r] = mel ? va : feature_log(va, feat);
+          } else {
+            store_bin_t<LAYOUT>(ol + kS * 32 * r, 0, y);
+          }
+        }
+        if (lane == 0) {
+          const float2 yn = make_float2(s == 0 ? pn.x : pn.y, 0.f);
+          if (kFeature) {
+            const float vn = feature_power(yn, feat);
+            o[rf::kHalf] = mel ? vn : feature_log(vn, feat);
+          } else {
+            store_bin_t<LAYOUT>(o, rf::kHalf, yn);
+          }
+        }
+        continue;
+      }
       if (kFeature) {
         // |Y|^power [/ size], and without a filterbank the logarithm, per bin
 #pragma unroll
@@ -809,9 +898,10 @@ bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0;
 struct PipeArgs {
   const float* x; int64_t rows, samples, row_stride, pad_left, frames; int shift; const float4* table; float* out;
   int ablate, layout, device; cudaStream_t stream; FeatureArgs feat;
+  const float* window; const float2* tab;   // the pair transform's constants are built from these (plan tables)
 };
 template <int L, bool D, bool S, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm, bool COMPACT = false,
-          int STAGES = kPipeStages>
+          int STAGES = kPipeStages, bool PAIR = false>
 int launch_pipe(const PipeArgs& a) {
   const int64_t units = a.rows * ceil_div(a.frames, NS);
   const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * CTAS);
@@ -829,14 +919,14 @@ int launch_pipe(const PipeArgs& a) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  auto kernel = stft1024_warp_kernel<L, D, S, NS, CTAS, COMPACT, STAGES>;
+  auto kernel = stft1024_warp_kernel<L, D, S, NS, CTAS, COMPACT, STAGES, PAIR>;
   static bool configured[64] = {};
   if (!configured[a.device & 63]) {
     B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[a.device & 63] = true;
   }
   B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, a.x, a.rows, a.samples, a.row_stride, a.pad_left, a.frames, a.shift,
-                              a.table, a.out, a.ablate, a.feat));
+                              a.table, a.out, a.ablate, a.feat, a.window, a.tab));
   B2S_LAUNCH_CHECK("stft1024_warp_kernel");
   return B2S_OK;
 }
@@ -857,15 +947,22 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                 "signal too large for the STFT warp kernel (%lld frames of %lld samples)", (long long)(rows * frames),
                 (long long)samples);
     const PipeArgs pa{x, rows, samples, row_stride, pad_left, frames, plan->shift, table, out, ablate, layout,
-                      plan->device, stream, feat ? *feat : FeatureArgs{}};
+                      plan->device, stream, feat ? *feat : FeatureArgs{}, win, plan->tw};
+    // B2S_FWD_PAIR=0: the 8 x 8 x 8 transform per frame instead of the pair transform per unit of two frames
+    const char* pe = getenv("B2S_FWD_PAIR");   // read per launch: one process can compare the two
+    const bool pair = !(pe && atoi(pe) == 0);
     if (layout == B2S_SPEC_FEATURE) {
+      if (pair) {
+        if (plan->shift == 256) return launch_pipe<B2S_SPEC_FEATURE, false, true, 2, 2, false, 2, true>(pa);
+        return launch_pipe<B2S_SPEC_FEATURE, false, false, 2, 2, false, 2, true>(pa);
+      }
       if (plan->shift == 256) return launch_pipe<B2S_SPEC_FEATURE, false, true>(pa);
       return launch_pipe<B2S_SPEC_FEATURE, false, false>(pa);
     }
     // tuning alternatives of the headline configuration (|Y| epilogue, shift 256): tools/hot_bench.py
     const char* ve = getenv("B2S_FWD_VARIANT");   // read per launch: one process can sweep the shapes
     const int variant = ve ? atoi(ve) : 0;
-    if (layout == B2S_SPEC_ABS && plan->shift == 256 && variant != 0) {
+    if (layout == B2S_SPEC_ABS && plan->shift == 256 && variant != 0 && !pair) {
       switch (variant) {
         case 1: return launch_pipe<B2S_SPEC_ABS, false, true, 2, 3, false, 1>(pa);
         case 2: return launch_pipe<B2S_SPEC_ABS, false, true, 1, 3, false, 2>(pa);
@@ -873,7 +970,10 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
         default: break;
       }
     }
-#define B2S_PIPE_S(L, D) do { if (plan->shift == 256) return launch_pipe<L, D, true>(pa); else return launch_pipe<L, D, false>(pa); } while (0)
+#define B2S_PIPE_S(L, D) do {                                                                        \
+      if (pair) { if (plan->shift == 256) return launch_pipe<L, D, true, 2, 2, false, 2, true>(pa);      \
+                  else return launch_pipe<L, D, false, 2, 2, false, 2, true>(pa); }                        \
+      if (plan->shift == 256) return launch_pipe<L, D, true>(pa); else return launch_pipe<L, D, false>(pa); } while (0)
     switch (layout) {
       case B2S_SPEC_INTERLEAVED: if (twice) B2S_PIPE_S(B2S_SPEC_INTERLEAVED, true); else B2S_PIPE_S(B2S_SPEC_INTERLEAVED, false); break;
       case B2S_SPEC_CONCAT: if (twice) B2S_PIPE_S(B2S_SPEC_CONCAT, true); else B2S_PIPE_S(B2S_SPEC_CONCAT, false); break;

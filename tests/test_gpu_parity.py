@@ -649,8 +649,13 @@ def test_full_size_properties(b2s):
     assert torch.equal(perm2, perm)
     mse, perm3, _, _ = b2s.review.pit_losses_per_example(masks, y_abs, x_abs)
     assert torch.equal(perm3, perm)
-    torch.testing.assert_close(loss, mse, rtol=1e-4, atol=1e-9)
-    torch.testing.assert_close(loss2, mse, rtol=1e-4, atol=1e-9)
+    # (ideal masks leave residuals of 1e-3 |X|: the loss is a near-cancellation, and rounding differences of 1e-7 |X|
+    # between two correct fp32 transforms -- the |Y|-recomputing kernel uses the 8 x 8 x 8 transform, the front-end and
+    # the two-source kernel the pair transform -- show up amplified in it; the absolute tolerance is therefore stated
+    # relative to the targets' energy, 1e-7 of it)
+    atol = 1e-7 * float((x_abs ** 2).mean())
+    torch.testing.assert_close(loss, mse, rtol=1e-4, atol=atol)
+    torch.testing.assert_close(loss2, mse, rtol=1e-4, atol=atol)
     # determinism (Trainer.test_run compares two runs at 1e-5 / 1e-6): bit identical here
     loss_again, _ = b2s.review.stft_mask_pit_step(y, s, masks, stft=stft)
     assert torch.equal(loss, loss_again)
