@@ -689,11 +689,15 @@ int launch_fused(const b2s_stft_plan* plan, const float* mixture, const float* y
       return launch_fused_pair(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse,
                                workspace, stream);
   }
-  if constexpr (K <= 2) {   // warp-specialised kernel (fused_ws.cuh): opt-in with B2S_FUSED_WS=1 -- measured slower
-    const char* e = getenv("B2S_FUSED_WS");   // (54.2 us against 47.6 us, profiles/r2_fused_ws.txt)
-    if (e && atoi(e) != 0)
-      return launch_fused_ws<K>(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse,
-                                workspace, stream);
+  if constexpr (K <= 2) {   // warp-specialised kernel (fused_ws.cuh): opt-in, B2S_FUSED_WS=1 (8 x 8 x 8 transforms) or
+    const char* e = getenv("B2S_FUSED_WS");   // =2 (pair transform, K = 2); profiles/r2_fused_experiments.txt
+    const int v = e ? atoi(e) : 0;
+    if (v == 2 && K == 2)
+      return launch_fused_ws<K, K == 2>(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm,
+                                        sse, workspace, stream);
+    if (v != 0)
+      return launch_fused_ws<K, false>(plan, yabs, sources, mask, meta, batch, samples, frames, pad_left, loss, perm, sse,
+                                       workspace, stream);
   }
   if (K == 2) {   // tuning alternatives of the headline configuration (tools/hot_bench.py)
     const char* e = getenv("B2S_FUSED_VARIANT");   // read per launch: one process can sweep the shapes

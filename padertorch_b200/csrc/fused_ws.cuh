@@ -30,6 +30,7 @@ constexpr int kWsSseWarps = 4;                                  // one warp grou
 constexpr int kWsThreads = 32 * (kWsStreams + kWsSseWarps);     // 384
 constexpr int kWsMagRow = 520;                                  // floats per magnitude row (513 bins, 16-byte multiple)
 constexpr int kWsSseRegs = 120, kWsTransformRegs = 192;         // 128 * 120 + 256 * 192 = 384 * 168
+constexpr int kWsSseRegsPair = 104, kWsTransformRegsPair = 200;  // 128 * 104 + 256 * 200 = 384 * 168
 
 __host__ __device__ constexpr int ws_stream_floats(int K) {
   return K * rf::kSize + 2 * 2 * rf::kTile1 + K * kWsMagRow + row_area_floats(K);
@@ -39,13 +40,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int K>
+// PAIR (K == 2): the transform warps run the pair transform (cfft_pair.cuh) instead of two 8 x 8 x 8 transforms.
+template <int K, bool PAIR>
 __global__ void __launch_bounds__(kWsThreads, 1)
 stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sources, const float* __restrict__ mask,
                    const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames, int shift,
                    int64_t pad_left, const float4* __restrict__ lane_table, int slots, double* __restrict__ partial,
                    int* __restrict__ counters, float* __restrict__ loss, int32_t* __restrict__ perm,
-                   double* __restrict__ sse, int exp_arg /* tuning builds only: 1 SSE warps skip the arithmetic, 2 no SSE warps */) {
+                   double* __restrict__ sse, const float* __restrict__ window, const float2* __restrict__ tab,
+                   int exp_arg /* tuning builds only: 1 SSE warps skip the arithmetic, 2 no SSE warps */) {
+  static_assert(!PAIR || K == 2, "the pair transform takes the two sources of a position");
   const int exp = kTuning ? exp_arg : 0;
   constexpr int NV = K * K;
   constexpr int F = rf::kBins;
@@ -74,7 +78,7 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
 
   if (warp >= kWsSseWarps) {
     // ================================================= transform warps ==========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsTransformRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PAIR ? kWsTransformRegsPair : kWsTransformRegs));
     const int st = warp - kWsSseWarps;
     const int64_t gs = (int64_t)blockIdx.x * kWsStreams + st;
     if (gs >= nstreams) return;
@@ -85,7 +89,16 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
     uint64_t* bar_full = &bars[st][2];
     uint64_t* bar_empty = &bars[st][3];
     rf::LaneConsts k;
-    k.load(lane_table, lane);
+    cp::PairConsts kp;
+    if (PAIR) {
+      kp.lane = lane;
+#pragma unroll
+      for (int p = 0; p < 32; ++p) kp.w[p] = 0.5f * __ldg(window + lane + 32 * p);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + ((lane * q) & 1023));
+    } else {
+      k.load(lane_table, lane);
+    }
     // slot p holds bin (p < 4 ? k0 : k4) + 64 p on the A side and 512 minus that on the B side
     const int k0 = rf::bin_a(lane, 0), k4 = rf::bin_a(lane, 4) - 256;
     const bool first = lane == 0;
@@ -186,7 +199,54 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
         __syncwarp();
       }
       auto next_copy = [&]() { start_signals(q + 1, bn, mn); };
-      if (K == 2) {
+      if (PAIR) {
+        float2 v[32];
+        {
+          const float* fa = sig + lane;
+          const float* fb = sig + rf::kSize + lane;
+#pragma unroll
+          for (int p = 0; p < 32; ++p) v[p] = make_float2(kp.w[p] * fa[32 * p], kp.w[p] * fb[32 * p]);
+        }
+        __syncwarp();   // every lane holds its samples (and the previous position's tile reads are done)
+        next_copy();
+        cp::radix32(v);
+#pragma unroll
+        for (int qq = 0; qq < 32; ++qq) {
+          const float2 u = v[cp::out_pos(qq)];
+          tile[lane * cp::kPitch + qq] = qq == 0 ? u : rf::cmul(u, kp.t[cp::out_pos(qq)]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < 32; ++l) v[l] = tile[l * cp::kPitch + lane];
+        cp::radix32(v);
+        const int partner = (32 - lane) & 31;
+        float xa[16], xb[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float2 z = v[cp::out_pos(r)];
+          const float2 hi = v[cp::out_pos(31 - r)], lo = v[cp::out_pos((32 - r) & 31)];
+          const float2 send = first ? lo : hi;
+          float2 mm;
+          mm.x = __shfl_sync(0xffffffffu, send.x, partner);
+          mm.y = __shfl_sync(0xffffffffu, send.y, partner);
+          const float2 cm = make_float2(mm.x, -mm.y);
+          const float2 sa = rf::add2(z, cm), d = rf::sub2(z, cm);
+          xa[r] = fft::sqrt_approx(fmaf(sa.x, sa.x, sa.y * sa.y));
+          xb[r] = fft::sqrt_approx(fmaf(d.x, d.x, d.y * d.y));
+        }
+        const float2 zn = v[cp::out_pos(16)];
+        if (!(exp & 2)) mbar_wait(bar_empty, empty_phase);   // the SSE warp has read the previous position's magnitudes
+        empty_phase ^= 1;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          mag[lane + 32 * r] = xa[r];
+          mag[kWsMagRow + lane + 32 * r] = xb[r];
+        }
+        if (first) {
+          mag[rf::kHalf] = 2.f * fabsf(zn.x);
+          mag[kWsMagRow + rf::kHalf] = 2.f * fabsf(zn.y);
+        }
+      } else if (K == 2) {
         float2 ya[2][8], yb[2][8];
         float ydc[2], ynyq[2];
         rf::rfft_streams<2, false, false>(sig, rf::kSize, tile, k, ya, yb, ydc, ynyq, 0, next_copy);
@@ -209,7 +269,7 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
   }
 
   // ===================================================== SSE warps ================================================
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsSseRegs));
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PAIR ? kWsSseRegsPair : kWsSseRegs));
   if (exp & 2) return;
   constexpr int U = kWsStreams / kWsSseWarps;   // streams per SSE warp
   int64_t q[U], p_end[U], gsu[U];
@@ -401,7 +461,7 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
     if (b_cur[u] >= 0) flush(u, b_cur[u]);
 }
 
-template <int K>
+template <int K, bool PAIR>
 int launch_fused_ws(const b2s_stft_plan* plan, const float* yabs, const float* sources, const float* mask,
                     const int64_t* meta, int64_t batch, int64_t samples, int64_t frames, int64_t pad_left,
                     float* loss, int32_t* perm, double* sse, void* workspace, cudaStream_t stream) {
@@ -416,7 +476,7 @@ int launch_fused_ws(const b2s_stft_plan* plan, const float* yabs, const float* s
   const int slots = (int)(ceil_div(frames * nstreams, total) + 2);
   constexpr size_t smem = sizeof(float) * kWsStreams * ws_stream_floats(K);
   static_assert(smem + 1024 <= 227 * 1024, "stream areas exceed the shared memory of an SM");
-  auto kernel = stft_pit_ws_kernel<K>;
+  auto kernel = stft_pit_ws_kernel<K, PAIR>;
   static bool configured[64] = {};
   if (!configured[plan->device & 63]) {
     B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -435,12 +495,14 @@ int launch_fused_ws(const b2s_stft_plan* plan, const float* yabs, const float* s
   cfg.numAttrs = use_pdl ? 1 : 0;
   const int shift = plan->shift;
   const float4* table = plan->lane_fwd;
+  const float* window = plan->awin;
+  const float2* tab = plan->tw;
   const char* ee = getenv("B2S_FUSED_WS_EXP");   // tuning builds only (results are wrong with any bit set)
   const int exp = ee ? atoi(ee) : 0;
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
   B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, yabs, sources, mask, meta, batch, samples, frames, shift, pad_left, table,
-                              slots, partial, counters, loss, perm, sse, exp));
+                              slots, partial, counters, loss, perm, sse, window, tab, exp));
   B2S_LAUNCH_CHECK("stft_pit_ws_kernel");
   return B2S_OK;
 }

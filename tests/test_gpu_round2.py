@@ -293,8 +293,13 @@ def test_warp_specialised_fused_kernel_against_oracle(b2s, B, K, T, ragged, monk
     md = torch.from_numpy(masks).to(dev())
     y_abs = stft.magnitude(yd)
     monkeypatch.delenv('B2S_FUSED_WS', raising=False)
+    monkeypatch.setenv('B2S_FUSED_PAIR', '0')    # reference: the one-role 8 x 8 x 8 pipeline
     loss0, perm0 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
-    monkeypatch.setenv('B2S_FUSED_WS', '1')
+    monkeypatch.delenv('B2S_FUSED_PAIR', raising=False)
+    lossp, permp = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
+    np.testing.assert_array_equal(permp.cpu().numpy(), perm0.cpu().numpy())   # default (pair kernel for K = 2)
+    np.testing.assert_allclose(lossp.cpu().numpy(), loss0.cpu().numpy(), rtol=1e-5)
+    monkeypatch.setenv('B2S_FUSED_WS', '2' if K == 2 and B % 2 == 1 else '1')   # 2: pair transform in the transform warps
     loss1, perm1 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
     loss2, perm2 = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
     torch.cuda.synchronize()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The two kernels of the bench step, three times each at the headline shape -- for ncu captures:
-    ncu --set full --clock-control none --import-source on -k regex:'stft_pit_fused|stft1024_warp' -s 2 -c 2 \
+    ncu --set full --clock-control none --import-source on -k regex:'stft_pit_pair|stft_pit_fused|stft1024_warp' -s 2 -c 2 \
         -o gpurun_out/prof python tools/fused_probe.py
 """
 import os

@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <vector>
 #include <cmath>
-#include "../prototypes/cfft_pair.cuh"
+#include "../../padertorch_b200/csrc/cfft_pair.cuh"
 using namespace b2s::cp;
 
 constexpr int kWarps = 4;
