@@ -62,15 +62,14 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
   bool sig_by_tma = false;
   int off_m = 0, off_y = 0;
   auto frames_of = [&](int64_t b) { return meta ? meta[2 * b + 1] : frames; };
-  int64_t ctx_b = -1;
+  // The context (row pointers, lengths) is that of the example whose position is REQUESTED next; it changes only when
+  // the walk below crosses an example boundary, so the steady state has no per-position context checks.
   int ctx_T = 0, ctx_M = 0;
   bool ctx_a16 = false;
   const float* ctx_row[K];
   const float* ctx_mask = nullptr;
   const float* ctx_y = nullptr;
-  auto set_ctx = [&](int64_t b) {
-    if (b == ctx_b) return;
-    ctx_b = b;
+  auto load_ctx = [&](int64_t b) {
     ctx_T = (int)(meta ? meta[2 * b] : samples);
     ctx_M = (int)frames_of(b);
     ctx_a16 = true;
@@ -83,10 +82,9 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
     ctx_y = yabs + b * frames * F;
   };
   const int pad = (int)pad_left;
-  auto start_signals = [&](int64_t q, int64_t b, int m) {
-    if (q >= p_end) return;
-    set_ctx(b);
-    if (m >= ctx_M) { sig_by_tma = false; return; }
+  // request the two source frames of frame m of the context's example: TMA, or zero-filling cp.async for frames that
+  // touch the zero padding at the signal's ends or are not 16-byte aligned
+  auto start_signals = [&](int m) {
     const int s0 = m * shift - pad;
     const bool a16 = ctx_a16 && (s0 & 3) == 0;
     const bool bulk = a16 && s0 >= 0 && s0 + rf::kSize <= ctx_T;
@@ -118,10 +116,9 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
       fft::cp_async_commit();
     }
   };
-  auto start_rows = [&](int64_t q, int64_t b, int m) {
-    if (q >= p_end) return;
-    set_ctx(b);
-    if (m >= ctx_M) return;
+  // request the mask rows [K][F] and the |Y| row of frame m of the context's example (enclosing 16-byte aligned
+  // ranges; the rows sit at the source's misalignment inside the landing areas)
+  auto start_rows = [&](int m) {
     const uintptr_t am = reinterpret_cast<uintptr_t>(ctx_mask + m * (K * F));
     const uintptr_t ay = reinterpret_cast<uintptr_t>(ctx_y + m * F);
     off_m = (int)(am & 15) >> 2;
@@ -195,30 +192,42 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
     }
   };
 
-  int64_t b = p_begin / frames;
-  int m = (int)(p_begin - b * frames);
   const int frames_i = (int)frames;
   const int partner = (32 - lane) & 31;
   const bool first = lane == 0;
+  // The walk over the LIVE positions of the range (frames beyond an example's own length -- ragged batches -- are
+  // skipped): (q, b, m) is the position being processed, (qn, bn, mn) the next live one (qn == p_end: none).  In the
+  // steady state the next position is the next frame of the same example: one comparison.
+  // Every warp whose (dense) range touches an example contributes a partial sum and a ticket for it, live frames or
+  // not: examples that the walk passes without a live position are flushed with zero sums.
+  const int64_t b_last = (p_end - 1) / frames;
+  int64_t q = p_begin, b = p_begin / frames;
+  int m = (int)(p_begin - b * frames);
   asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing of the caller's tensors is requested before this
-  start_signals(p_begin, b, m);
-  start_rows(p_begin, b, m);
-  int64_t b_cur = p_begin < p_end ? b : -1;
-  for (int64_t q = p_begin; q < p_end; ++q) {
-    int64_t bn = b;
+  load_ctx(b);
+  while (m >= ctx_M) {   // the range starts in the padding of a shorter example
+    flush(b);
+    q += frames_i - m;
+    ++b; m = 0;
+    if (q >= p_end) return;
+    load_ctx(b);
+  }
+  start_signals(m);
+  start_rows(m);
+  for (;;) {
+    int64_t qn = q + 1, bn = b;
     int mn = m + 1;
-    if (mn == frames_i) { mn = 0; ++bn; }
-    if (b != b_cur) {   // warp-uniform
-      flush(b_cur);
-      b_cur = b;
-    }
-    set_ctx(b);
-    if (m >= ctx_M) {   // position beyond this example's length (ragged batch)
-      start_signals(q + 1, bn, mn);
-      start_rows(q + 1, bn, mn);
-      b = bn; m = mn;
-      continue;
-    }
+    const bool same = qn < p_end && mn < ctx_M;   // next frame of the same example: the context stays
+    auto find_next = [&]() {            // rare: example boundary, padding frames, end of the range
+      for (;;) {
+        if (qn >= p_end) { qn = p_end; bn = b_last + 1; return; }
+        if (mn >= frames_i) { ++bn; mn = 0; }
+        if (bn != b) load_ctx(bn);       // (for bn == b the context is already that example's)
+        if (mn < ctx_M) return;
+        qn += frames_i - mn;             // the rest of this example is padding
+        mn = frames_i;
+      }
+    };
     if (sig_by_tma) {
       mbar_wait(bar_sig, sig_phase);
       sig_phase ^= 1;
@@ -239,7 +248,8 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
 #endif
     }
     __syncwarp();                      // every lane holds its samples: the frames may be overwritten
-    start_signals(q + 1, bn, mn);
+    if (!same) find_next();            // (switches the context to the next position's example)
+    if (qn < p_end) start_signals(mn);
     cp::radix32(v);
 #pragma unroll
     for (int qq = 0; qq < 32; ++qq) {
@@ -308,10 +318,13 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
       }
     }
     __syncwarp();   // every lane has read its rows: the area may be overwritten
-    start_rows(q + 1, bn, mn);
-    b = bn; m = mn;
+    if (qn < p_end) start_rows(mn);
+    if (bn != b) {   // warp-uniform: the range leaves example b (and possibly passes examples without a live frame)
+      for (int64_t bb = b; bb < bn; ++bb) flush(bb);
+      if (qn >= p_end) break;
+    }
+    q = qn; b = bn; m = mn;
   }
-  if (b_cur >= 0) flush(b_cur);
 }
 
 int launch_fused_pair(const b2s_stft_plan* plan, const float* yabs, const float* sources, const float* mask,
