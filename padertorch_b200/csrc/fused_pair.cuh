@@ -15,10 +15,17 @@
 #define B2S_PAIR_PACKED_WINDOW 0
 #endif
 constexpr int kPairWarps = 4, kPairCtas = 2;
-__host__ __device__ constexpr int pair_warp_floats() {
-  return 2 * rf::kSize + 2 * 32 * cp::kPitch + row_area_floats(2);   // two frames, the transpose tile, mask / |Y| rows
+// RING (shift 256): the source frames are not copied whole.  Each source keeps a ring of five hops of 256 samples; the
+// walk visits consecutive frames of an utterance, so frame m + 1 needs ONE new hop per source (1 KB instead of 4 KB),
+// and that hop's slot is not part of the frame being transformed: it is requested at the START of position m -- a
+// whole position ahead instead of two thirds of one -- on the other of two mbarriers.
+constexpr int kPairRingHops = 5;
+__host__ __device__ constexpr int pair_sig_floats(bool ring) { return ring ? kPairRingHops * kHop : rf::kSize; }
+__host__ __device__ constexpr int pair_warp_floats(bool ring) {
+  return 2 * pair_sig_floats(ring) + 2 * 32 * cp::kPitch + row_area_floats(2);   // two sources, the transpose tile, rows
 }
 
+template <bool RING>
 __global__ void __launch_bounds__(32 * kPairWarps, kPairCtas)
 stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ sources, const float* __restrict__ mask,
                      const int64_t* __restrict__ meta, int64_t batch, int64_t samples, int64_t frames, int shift,
@@ -27,18 +34,20 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
                      int32_t* __restrict__ perm, double* __restrict__ sse) {
   constexpr int K = 2, NV = 4;
   constexpr int F = rf::kBins;
-  constexpr int kWarpFloats = pair_warp_floats();
+  constexpr int kSig = pair_sig_floats(RING);
+  constexpr int kWarpFloats = pair_warp_floats(RING);
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t bars[kPairWarps][2];
+  __shared__ __align__(8) uint64_t bars[kPairWarps][3];   // frames (two, alternating by position with RING), rows
   __shared__ double totals_sm[kPairWarps][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sig = smem + warp * kWarpFloats;                               // source t at sig + t * 1024
-  float2* tile = reinterpret_cast<float2*>(sig + 2 * rf::kSize);        // [32][kPitch]
-  float* rows_area = sig + 2 * rf::kSize + 2 * 32 * cp::kPitch;
+  float* sig = smem + warp * kWarpFloats;                               // source t at sig + t * kSig
+  float2* tile = reinterpret_cast<float2*>(sig + 2 * kSig);             // [32][kPitch]
+  float* rows_area = sig + 2 * kSig + 2 * 32 * cp::kPitch;
   uint64_t* bar_sig = &bars[warp][0];
-  uint64_t* bar_rows = &bars[warp][1];
+  uint64_t* bar_rows = &bars[warp][2];
   if (lane == 0) {
-    mbar_init(bar_sig, 1);
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
     mbar_init(bar_rows, 1);
     fence_mbar_init();
   }
@@ -50,7 +59,7 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
 #pragma unroll
   for (int p = 0; p < 32; ++p) k.w[p] = 0.5f * __ldg(window + lane + 32 * p);
 #pragma unroll
-  for (int q = 0; q < 32; ++q) k.t[cp::out_pos(q)] = __ldg(tab + ((lane * q) & 1023));
+  for (int q = 0; q < 32; ++q) k.t[cp::out_pos(q)] = __ldg(tab + 32 * q + lane)   /* plan->pair_tw: [q][lane] */;
 
   const int64_t total = batch * frames;
   const int64_t nwarps = min((int64_t)gridDim.x * kPairWarps, total);
@@ -115,6 +124,42 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
       }
       fft::cp_async_commit();
     }
+  };
+  // RING: request hops [h0, h1) of the context's example on frame barrier `which`; bit `which` of the two masks says
+  // how they travel (bulk copies completing on the barrier / zero-filling cp.async for hops that touch the padding at
+  // the signal's ends or are not 16-byte aligned)
+  unsigned ring_phase = 0, ring_bulk = 0, ring_async = 0;
+  auto request_hops = [&](int h0, int h1, int which) {
+    int nbulk = 0;
+    for (int h = h0; h < h1; ++h) {
+      const int s0 = h * kHop - pad;
+      nbulk += (ctx_a16 && (s0 & 3) == 0 && s0 >= 0 && s0 + kHop <= ctx_T) ? 1 : 0;
+    }
+    const bool any_async = nbulk < h1 - h0;
+    ring_bulk = nbulk > 0 ? (ring_bulk | (1u << which)) : (ring_bulk & ~(1u << which));
+    ring_async = any_async ? (ring_async | (1u << which)) : (ring_async & ~(1u << which));
+    if (nbulk > 0 && lane == 0) mbar_expect_tx(&bars[warp][which], (unsigned)(nbulk * K * kHop * 4));
+    for (int h = h0; h < h1; ++h) {
+      const int s0 = h * kHop - pad;
+      float* dst = sig + (h % kPairRingHops) * kHop;
+      if (ctx_a16 && (s0 & 3) == 0 && s0 >= 0 && s0 + kHop <= ctx_T) {
+        if (lane == 0) {
+#pragma unroll
+          for (int t = 0; t < K; ++t) bulk_g2s(dst + t * kSig, ctx_row[t] + s0, kHop * 4u, &bars[warp][which]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const float* xr = ctx_row[t];
+          for (int i = lane; i < kHop; i += 32) {
+            const int n = s0 + i;
+            const bool ok = n >= 0 && n < ctx_T;
+            fft::cp_async_4_zfill(dst + t * kSig + i, ok ? xr + n : xr, ok ? 4 : 0);
+          }
+        }
+      }
+    }
+    if (any_async) fft::cp_async_commit();
   };
   // request the mask rows [K][F] and the |Y| row of frame m of the context's example (enclosing 16-byte aligned
   // ranges; the rows sit at the source's misalignment inside the landing areas)
@@ -212,12 +257,15 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
     if (q >= p_end) return;
     load_ctx(b);
   }
-  start_signals(m);
+  int which = 0;   // RING: frame barrier of the current position
+  if (RING) request_hops(m, m + 4, 0); else start_signals(m);
   start_rows(m);
   for (;;) {
     int64_t qn = q + 1, bn = b;
     int mn = m + 1;
     const bool same = qn < p_end && mn < ctx_M;   // next frame of the same example: the context stays
+    // RING: the next frame of the same example adds hop m + 4, whose slot the current frame does not use: request it now
+    if (RING && same) request_hops(m + 4, m + 5, which ^ 1);
     auto find_next = [&]() {            // rare: example boundary, padding frames, end of the range
       for (;;) {
         if (qn >= p_end) { qn = p_end; bn = b_last + 1; return; }
@@ -228,7 +276,16 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
         mn = frames_i;
       }
     };
-    if (sig_by_tma) {
+    if (RING) {
+      if (ring_bulk & (1u << which)) {
+        mbar_wait(&bars[warp][which], (ring_phase >> which) & 1u);
+        ring_phase ^= 1u << which;
+      }
+      if (ring_async & (1u << which)) {   // (also waits for the next position's hop if that one travels by cp.async)
+        fft::cp_async_wait_all();
+        __syncwarp();
+      }
+    } else if (sig_by_tma) {
       mbar_wait(bar_sig, sig_phase);
       sig_phase ^= 1;
     } else {
@@ -237,19 +294,27 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
     }
     // ---- pass 1: z[n] = w[n] (s_0[n] + i s_1[n]), n = lane + 32 p: conflict-free strided loads, radix-32 in registers
     float2 v[32];
-    {
+    if (RING) {   // sample lane + 32 p lies in hop p / 8 of the frame: ring slot (m + p / 8) % 5
+      const int base = m % kPairRingHops;
+      const float* fh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fh[j] = sig + lane + ((base + j >= kPairRingHops) ? base + j - kPairRingHops : base + j) * kHop;
+#pragma unroll
+      for (int p = 0; p < 32; ++p)
+        v[p] = make_float2(k.w[p] * fh[p / 8][32 * (p % 8)], k.w[p] * fh[p / 8][kSig + 32 * (p % 8)]);
+    } else {
       const float* fa = sig + lane;
       const float* fb = sig + rf::kSize + lane;
 #pragma unroll
-#if B2S_PAIR_PACKED_WINDOW
-      for (int p = 0; p < 32; ++p) v[p] = rf::mul2(make_float2(fa[32 * p], fb[32 * p]), rf::bcast(k.w[p]));
-#else
       for (int p = 0; p < 32; ++p) v[p] = make_float2(k.w[p] * fa[32 * p], k.w[p] * fb[32 * p]);
-#endif
     }
     __syncwarp();                      // every lane holds its samples: the frames may be overwritten
     if (!same) find_next();            // (switches the context to the next position's example)
-    if (qn < p_end) start_signals(mn);
+    if (qn < p_end) {
+      // RING: a continuation was requested at the top; the first frame of another example fills four hops (the ring's
+      // slots are free: every lane has its samples)
+      if (!RING) start_signals(mn); else if (!same) request_hops(mn, mn + 4, which ^ 1);
+    }
     cp::radix32(v);
 #pragma unroll
     for (int qq = 0; qq < 32; ++qq) {
@@ -324,6 +389,7 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
       if (qn >= p_end) break;
     }
     q = qn; b = bn; m = mn;
+    which ^= 1;
   }
 }
 
@@ -336,12 +402,19 @@ int launch_fused_pair(const b2s_stft_plan* plan, const float* yabs, const float*
   B2S_REQUIRE(samples < ((int64_t)1 << 30) && frames < ((int64_t)1 << 20) && pad_left < ((int64_t)1 << 30),
               "signal too long for the fused STFT->PIT kernel (%lld samples)", (long long)samples);
   const FusedGrid g = fused_grid(batch, frames, FusedShape{kPairWarps, kPairCtas, 1});
-  constexpr size_t smem = sizeof(float) * kPairWarps * pair_warp_floats();
-  static_assert(smem * kPairCtas + 2048 <= 227 * 1024, "pipelines exceed the shared memory of an SM");
-  static bool configured[64] = {};
-  if (!configured[plan->device & 63]) {
-    B2S_CUDA(cudaFuncSetAttribute(stft_pit_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[plan->device & 63] = true;
+  // the hop ring (shift 256, 16-byte granular padding) is opt-in, B2S_PAIR_RING=1: measured 45.3 us against 44.0 us
+  // with whole frames per position (profiles/r2_fused_experiments.txt) -- a quarter of the L2 -> shared-memory bytes
+  // and a whole position of prefetch distance do not pay for the slot arithmetic
+  const char* re = getenv("B2S_PAIR_RING");
+  const bool ring = plan->shift == kHop && pad_left % 4 == 0 && re && atoi(re) != 0;
+  const size_t smem = sizeof(float) * kPairWarps * pair_warp_floats(ring);
+  static_assert(sizeof(float) * kPairWarps * pair_warp_floats(true) * kPairCtas + 2048 <= 227 * 1024,
+                "pipelines exceed the shared memory of an SM");
+  auto kernel = ring ? stft_pit_pair_kernel<true> : stft_pit_pair_kernel<false>;
+  static bool configured[2][64] = {};
+  if (!configured[ring][plan->device & 63]) {
+    B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[ring][plan->device & 63] = true;
   }
   static const bool use_pdl = [] { const char* e = getenv("B2S_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
@@ -356,11 +429,11 @@ int launch_fused_pair(const b2s_stft_plan* plan, const float* yabs, const float*
   cfg.numAttrs = use_pdl ? 1 : 0;
   const int shift = plan->shift;
   const float* window = plan->awin;
-  const float2* tab = plan->tw;
+  const float2* tab = plan->pair_tw;
   const int slots = g.slots;
   double* partial = ws_partials(workspace);
   int* counters = ws_counters(workspace);
-  B2S_CUDA(cudaLaunchKernelEx(&cfg, stft_pit_pair_kernel, yabs, sources, mask, meta, batch, samples, frames, shift,
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, kernel, yabs, sources, mask, meta, batch, samples, frames, shift,
                               pad_left, window, tab, slots, partial, counters, loss, perm, sse));
   B2S_LAUNCH_CHECK("stft_pit_pair_kernel");
   return B2S_OK;

@@ -95,7 +95,7 @@ stft_pit_ws_kernel(const float* __restrict__ yabs, const float* __restrict__ sou
 #pragma unroll
       for (int p = 0; p < 32; ++p) kp.w[p] = 0.5f * __ldg(window + lane + 32 * p);
 #pragma unroll
-      for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + ((lane * q) & 1023));
+      for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + 32 * q + lane)   /* plan->pair_tw: [q][lane] */;
     } else {
       k.load(lane_table, lane);
     }
@@ -496,7 +496,7 @@ int launch_fused_ws(const b2s_stft_plan* plan, const float* yabs, const float* s
   const int shift = plan->shift;
   const float4* table = plan->lane_fwd;
   const float* window = plan->awin;
-  const float2* tab = plan->tw;
+  const float2* tab = plan->pair_tw;
   const char* ee = getenv("B2S_FUSED_WS_EXP");   // tuning builds only (results are wrong with any bit set)
   const int exp = ee ? atoi(ee) : 0;
   double* partial = ws_partials(workspace);

@@ -14,4 +14,6 @@ struct b2s_stft_plan {
   // inverse transform ([23][32] float4, rf::InvLaneConsts):
   float4* lane_inv_syn;   // synthesis window, scale 1    (iSTFT)
   float4* lane_inv_ana;   // analysis window, scale 1/2   (adjoint of the STFT)
+  // pair transform (cfft_pair.cuh): inter-pass twiddles exp(-2 pi i lane q / 1024) as [q][lane] (coalesced per-lane loads)
+  float2* pair_tw;
 };
