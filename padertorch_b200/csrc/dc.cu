@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "rfft_packed.cuh"   // packed fp32x2 helpers (rf::fma2, rf::bcast)
 
 using namespace b2s;
 
@@ -279,39 +280,36 @@ __host__ __device__ inline int frame_area(int rows, int F) { return (rows * F + 
 
 // One frame of block pair (BA, BB): lanes own bins lane, lane + 32, ...; with compile-time geometry every
 // operand address is base register + immediate.
+// The accumulators are packed pairs (acc[i][jj] = entries (i, 2 jj) and (i, 2 jj + 1)): one FFMA2 with a broadcast
+// operand per pair instead of two FFMA -- the kernel is bound by issue slots (6 500 instructions per frame and CTA
+// with scalar FFMA), not by HBM or the FMA pipe; a diagonal block computes the pairs that touch its upper triangle
+// (20 instead of 36 scalar products' worth of instructions).
 template <int FT, int ET, int KT, int BA, int BB>
 __device__ __forceinline__ void gram_frame_block(const float* be_, const float* bt_, const float* zrow, int F_rt,
-                                                 int E_rt, int K_rt, int lane, float (&acc)[BS][BS]) {
+                                                 int E_rt, int K_rt, int lane, float2 (&acc)[BS][BS / 2]) {
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, C = E + (KT ? KT : K_rt);
   constexpr bool diag = BA == BB;
   auto row = [&](int ch, int off) -> const float* {
     return (ch < E ? be_ + ch * F : (ch < C ? bt_ + (ch - E) * F : zrow)) + off;
   };
+  auto step = [&](int off) {
+    float va[BS];
+    float2 vb[BS / 2];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) va[i] = row(BA * BS + i, off)[0];
+#pragma unroll
+    for (int jj = 0; jj < BS / 2; ++jj)
+      vb[jj] = diag ? make_float2(va[2 * jj], va[2 * jj + 1])
+                    : make_float2(row(BB * BS + 2 * jj, off)[0], row(BB * BS + 2 * jj + 1, off)[0]);
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int jj = diag ? i / 2 : 0; jj < BS / 2; ++jj) acc[i][jj] = rf::fma2(rf::bcast(va[i]), vb[jj], acc[i][jj]);
+  };
   const int full_steps = F / 32;
 #pragma unroll 4
-  for (int j = 0; j < full_steps; ++j) {
-    float va[BS], vb[BS];
-#pragma unroll
-    for (int i = 0; i < BS; ++i) va[i] = row(BA * BS + i, 32 * j)[0];
-#pragma unroll
-    for (int i = 0; i < BS; ++i) vb[i] = diag ? va[i] : row(BB * BS + i, 32 * j)[0];
-#pragma unroll
-    for (int i = 0; i < BS; ++i)
-#pragma unroll
-      for (int jj = diag ? i : 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
-  }
-  if (lane + 32 * full_steps < F) {   // the F % 32 last bins
-    float va[BS], vb[BS];
-#pragma unroll
-    for (int i = 0; i < BS; ++i) {
-      va[i] = row(BA * BS + i, 32 * full_steps)[0];
-      vb[i] = diag ? va[i] : row(BB * BS + i, 32 * full_steps)[0];
-    }
-#pragma unroll
-    for (int i = 0; i < BS; ++i)
-#pragma unroll
-      for (int jj = diag ? i : 0; jj < BS; ++jj) acc[i][jj] = fmaf(va[i], vb[jj], acc[i][jj]);
-  }
+  for (int j = 0; j < full_steps; ++j) step(32 * j);
+  if (lane + 32 * full_steps < F) step(32 * full_steps);   // the F % 32 last bins
 }
 
 // FT / ET / KT != 0: bins / embedding channels / sources known at compile time (513 / 20 / 2)
@@ -360,11 +358,11 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
   const int bb = warp < 3 ? warp : (warp < 5 ? warp - 2 : 2);
   const bool active = ba * BS < C && bb * BS < C;
   const bool diag = ba == bb;
-  float acc[BS][BS];
+  float2 acc[BS][BS / 2];   // packed pairs of Gram entries (i, 2 jj), (i, 2 jj + 1)
 #pragma unroll
   for (int i = 0; i < BS; ++i)
 #pragma unroll
-    for (int j = 0; j < BS; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < BS / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   for (int t = t0; t < t1; ++t) {
     const int s = (t - t0) & 1;
@@ -391,7 +389,7 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
 #pragma unroll
     for (int j = 0; j < BS; ++j) {
       if (diag && j < i) continue;   // (warp-uniform) the lower triangle of a diagonal block is its mirror image
-      const float sum = warp_sum(acc[i][j]);
+      const float sum = warp_sum((j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
       if (lane == 0) {
         mine[(ba * BS + i) * kTC + bb * BS + j] = (double)sum;
         mine[(bb * BS + j) * kTC + ba * BS + i] = (double)sum;
