@@ -549,3 +549,41 @@ def test_ring_inverse_against_chunked_kernel_and_oracle(b2s, rows, T, layout, mo
         ref = ReferenceSTFT(1024, 256, complex_representation=layout)
         want = ref.inverse(spec.detach().cpu())
         assert float((z1.cpu() - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('B,T,shift,ragged', [(1, 3000, 256, False), (3, 9001, 256, False), (4, 12002, 256, True),
+                                              (2, 8000, 512, False), (3, 7003, 128, True), (70, 2500, 256, False)])
+def test_pair_kernel_edge_cases_against_oracle(b2s, B, T, shift, ragged, monkeypatch):
+    """The two-source pair-transform kernel (csrc/fused_pair.cuh; the default when |Y| is given) on the cases its fast
+    path does not cover: rows that are not 16-byte aligned (odd lengths: 4-byte zero-filling copies), other shifts,
+    ragged batches whose ranges start or end in the padding of a shorter example, more examples than pipelines have
+    positions; with and without the opt-in hop ring.  Permutations bit exact, losses within 1e-4 of the oracle."""
+    from oracle import path as OP
+    from oracle.stft import ReferenceSTFT
+    y, s, rng = _step_inputs(B, 2, T, 23 + B)
+    lengths = [int(T - 700 * (b % 3) - b) for b in range(B)] if ragged else None
+    if ragged:
+        for b, n in enumerate(lengths):
+            y[b, n:] = 0
+            s[b, :, n:] = 0
+    stft = b2s.ops.STFT(1024, shift)
+    M = stft.samples_to_frames(T)
+    masks = rng.rand(B, M, 2, 513).astype(np.float32)
+    yd, sd, md = torch.from_numpy(y).to(dev()), torch.from_numpy(s).to(dev()), torch.from_numpy(masks).to(dev())
+    y_abs = stft.magnitude(yd)
+    results = []
+    for ring in ('0', '1'):
+        monkeypatch.setenv('B2S_PAIR_RING', ring)
+        loss, perm = b2s.review.stft_mask_pit_step(None, sd, md, stft=stft, observation_abs=y_abs, num_samples=lengths)
+        results.append((loss.cpu().numpy(), perm.cpu().numpy()))
+    monkeypatch.delenv('B2S_PAIR_RING', raising=False)
+    np.testing.assert_array_equal(results[0][1], results[1][1])
+    np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-6)
+    ref = ReferenceSTFT(1024, shift)
+    for b in range(min(B, 6)):
+        n = lengths[b] if ragged else T
+        m_b = stft.samples_to_frames(n)
+        want_loss, want_perm, _ = OP.stft_mask_pit_step(torch.from_numpy(y[b:b + 1, :n]), torch.from_numpy(s[b:b + 1, :, :n]),
+                                                       torch.from_numpy(masks[b:b + 1, :m_b]), stft=ref)
+        np.testing.assert_array_equal(results[0][1][b], np.asarray(want_perm)[0])
+        np.testing.assert_allclose(results[0][0][b], float(want_loss[0]), rtol=LOSS_RTOL)
