@@ -830,6 +830,204 @@ istft_ring_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, 
   }
 }
 
+// ------------------------------------------------------------------------------------------- pair ring inverse
+// The ring inverse with the pair transform run backwards (interleaved complex rows, shift 256): the spectra A, B of
+// the two frames of a step form ONE Hermitian-extended 1024-point complex spectrum Z = A + i B (Z[1024 - k] =
+// conj A[k] + i conj B[k]: the mirrored half is read from the same landed rows, no exchange), whose inverse transform
+// z = a + i b carries frame m in its real and frame m + 1 in its imaginary part.  z = conj(FFT(conj Z)) runs through
+// the forward machinery of cfft_pair.cuh (radix-32, one exchange, radix-32); lane j ends up with samples j + 32 q of
+// both frames -- eight per hop at the same positions for every frame, so the overlap-add is a register shift register
+// again (5 hops x 8 floats) and a completed hop leaves as eight warp-wide contiguous 128-byte stores.  Chunks, chunk
+// boundaries (ticketed workspace) and the summation order are those of istft_ring_kernel.
+__global__ void __launch_bounds__(32 * kRingWarps, 2)
+istft_pair_ring_kernel(const float* __restrict__ spec, int64_t rows, int64_t frames, int64_t chunks_per_row,
+                       int64_t crop_left, int64_t samples_out, const float* __restrict__ window,
+                       const float2* __restrict__ tab, float scale /* 1: iSTFT, 1/2: adjoint of the STFT */,
+                       float* __restrict__ out, int* __restrict__ tickets, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float ring_smem[];
+  __shared__ __align__(8) uint64_t ring_bars[kRingWarps][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* bufs = reinterpret_cast<float2*>(ring_smem + warp * ring_warp_floats(2));   // [2][2][kTile1]
+  if (lane == 0) {
+    tma::mbar_init(&ring_bars[warp][0], 1);
+    tma::mbar_init(&ring_bars[warp][1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+  cp::PairConsts kp;
+  kp.lane = lane;
+#pragma unroll
+  for (int p = 0; p < 32; ++p) kp.w[p] = scale * __ldg(window + lane + 32 * p);
+#pragma unroll
+  for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + 32 * q + lane);
+  const float dc_fix = 1.f / scale;   // DC and Nyquist are not scaled
+  const bool first = lane == 0;
+  unsigned phase_bits = 0, off_bits = 0;
+  const int64_t units = rows * chunks_per_row;
+  const int64_t nwarps = (int64_t)gridDim.x * kRingWarps;
+  const int64_t total_hops = (crop_left + samples_out + kRingHop - 1) / kRingHop;
+  // a lane's samples of a hop: lane + 32 i, i = 0..7
+  auto store_hop = [&](float* orow, int64_t h, const float (&v)[8]) {
+    if (h >= total_hops) return;
+    const int64_t n0 = h * kRingHop - crop_left + lane;
+    if (n0 - lane >= 0 && n0 - lane + kRingHop <= samples_out) {   // warp-uniform: the whole hop lies inside the row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) orow[n0 + 32 * i] = v[i];
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t n = n0 + 32 * i;
+      if (n >= 0 && n < samples_out) orow[n] = v[i];
+    }
+  };
+  auto park_hop = [&](int64_t bid, int side, int j, const float (&v)[8]) {
+    float* dst = partials + bid * kBoundaryFloats + ((side * 3 + j) * 8) * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i * 32] = v[i];
+  };
+  auto publish = [&](bool lead, bool trail, int64_t bid_lead, int64_t bid_trail, int64_t row, int64_t f0, int64_t f1) {
+    if (!lead && !trail) return;
+    __threadfence();
+    __syncwarp();
+    int old = 0;
+    if (lane == 0 && lead) old = atomicAdd(tickets + bid_lead, 1);
+    if (lane == 1 && trail) old = atomicAdd(tickets + bid_trail, 1);
+    const int old_lead = __shfl_sync(0xffffffffu, old, 0), old_trail = __shfl_sync(0xffffffffu, old, 1);
+    const bool second_lead = lead && old_lead == 1, second_trail = trail && old_trail == 1;
+    if (!second_lead && !second_trail) return;   // warp-uniform
+    __threadfence();
+    float* orow = out + row * samples_out;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (!(w == 0 ? second_lead : second_trail)) continue;
+      const int64_t bid = w == 0 ? bid_lead : bid_trail, h_first = w == 0 ? f0 : f1;
+      const float* e = partials + bid * kBoundaryFloats + lane;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldcg(e + (j * 8 + i) * 32) + __ldcg(e + ((3 + j) * 8 + i) * 32);
+        store_hop(orow, h_first + j, v);
+      }
+      if (lane == 0) tickets[bid] = 0;
+    }
+  };
+  for (int64_t u = (int64_t)blockIdx.x * kRingWarps + warp; u < units; u += nwarps) {
+    const int64_t row = u / chunks_per_row, c = u - row * chunks_per_row;
+    const int64_t f0 = frames * c / chunks_per_row, f1 = frames * (c + 1) / chunks_per_row;
+    float* orow = out + row * samples_out;
+    const bool lead_partial = f0 > 0, trail_partial = f1 < frames;
+    const int64_t bid_lead = row * (chunks_per_row - 1) + (c - 1), bid_trail = bid_lead + 1;
+    auto stage_step = [&](int which, int64_t m) {
+      unsigned bytes[2], total = 0;
+      uintptr_t from[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(spec) + (uintptr_t)(row * frames + m + s) * (rf::kBins * 8);
+        off_bits = (off_bits & ~(1u << (which * 2 + s))) | ((unsigned)((addr >> 3) & 1) << (which * 2 + s));
+        from[s] = addr & ~(uintptr_t)15;
+        bytes[s] = m + s < f1 ? (unsigned)(((addr & 15) + rf::kBins * 8 + 15) & ~15u) : 0u;
+        total += bytes[s];
+      }
+      if (lane == 0) {
+        tma::fence_proxy_async();   // the region was this warp's transpose tile (generic-proxy stores and loads)
+        tma::mbar_expect_tx(&ring_bars[warp][which], total);
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (bytes[s]) tma::bulk_g2s(bufs + (which * 2 + s) * rf::kTile1, reinterpret_cast<const void*>(from[s]), bytes[s], &ring_bars[warp][which]);
+      }
+    };
+    stage_step(0, f0);
+    float acc[5][8];   // hop m + t of the current step; slots 0..2 carry sums of earlier frames
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    int which = 0;
+    for (int64_t m = f0; m < f1; m += 2, which ^= 1) {
+      const bool more = m + 2 < f1, two = m + 1 < f1;
+      if (more) stage_step(which ^ 1, m + 2);
+      tma::mbar_wait(&ring_bars[warp][which], (phase_bits >> which) & 1u);
+      phase_bits ^= 1u << which;
+      const float2* ra = bufs + (which * 2) * rf::kTile1 + ((off_bits >> (which * 2)) & 1u);
+      const float2* rb = bufs + (which * 2 + 1) * rf::kTile1 + ((off_bits >> (which * 2 + 1)) & 1u);
+      // v[r] = conj Z[lane + 32 r], Z = A + i B Hermitian-extended: bins up to 512 directly, the rest from the mirror bin
+      float2 v[32];
+      const int kmir = rf::kHalf - lane;   // mirror of bin lane + 32 r (r >= 16) is kmir - 32 (r - 16)
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const int k = r < 16 ? lane + 32 * r : kmir - 32 * (r - 16);
+        float2 A = ra[k];
+        float2 B = two ? rb[k] : make_float2(0.f, 0.f);
+        if ((r == 0 || r == 16) && first) {   // DC / Nyquist: real, not scaled
+          A = make_float2(A.x * dc_fix, 0.f);
+          B = make_float2(B.x * dc_fix, 0.f);
+        }
+        v[r] = r < 16 ? make_float2(A.x - B.y, -A.y - B.x) : make_float2(A.x + B.y, A.y - B.x);
+      }
+      __syncwarp();   // every lane holds its bins: the landing regions become the transpose tile
+      float2* tile = bufs + (which * 2) * rf::kTile1;   // 2 * kTile1 >= 32 * kPitch float2
+      cp::radix32(v);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float2 w = v[cp::out_pos(q)];
+        tile[lane * cp::kPitch + q] = q == 0 ? w : rf::cmul(w, kp.t[cp::out_pos(q)]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int l = 0; l < 32; ++l) v[l] = tile[l * cp::kPitch + lane];
+      __syncwarp();   // the tile's reads are done: the regions may receive the step after next
+      cp::radix32(v);
+      // v[q] = conj z[lane + 32 q]: frame m = Re z, frame m + 1 = Im z = -Im v; window, then the register overlap-add
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float xa = v[cp::out_pos(q)].x * kp.w[q];
+        float (&dst)[8] = acc[q / 8];
+        if (q / 8 == 3) dst[q % 8] = xa; else dst[q % 8] += xa;   // a frame's last hop: first contribution
+      }
+      if (two) {   // warp-uniform
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float xb = -v[cp::out_pos(q)].y * kp.w[q];
+          float (&dst)[8] = acc[1 + q / 8];
+          if (q / 8 == 3) dst[q % 8] = xb; else dst[q % 8] += xb;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int64_t h = m + s;
+        if (h < f1) {
+          if (lead_partial && h < f0 + 3) park_hop(bid_lead, 1, (int)(h - f0), acc[s]);
+          else store_hop(orow, h, acc[s]);
+        }
+      }
+      if (two) {   // shift the register ring by two hops (a short last step keeps its slots)
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] = acc[t + 2][i];
+      }
+    }
+    const bool short_last = (f1 - f0) & 1;
+    float tail[3][8];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tail[j][i] = short_last ? acc[j + 1][i] : acc[j][i];
+    if (trail_partial) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) park_hop(bid_trail, 0, j, tail[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) store_hop(orow, f1 + j, tail[j]);
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int64_t h = f1 + 3; h < total_hops; ++h) store_hop(orow, h, z);
+    }
+    publish(lead_partial, trail_partial, bid_lead, bid_trail, row, f0, f1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- generic inverse
 // Kernel A: one CTA per frame writes win[k] * (G0 + (-1)^k G_{N/2} + c sum_{0<f<N/2} Re(G_f e^{+i theta}))
 // to scratch[row, m, wlen].  Kernel B gathers the overlap-add.
@@ -1056,6 +1254,19 @@ int launch_inverse(const b2s_stft_plan* plan, const float* spec, int64_t rows, i
     B2S_REQUIRE(win == (adjoint ? plan->awin : plan->swin), "internal: window / table mismatch");
     int* tickets = reinterpret_cast<int*>(scratch);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + kTicketBytes);
+    // interleaved rows, two frames per step: the pair transform run backwards (B2S_INV_PAIR=0: rf::irfft_streams<2>)
+    const char* ipe = getenv("B2S_INV_PAIR");
+    if (ring_ns == 2 && layout == B2S_SPEC_INTERLEAVED && plan->wlen == fft::kSize && !(ipe && atoi(ipe) == 0)) {
+      static bool pair_configured[64] = {};
+      if (!pair_configured[plan->device & 63]) {
+        B2S_CUDA(cudaFuncSetAttribute(istft_pair_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_configured[plan->device & 63] = true;
+      }
+      istft_pair_ring_kernel<<<g.grid, 32 * kRingWarps, smem, stream>>>(spec, rows, frames, g.chunks_per_row, crop_left,
+          samples_out, win, plan->pair_tw, 0.5f * interior_scale, out, tickets, partials);
+      B2S_LAUNCH_CHECK("istft_pair_ring_kernel");
+      return B2S_OK;
+    }
     kernel<<<g.grid, 32 * kRingWarps, smem, stream>>>(spec, rows, frames, g.chunks_per_row, crop_left, samples_out,
         adjoint ? plan->lane_inv_ana : plan->lane_inv_syn, 0.5f * interior_scale, out, tickets, partials);
     B2S_LAUNCH_CHECK("istft_ring_kernel");
