@@ -52,6 +52,23 @@ DcGrid dc_grid(int64_t batch, int64_t max_frames, int64_t bins, int channels, bo
 struct Strides { int64_t t, c, f; };
 
 // Ticket + fixed-order fold of the chunk partials -> gram[b][C][C] and the loss (all threads call it).
+// Sums of 32 per-lane values across the warp, value l delivered to lane l: five halving steps in which a lane keeps
+// the half of its values its own lane bit selects, sends the other half to its partner and adds what it receives --
+// 31 shuffles for 32 sums instead of 160, and afterwards every lane holds one result (parallel stores).
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int E, int64_t N,
                                           double* __restrict__ partial, int* __restrict__ counters,
                                           double* __restrict__ gram, float* __restrict__ loss) {
@@ -75,11 +92,13 @@ __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int
     const double w = (re == ce) ? 1.0 : -1.0;  // the two mixed blocks together give -2 |V^T Y|^2
     local += w * s * s;
   }
-  red[threadIdx.x] = local;
+  // fixed tree: lanes by xor-shuffle, then the warps' sums in warp order
+  const double wsum = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wsum;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < (int)blockDim.x; ++i) s += red[i];
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += red[w];
     loss[b] = (float)(s / ((double)N * (double)N));
     counters[b] = 0;
   }
@@ -384,17 +403,23 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
     if (threadIdx.x == 0 && t + 2 < t1) issue(t + 2, s);
   }
   double* mine = partial + ((int64_t)b * nchunks + chunk) * kTC * kTC;
+  // the block's 64 sums in two transposed reductions: lane l receives entries l and 32 + l (row-major i * 8 + j) and
+  // stores them (and their mirror images) itself
 #pragma unroll
-  for (int i = 0; i < BS; ++i)
+  for (int half = 0; half < 2; ++half) {
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      if (diag && j < i) continue;   // (warp-uniform) the lower triangle of a diagonal block is its mirror image
-      const float sum = warp_sum((j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
-      if (lane == 0) {
-        mine[(ba * BS + i) * kTC + bb * BS + j] = (double)sum;
-        mine[(bb * BS + j) * kTC + ba * BS + i] = (double)sum;
-      }
+    for (int e = 0; e < 32; ++e) {
+      const int i = (32 * half + e) / BS, j = (32 * half + e) % BS;
+      v[e] = (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x;
     }
+    const float sum = warp_transpose_sum32(v, lane);
+    const int i = (32 * half + lane) / BS, j = (32 * half + lane) % BS;
+    if (!(diag && j < i)) {   // the lower triangle of a diagonal block is its mirror image
+      mine[(ba * BS + i) * kTC + bb * BS + j] = (double)sum;
+      mine[(bb * BS + j) * kTC + ba * BS + i] = (double)sum;
+    }
+  }
   dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
 }
 
