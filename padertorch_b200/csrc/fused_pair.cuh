@@ -57,7 +57,7 @@ stft_pit_pair_kernel(const float* __restrict__ yabs, const float* __restrict__ s
   cp::PairConsts k;
   k.lane = lane;
 #pragma unroll
-  for (int p = 0; p < 32; ++p) k.w[p] = 0.5f * __ldg(window + lane + 32 * p);
+  for (int p = 0; p < 32; ++p) k.w[p] = __ldg(window + lane + 32 * p);   // plan->awin_half: no arithmetic behind the loads
 #pragma unroll
   for (int q = 0; q < 32; ++q) k.t[cp::out_pos(q)] = __ldg(tab + 32 * q + lane)   /* plan->pair_tw: [q][lane] */;
 
@@ -428,7 +428,7 @@ int launch_fused_pair(const b2s_stft_plan* plan, const float* yabs, const float*
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
   const int shift = plan->shift;
-  const float* window = plan->awin;
+  const float* window = plan->awin_half;
   const float2* tab = plan->pair_tw;
   const int slots = g.slots;
   double* partial = ws_partials(workspace);

@@ -200,7 +200,7 @@ stft1024_warp_kernel(const float* __restrict__ x, int64_t rows, int64_t samples,
     // the separation's factor 1/2 is part of the window; DOUBLE_INTERIOR (adjoint of the iSTFT) wants the interior
     // bins doubled: the window stays whole and the two edge bins are halved instead
 #pragma unroll
-    for (int p = 0; p < 32; ++p) kp.w[p] = (DOUBLE_INTERIOR ? 1.f : 0.5f) * __ldg(window + lane + 32 * p);
+    for (int p = 0; p < 32; ++p) kp.w[p] = __ldg(window + lane + 32 * p);   // pre-scaled by the launcher's choice of table
 #pragma unroll
     for (int q = 0; q < 32; ++q) kp.t[cp::out_pos(q)] = __ldg(tab + 32 * q + lane);   // plan->pair_tw: [q][lane]
   } else {
@@ -1145,7 +1145,7 @@ int launch_forward(const b2s_stft_plan* plan, const float* x, int64_t rows, int6
                 "signal too large for the STFT warp kernel (%lld frames of %lld samples)", (long long)(rows * frames),
                 (long long)samples);
     const PipeArgs pa{x, rows, samples, row_stride, pad_left, frames, plan->shift, table, out, ablate, layout,
-                      plan->device, stream, feat ? *feat : FeatureArgs{}, win, plan->pair_tw};
+                      plan->device, stream, feat ? *feat : FeatureArgs{}, twice ? win : plan->awin_half, plan->pair_tw};
     // B2S_FWD_PAIR=0: the 8 x 8 x 8 transform per frame instead of the pair transform per unit of two frames
     const char* pe = getenv("B2S_FWD_PAIR");   // read per launch: one process can compare the two
     const bool pair = !(pe && atoi(pe) == 0);
@@ -1362,7 +1362,7 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
   plan->fast = size == fft::kSize;
   plan->awin = nullptr; plan->swin = nullptr; plan->tw = nullptr;
   plan->lane_fwd = nullptr; plan->lane_adj = nullptr; plan->lane_inv_syn = nullptr; plan->lane_inv_ana = nullptr;
-  plan->pair_tw = nullptr;
+  plan->pair_tw = nullptr; plan->awin_half = nullptr;
   cudaError_t e = cudaMalloc(&plan->awin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->swin, sizeof(float) * size);
   if (e == cudaSuccess) e = cudaMalloc(&plan->tw, sizeof(float2) * size);
@@ -1399,6 +1399,10 @@ int b2s_stft_plan_create(b2s_stft_plan** out, int device, int size, int shift, i
     std::vector<float2> ptw(32 * 32);
     for (int q = 0; q < 32; ++q)
       for (int lane = 0; lane < 32; ++lane) ptw[q * 32 + lane] = tw[(lane * q) & 1023];
+    std::vector<float> half(size);
+    for (int i = 0; i < size; ++i) half[i] = 0.5f * aw[i];
+    if (e == cudaSuccess) e = cudaMalloc(&plan->awin_half, sizeof(float) * size);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->awin_half, half.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&plan->pair_tw, sizeof(float2) * 32 * 32);
     if (e == cudaSuccess) e = cudaMemcpy(plan->pair_tw, ptw.data(), sizeof(float2) * 32 * 32, cudaMemcpyHostToDevice);
   }
@@ -1417,7 +1421,7 @@ int b2s_stft_plan_destroy(b2s_stft_plan* plan) {
   cudaFree(plan->awin); cudaFree(plan->swin); cudaFree(plan->tw);
   cudaFree(plan->lane_fwd); cudaFree(plan->lane_adj);
   cudaFree(plan->lane_inv_syn); cudaFree(plan->lane_inv_ana);
-  cudaFree(plan->pair_tw);
+  cudaFree(plan->pair_tw); cudaFree(plan->awin_half);
   delete plan;
   return B2S_OK;
 }

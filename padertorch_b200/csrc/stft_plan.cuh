@@ -16,4 +16,6 @@ struct b2s_stft_plan {
   float4* lane_inv_ana;   // analysis window, scale 1/2   (adjoint of the STFT)
   // pair transform (cfft_pair.cuh): inter-pass twiddles exp(-2 pi i lane q / 1024) as [q][lane] (coalesced per-lane loads)
   float2* pair_tw;
+  float* awin_half;   // [size] 0.5 * analysis window: the pair transform's window constants, ready to use (no arithmetic
+                      // between their loads and the first frame: the loads overlap the first copy's latency)
 };
