@@ -199,6 +199,16 @@ B2S_API int b2s_pair_loss(const double* stats, const int64_t* meta, int64_t grou
 B2S_API int b2s_pair_loss_set(const double* stats, const int64_t* meta, int64_t groups, int64_t inner,
                       int sources, int count, const int* kinds, const int* reductions, int flags,
                       double tau, float* loss, int32_t* perm, float* mean, b2s_stream stream);
+/* b2s_pair_stats_forward followed by b2s_pair_loss_set with inner == 1 (groups = examples: TasNet.loss,
+ * tasnet/model.py:154-176) in ONE launch: the CTA that completes an example's statistics evaluates the loss set
+ * from them, the CTA that completes the last example folds the batch means.  Same outputs as the two calls
+ * (stats is written as well: the backward reads it).  Rows that cannot be read with 16-byte loads and
+ * sources > 4 run the two launches internally.                                                       */
+B2S_API int b2s_pair_stats_loss_set(const float* estimate, const float* target, const int64_t* meta,
+                            int64_t groups, int64_t max_length, int sources,
+                            int64_t estimate_source_stride, int64_t target_source_stride, int count,
+                            const int* kinds, const int* reductions, int flags, double tau, double* stats,
+                            float* loss, int32_t* perm, float* mean, void* workspace, b2s_stream stream);
 /* grad_estimate[row i of group g] = grad_scale * grad_loss[. * grad_loss_stride] * dl/de_i for the
  * pairing the forward chose (perm NULL: identity).  grad_loss indexes examples (pit) or rows
  * (pit == 0); stride 0 broadcasts one upstream value (the gradient of a batch mean: scale 1/B).    */

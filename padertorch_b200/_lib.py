@@ -53,6 +53,9 @@ SIGNATURES = {
                               c_void, c_void, c_void]),
     'b2s_pair_loss_set': (c_int, [c_void, c_void, c_i64, c_i64, c_int, c_int, ctypes.POINTER(c_int),
                                   ctypes.POINTER(c_int), c_int, c_dbl, c_void, c_void, c_void, c_void]),
+    'b2s_pair_stats_loss_set': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64, c_int,
+                                        ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_dbl, c_void, c_void,
+                                        c_void, c_void, c_void, c_void]),
     'b2s_pair_backward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_i64, c_i64,
                                   c_void, c_int, c_int, c_dbl, c_int, c_int, c_void, c_void, c_i64,
                                   c_dbl, c_void, c_void]),

@@ -423,6 +423,166 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
   dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
 }
 
+// ------------------------------------------------------------------------------------------- ring form of the frame kernel
+// dc_gram_frame_kernel pays for two things its arithmetic does not need: (1) its six warps carry unequal work (a
+// diagonal block is 20 packed products per step, an off-diagonal one 32) and meet at a block barrier after EVERY
+// frame, and (2) each block pair loads its own 16 operand rows (96 LDS per 32 bins and CTA).  Here a warp owns one
+// diagonal block AND the off-diagonal block that shares its row block -- (0,0)+(0,1), (1,1)+(1,2), (2,2)+(2,0): 52
+// packed products per step for every warp, 16 operand loads for both blocks (48 LDS per 32 bins) -- and four such
+// role triples (12 warps, one CTA per SM) share the 32-bin steps of the frames round robin over a running step
+// counter, so all warps carry the same work whatever the number of bins.  Frames travel through a ring of four
+// whole-frame stages (TMA bulk copies as above, `full` mbarrier per stage); a warp releases a stage by one arrival
+// on the stage's `empty` mbarrier and runs on; no block barrier exists in the frame loop.  Warp 0 refills the
+// stage of frame f - 1 with frame f + 3 when it starts frame f (three frames of slack for everyone else).
+constexpr int kRgGroups = 4, kRgWarps = 3 * kRgGroups, kRgStages = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
+}
+
+// One 32-bin step of the blocks (BA, BA) [upper triangle] and (BA, BB).
+template <int FT, int ET, int KT, int BA, int BB>
+__device__ __forceinline__ void gram_ring_step(const float* be_, const float* bt_, const float* zrow, int F, int E,
+                                               int C, int off, float2 (&accd)[BS][BS / 2], float2 (&acco)[BS][BS / 2]) {
+  auto row = [&](int ch) -> const float* {
+    return (ch < E ? be_ + ch * F : (ch < C ? bt_ + (ch - E) * F : zrow)) + off;
+  };
+  float va[BS];
+  float2 vb[BS / 2];
+#pragma unroll
+  for (int i = 0; i < BS; ++i) va[i] = row(BA * BS + i)[0];
+#pragma unroll
+  for (int jj = 0; jj < BS / 2; ++jj) vb[jj] = make_float2(row(BB * BS + 2 * jj)[0], row(BB * BS + 2 * jj + 1)[0]);
+#pragma unroll
+  for (int i = 0; i < BS; ++i) {
+#pragma unroll
+    for (int jj = i / 2; jj < BS / 2; ++jj)
+      accd[i][jj] = rf::fma2(rf::bcast(va[i]), make_float2(va[2 * jj], va[2 * jj + 1]), accd[i][jj]);
+#pragma unroll
+    for (int jj = 0; jj < BS / 2; ++jj) acco[i][jj] = rf::fma2(rf::bcast(va[i]), vb[jj], acco[i][jj]);
+  }
+}
+
+template <int FT, int ET, int KT>
+__global__ void __launch_bounds__(32 * kRgWarps, 1)
+dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
+                    const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
+                    int K_rt, double* __restrict__ partial, int* __restrict__ counters,
+                    double* __restrict__ gram, float* __restrict__ loss) {
+  extern __shared__ __align__(16) float fsm[];   // [kRgStages][area_e + area_t] frame stages, then a row of zeros
+  __shared__ __align__(8) uint64_t full[kRgStages], empty[kRgStages];
+  const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
+  const int b = blockIdx.x, chunk = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = E + K;
+  const int area_e = frame_area(E, F), area_t = frame_area(K, F), buf_floats = area_e + area_t;
+  float* zrow = fsm + kRgStages * buf_floats;
+  const int64_t T = meta[b * B2S_DC_META + 0];
+  const float* e_ = emb + meta[b * B2S_DC_META + 1];
+  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  const int64_t N = T * F;
+  const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
+  const int n = t1 - t0;
+  for (int i = threadIdx.x; i < (F + 31) / 32 * 32; i += blockDim.x) zrow[i] = 0.f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kRgStages; ++s) {
+      tma::mbar_init(&full[s], 1);
+      tma::mbar_init(&empty[s], kRgWarps);
+    }
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t, int s) {   // one lane
+    const uintptr_t ae = reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t);
+    const uintptr_t at = reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t);
+    const unsigned be = (unsigned)(((ae & 15) + (size_t)E * F * 4 + 15) & ~(size_t)15);
+    const unsigned bt = (unsigned)(((at & 15) + (size_t)K * F * 4 + 15) & ~(size_t)15);
+    tma::fence_proxy_async();   // the stage was last read through the generic proxy
+    tma::mbar_expect_tx(&full[s], be + bt);
+    tma::bulk_g2s(fsm + s * buf_floats, reinterpret_cast<const void*>(ae & ~(uintptr_t)15), be, &full[s]);
+    tma::bulk_g2s(fsm + s * buf_floats + area_e, reinterpret_cast<const void*>(at & ~(uintptr_t)15), bt, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int f = 0; f < kRgStages && f < n; ++f) issue(t0 + f, f);
+  }
+  const int role = warp % 3, group = warp / 3;
+  float2 accd[BS][BS / 2], acco[BS][BS / 2];
+#pragma unroll
+  for (int i = 0; i < BS; ++i)
+#pragma unroll
+    for (int j = 0; j < BS / 2; ++j) { accd[i][j] = make_float2(0.f, 0.f); acco[i][j] = make_float2(0.f, 0.f); }
+
+  const int full_steps = F / 32;
+  const bool tail = (F & 31) != 0;
+  const int nsteps = full_steps + (tail ? 1 : 0);
+  int first = group;   // this warp's first step of the current frame: (f * nsteps + j) % kRgGroups == group
+  for (int f = 0; f < n; ++f) {
+    const int s = f & (kRgStages - 1);
+    if (warp == 0 && f >= 1 && f + kRgStages - 1 < n) {
+      if (lane == 0) {
+        const int r = (f - 1) & (kRgStages - 1);
+        tma::mbar_wait(&empty[r], (unsigned)((f - 1) / kRgStages) & 1u);
+        issue(t0 + f + kRgStages - 1, r);
+      }
+      __syncwarp();
+    }
+    tma::mbar_wait(&full[s], (unsigned)(f / kRgStages) & 1u);
+    const int64_t t = t0 + f;
+    const float* be_ = fsm + s * buf_floats + (int)((reinterpret_cast<uintptr_t>(e_ + t * se_t) & 15) >> 2) + lane;
+    const float* bt_ = fsm + s * buf_floats + area_e + (int)((reinterpret_cast<uintptr_t>(t_ + t * st_t) & 15) >> 2) + lane;
+    const float* z_ = zrow + lane;
+    // this warp's steps of the frame: first, first + 4, ... (whole rounds unrolled: the next step's operand loads
+    // overlap the current step's products), then the F % 32 last bins if that step is this warp's
+    auto frame_steps = [&](auto stepf) {
+      const int rounds = full_steps / kRgGroups;
+#pragma unroll 4
+      for (int q = 0; q < rounds; ++q) stepf(32 * (first + kRgGroups * q));
+      const int j = first + kRgGroups * rounds;
+      if (j < full_steps) stepf(32 * j);
+      if (tail && (full_steps - first) % kRgGroups == 0 && lane + 32 * full_steps < F) stepf(32 * full_steps);
+    };
+    switch (role) {   // warp-uniform
+      case 0: frame_steps([&](int off) { gram_ring_step<FT, ET, KT, 0, 1>(be_, bt_, z_, F, E, C, off, accd, acco); }); break;
+      case 1: frame_steps([&](int off) { gram_ring_step<FT, ET, KT, 1, 2>(be_, bt_, z_, F, E, C, off, accd, acco); }); break;
+      default: frame_steps([&](int off) { gram_ring_step<FT, ET, KT, 2, 0>(be_, bt_, z_, F, E, C, off, accd, acco); }); break;
+    }
+    first = (first + kRgGroups * nsteps - nsteps) % kRgGroups;   // (group - (f + 1) * nsteps) mod kRgGroups
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  __syncthreads();   // every stage has been consumed by every warp: the stages are free for the reduction
+  // Each warp reduces its 2 x 64 sums (transposed: lane l ends up with entries l and 32 + l of either block); the four
+  // groups' sums meet in shared memory and are folded in group order.
+  float* red = fsm;   // [kRgGroups][3 roles][4][32]
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int i = (32 * (q & 1) + e) / BS, jx = (32 * (q & 1) + e) % BS;
+      const float2 a = q < 2 ? accd[i][jx / 2] : acco[i][jx / 2];
+      v[e] = (jx & 1) ? a.y : a.x;
+    }
+    red[((group * 3 + role) * 4 + q) * 32 + lane] = warp_transpose_sum32(v, lane);
+  }
+  __syncthreads();
+  double* mine = partial + ((int64_t)b * nchunks + chunk) * kTC * kTC;
+  {
+    const int r = warp % 3, q = (warp / 3);   // thread = (role r, quarter q, lane): 3 x 4 x 32 = blockDim
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < kRgGroups; ++g) sum += (double)red[((g * 3 + r) * 4 + q) * 32 + lane];
+    const int ba = r, bb = q < 2 ? r : (r + 1) % 3;
+    const int i = (32 * (q & 1) + lane) / BS, jx = (32 * (q & 1) + lane) % BS;
+    if (!(q < 2 && jx < i)) {   // the lower triangle of a diagonal block is its mirror image
+      mine[(ba * BS + i) * kTC + bb * BS + jx] = sum;
+      mine[(bb * BS + jx) * kTC + ba * BS + i] = sum;
+    }
+  }
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
+}
+
 // grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
 // Thread = 2 points x one block of 8 output channels; the coefficient matrix sits in shared memory.
 __global__ void __launch_bounds__(256)
@@ -762,6 +922,27 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
       B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       B2S_CUDA(cudaFuncSetAttribute(dc_gram_frame_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured[dev & 63] = true;
+    }
+    // ring form: one CTA of 12 warps per SM, four whole-frame stages (B2S_DC_RING=0: the six-warp kernel below)
+    static const bool ring = [] { const char* e = getenv("B2S_DC_RING"); return e ? atoi(e) != 0 : true; }();
+    const size_t ring_smem = sizeof(float) * (kRgStages * (frame_area(embedding_dim, (int)bins) + frame_area(sources, (int)bins)) +
+                                             (bins + 31) / 32 * 32);
+    if (ring && ring_smem <= 200 * 1024) {
+      static bool ring_configured[64] = {};
+      if (!ring_configured[dev & 63]) {
+        B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ring_configured[dev & 63] = true;
+      }
+      int rchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 8),
+                                                               (int64_t)kNumSMs / std::max<int64_t>(1, batch)));
+      rchunks = std::min(rchunks, g.nchunks);
+      auto rkernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_gram_ring_kernel<513, 20, 2>
+                                                                        : dc_gram_ring_kernel<0, 0, 0>;
+      rkernel<<<dim3((unsigned)batch, rchunks), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
+          embedding, target, meta, se.t, st.t, rchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss);
+      B2S_LAUNCH_CHECK("dc_gram_ring_kernel");
+      return B2S_OK;
     }
     // frames are split over about two CTAs per SM (each double-buffers whole frames)
     int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 4),

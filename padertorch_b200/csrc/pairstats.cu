@@ -23,6 +23,80 @@ namespace {
 constexpr int kStatsThreads = 256;
 constexpr double kLn10 = 2.302585092994045684;
 
+// A set of PIT losses evaluated from the statistics (b2s_pair_loss_set), and the same set evaluated INSIDE the
+// statistics kernel by the CTA that folds an example's chunks (b2s_pair_stats_loss_set: one launch for TasNet.loss).
+struct LossSet { int n; int kind[B2S_MAX_LOSS_SET]; int reduction[B2S_MAX_LOSS_SET]; };
+struct FusedLossSet {
+  LossSet set;            // set.n == 0: statistics only
+  int flags;
+  double tau;
+  float* loss;            // [n][examples]
+  int32_t* perm;          // [n][examples][K]
+  float* mean;            // [n]
+  int* done;              // ticket of finished examples (zero between calls)
+  int64_t examples;
+};
+// Value of one pair loss and its partial derivatives w.r.t. the estimate-side statistics.
+struct PairEval { double value, dEe, dD, dSe; };
+
+__device__ inline PairEval eval_pair(int kind, int flags, double tau, double T, double Ee, double D,
+                                     double Tt, double Se, double St) {
+  PairEval r;
+  r.dSe = 0.0;
+  const bool offset = (flags & B2S_FLAG_OFFSET_INVARIANT) != 0;
+  const double Se0 = Se, St0 = St;
+  if (offset) {  // statistics of the mean-removed signals
+    Ee -= Se * Se / T;
+    D -= Se * St / T;
+    Tt -= St * St / T;
+  }
+  switch (kind) {
+    case B2S_LOSS_MSE: {
+      r.value = (Ee - 2.0 * D + Tt) / T;
+      r.dEe = 1.0 / T; r.dD = -2.0 / T;
+    } break;
+    case B2S_LOSS_LOG_MSE: {
+      double m = (Ee - 2.0 * D + Tt) / T;
+      if (tau >= 0.0) m += tau * Tt / T;
+      r.value = log10(m);
+      const double dm = 1.0 / (m * kLn10);
+      r.dEe = dm / T; r.dD = -2.0 * dm / T;
+    } break;
+    case B2S_LOSS_LOG1P_MSE: {
+      const double m = (Ee - 2.0 * D + Tt) / T;
+      r.value = log10(1.0 + m);
+      const double dm = 1.0 / ((1.0 + m) * kLn10);
+      r.dEe = dm / T; r.dD = -2.0 * dm / T;
+    } break;
+    case B2S_LOSS_SDR: {
+      double den = Ee - 2.0 * D + Tt;
+      if (tau >= 0.0) den += tau * Tt;
+      r.value = -10.0 * log10(Tt / den);
+      const double dden = 10.0 / (kLn10 * den);
+      r.dEe = dden; r.dD = -2.0 * dden;
+    } break;
+    default: {  // B2S_LOSS_SI_SDR
+      const double alpha = D / Tt;
+      const double sig = alpha * alpha * Tt;
+      const double noise = Ee - 2.0 * alpha * D + alpha * alpha * Tt;
+      const double den = tau >= 0.0 ? noise + tau * sig : noise;
+      r.value = -10.0 * log10(sig / den);
+      const double dnoise = 10.0 / (kLn10 * den);
+      r.dEe = dnoise;
+      if (flags & B2S_FLAG_GRAD_STOP) {
+        r.dD = -2.0 * alpha * dnoise;
+      } else {
+        // sig = D^2/Tt, noise = Ee - D^2/Tt
+        const double dsig = -10.0 / kLn10 * (1.0 / sig - (tau >= 0.0 ? tau / den : 0.0));
+        r.dD = 2.0 * alpha * (dsig - dnoise);
+      }
+    } break;
+  }
+  if (offset) r.dSe = r.dEe * (-2.0 * Se0 / T) + r.dD * (-St0 / T);
+  return r;
+}
+
+
 __host__ __device__ inline int stats_per_group(int K) { return K * K + 4 * K; }
 
 int pair_chunks(int64_t groups, int64_t max_length) {
@@ -36,11 +110,37 @@ int pair_chunks(int64_t groups, int64_t max_length) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(c, most));
 }
 
+// The K! assignments of one K x K cost matrix in itertools order; the first minimum wins (source_separation.py:112-119).
 template <int K>
-__global__ void __launch_bounds__(kStatsThreads)
+__device__ __forceinline__ double best_assignment(const double* cost, int (&bp)[K]) {
+  int p[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = k; bp[k] = k; }
+  double best = 0.0;
+  int idx = 0;
+  do {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) if (p[k] == i) v += cost[i * K + k];
+    }
+    if (idx == 0 || candidate_better(v, idx, best, 0)) {   // strictly better only
+      best = v;
+#pragma unroll
+      for (int k = 0; k < K; ++k) bp[k] = p[k];
+    }
+    ++idx;
+  } while (next_permutation(p, K));
+  return best;
+}
+
+template <int K, bool PIPE>
+__global__ void __launch_bounds__(kStatsThreads, K <= 4 ? 2 : 1)
 pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
                   const int64_t* __restrict__ meta, int nchunks, int64_t est_stride, int64_t tgt_stride,
-                  double* __restrict__ partial, int* __restrict__ counters, double* __restrict__ stats) {
+                  double* __restrict__ partial, int* __restrict__ counters, double* __restrict__ stats,
+                  const FusedLossSet f) {
   constexpr int NV = K * K + 4 * K;
   __shared__ double sm[NV * (kStatsThreads / 32)];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent (the loss-set kernel) may be scheduled
@@ -92,6 +192,43 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
       fold(a, b);
     };
     int64_t v = v0 + threadIdx.x;
+    if constexpr (PIPE && K <= 2) {
+      // software pipeline over units of two 16-byte loads per row: the NEXT unit's 4K loads are issued before the
+      // current unit is folded, so every thread keeps 4K loads in flight through the fp64 arithmetic as well
+      float4 ea[K], ta[K], eb[K], tb[K];
+      bool have = v + kStatsThreads < v1;
+      if (have) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          ea[i] = __ldg(e4 + i * es4 + v);
+          ta[i] = __ldg(t4 + i * ts4 + v);
+          eb[i] = __ldg(e4 + i * es4 + v + kStatsThreads);
+          tb[i] = __ldg(t4 + i * ts4 + v + kStatsThreads);
+        }
+      }
+      while (have) {
+        const int64_t vn = v + 2 * kStatsThreads;
+        const bool more = vn + kStatsThreads < v1;
+        float4 na[K], nta[K], nb[K], ntb[K];
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            na[i] = __ldg(e4 + i * es4 + vn);
+            nta[i] = __ldg(t4 + i * ts4 + vn);
+            nb[i] = __ldg(e4 + i * es4 + vn + kStatsThreads);
+            ntb[i] = __ldg(t4 + i * ts4 + vn + kStatsThreads);
+          }
+        }
+        fold4(ea, ta);
+        fold4(eb, tb);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) { ea[i] = na[i]; ta[i] = nta[i]; eb[i] = nb[i]; tb[i] = ntb[i]; }
+        }
+        v = vn;
+        have = more;
+      }
+    }
     for (; K <= 3 && v + kStatsThreads < v1; v += 2 * kStatsThreads) {   // (register budget: K <= 3 only)
       float4 ea[K], ta[K], eb[K], tb[K];
 #pragma unroll
@@ -172,8 +309,47 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
     const volatile double* p = partial + (int64_t)g * nchunks * NV + i;
     for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
     stats[(int64_t)g * NV + i] = s;
+    sm[i] = s;
   }
   if (threadIdx.x == 0) counters[g] = 0;
+  if constexpr (K <= 4) {
+    // b2s_pair_stats_loss_set (inner == 1): the CTA that folded the example evaluates the loss set from the
+    // statistics it holds; the CTA that finishes the LAST example folds the batch means -- one launch in all
+    if (f.set.n == 0) return;
+    constexpr int KK = K * K;
+    __shared__ double cost_sm[B2S_MAX_LOSS_SET * KK];
+    __syncthreads();
+    if ((int)threadIdx.x < f.set.n * KK) {
+      const int which = threadIdx.x / KK, ij = threadIdx.x - which * KK;
+      const int ci = ij / K, cj = ij - ci * K;
+      cost_sm[threadIdx.x] = eval_pair(f.set.kind[which], f.flags, f.tau, (double)T, sm[KK + ci], sm[ci * K + cj],
+                                       sm[KK + K + cj], sm[KK + 2 * K + ci], sm[KK + 3 * K + cj]).value;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < f.set.n) {
+      const int which = threadIdx.x;
+      int bp[K];
+      double best = best_assignment<K>(cost_sm + which * KK, bp);
+      if (f.set.reduction[which] == B2S_REDUCE_MEAN) best /= (double)K;
+      f.loss[which * f.examples + g] = (float)best;
+#pragma unroll
+      for (int k = 0; k < K; ++k) f.perm[(which * f.examples + g) * K + k] = bp[k];
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(f.done, 1) == (int)f.examples - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp < f.set.n) {   // batch means, fixed order: lane-strided partial sums folded by the warp tree
+      const volatile float* row = f.loss + warp * f.examples;
+      double local = 0.0;
+      for (int64_t ex = lane; ex < f.examples; ex += 32) local += (double)row[ex];
+      local = warp_sum(local);
+      if (lane == 0) f.mean[warp] = (float)(local / (double)f.examples);
+    }
+    if (threadIdx.x == 0) *f.done = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------- segment-staged statistics
@@ -340,65 +516,6 @@ pair_stats_seg_kernel(const float* __restrict__ est, const float* __restrict__ t
   if (g_cur >= 0) flush(g_cur);
 }
 
-// Value of one pair loss and its partial derivatives w.r.t. the estimate-side statistics.
-struct PairEval { double value, dEe, dD, dSe; };
-
-__device__ inline PairEval eval_pair(int kind, int flags, double tau, double T, double Ee, double D,
-                                     double Tt, double Se, double St) {
-  PairEval r;
-  r.dSe = 0.0;
-  const bool offset = (flags & B2S_FLAG_OFFSET_INVARIANT) != 0;
-  const double Se0 = Se, St0 = St;
-  if (offset) {  // statistics of the mean-removed signals
-    Ee -= Se * Se / T;
-    D -= Se * St / T;
-    Tt -= St * St / T;
-  }
-  switch (kind) {
-    case B2S_LOSS_MSE: {
-      r.value = (Ee - 2.0 * D + Tt) / T;
-      r.dEe = 1.0 / T; r.dD = -2.0 / T;
-    } break;
-    case B2S_LOSS_LOG_MSE: {
-      double m = (Ee - 2.0 * D + Tt) / T;
-      if (tau >= 0.0) m += tau * Tt / T;
-      r.value = log10(m);
-      const double dm = 1.0 / (m * kLn10);
-      r.dEe = dm / T; r.dD = -2.0 * dm / T;
-    } break;
-    case B2S_LOSS_LOG1P_MSE: {
-      const double m = (Ee - 2.0 * D + Tt) / T;
-      r.value = log10(1.0 + m);
-      const double dm = 1.0 / ((1.0 + m) * kLn10);
-      r.dEe = dm / T; r.dD = -2.0 * dm / T;
-    } break;
-    case B2S_LOSS_SDR: {
-      double den = Ee - 2.0 * D + Tt;
-      if (tau >= 0.0) den += tau * Tt;
-      r.value = -10.0 * log10(Tt / den);
-      const double dden = 10.0 / (kLn10 * den);
-      r.dEe = dden; r.dD = -2.0 * dden;
-    } break;
-    default: {  // B2S_LOSS_SI_SDR
-      const double alpha = D / Tt;
-      const double sig = alpha * alpha * Tt;
-      const double noise = Ee - 2.0 * alpha * D + alpha * alpha * Tt;
-      const double den = tau >= 0.0 ? noise + tau * sig : noise;
-      r.value = -10.0 * log10(sig / den);
-      const double dnoise = 10.0 / (kLn10 * den);
-      r.dEe = dnoise;
-      if (flags & B2S_FLAG_GRAD_STOP) {
-        r.dD = -2.0 * alpha * dnoise;
-      } else {
-        // sig = D^2/Tt, noise = Ee - D^2/Tt
-        const double dsig = -10.0 / kLn10 * (1.0 / sig - (tau >= 0.0 ? tau / den : 0.0));
-        r.dD = 2.0 * alpha * (dsig - dnoise);
-      }
-    } break;
-  }
-  if (offset) r.dSe = r.dEe * (-2.0 * Se0 / T) + r.dD * (-St0 / T);
-  return r;
-}
 
 // one CTA per example (= `inner` consecutive groups)
 __global__ void __launch_bounds__(128)
@@ -462,8 +579,6 @@ pair_loss_kernel(const double* __restrict__ stats, const int64_t* __restrict__ m
 // Several PIT losses of the same statistics in ONE launch, plus their batch means (TasNet.loss evaluates
 // three loss functions per step and averages each over the batch: 3 x (loss kernel + mean kernel) otherwise).
 // CTA = loss kind; thread = example (K <= 4: the K! <= 24 assignments are walked serially in itertools order).
-struct LossSet { int n; int kind[B2S_MAX_LOSS_SET]; int reduction[B2S_MAX_LOSS_SET]; };
-
 template <int K>
 __global__ void __launch_bounds__(256)
 pair_loss_set_kernel(const double* __restrict__ stats, const int64_t* __restrict__ meta, int64_t examples,
@@ -497,26 +612,8 @@ pair_loss_set_kernel(const double* __restrict__ stats, const int64_t* __restrict
     }
     __syncthreads();
     if (on && ij == 0) {
-      const double* cost = cost_sm + te * KK;
-      int p[K], bp[K];
-#pragma unroll
-      for (int k = 0; k < K; ++k) { p[k] = k; bp[k] = k; }
-      double best = 0.0;
-      int idx = 0;
-      do {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-#pragma unroll
-          for (int i = 0; i < K; ++i) if (p[k] == i) v += cost[i * K + k];
-        }
-        if (idx == 0 || candidate_better(v, idx, best, 0)) {   // strictly better only: the first minimum wins
-          best = v;
-#pragma unroll
-          for (int k = 0; k < K; ++k) bp[k] = p[k];
-        }
-        ++idx;
-      } while (next_permutation(p, K));
+      int bp[K];
+      double best = best_assignment<K>(cost_sm + te * KK, bp);
       if (reduction == B2S_REDUCE_MEAN) best /= (double)(K * inner);
       const float out = (float)best;
       loss[which * examples + ex] = out;
@@ -810,10 +907,15 @@ int64_t b2s_pair_workspace_bytes(int64_t groups, int64_t max_length, int sources
   return kTicketBytes + (int64_t)sizeof(double) * groups * chunks * stats_per_group(sources) + 16;
 }
 
-int b2s_pair_stats_forward(const float* estimate, const float* target, const int64_t* meta,
-                           int64_t groups, int64_t max_length, int sources,
-                           int64_t estimate_source_stride, int64_t target_source_stride, double* stats,
-                           void* workspace, b2s_stream stream) {
+}  // extern "C"
+
+namespace {
+// The statistics pass; `fused` (may be NULL) asks the (group, chunk) kernel to evaluate a loss set in the same launch.
+// Returns through `*fused_done` whether it did (the segment-staged kernel and K > 4 do not).
+int pair_stats_launch(const float* estimate, const float* target, const int64_t* meta,
+                      int64_t groups, int64_t max_length, int sources,
+                      int64_t estimate_source_stride, int64_t target_source_stride, double* stats,
+                      void* workspace, b2s_stream stream, const FusedLossSet* fused, bool* fused_done) {
   B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
               "sources=%d outside the supported range 1..%d", sources, B2S_MAX_SOURCES);
   B2S_REQUIRE(groups >= 0 && groups <= kMaxTickets && max_length >= 0, "bad extents (groups=%lld)",
@@ -861,8 +963,20 @@ int b2s_pair_stats_forward(const float* estimate, const float* target, const int
     return B2S_OK;
   }
   const dim3 grid((unsigned)groups, chunks);
-#define CALL(K) pair_stats_kernel<K><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks, \
-      estimate_source_stride, target_source_stride, partial, counters, stats)
+  // B2S_PAIR_PIPE=0: the loop without the software pipeline (A/B measurements)
+  static const bool pipe = [] { const char* e = getenv("B2S_PAIR_PIPE"); return e ? atoi(e) != 0 : true; }();
+  FusedLossSet f = {};
+  if (fused && sources <= 4) {
+    f = *fused;
+    f.done = counters + (kMaxTickets - 1);
+    *fused_done = true;
+  }
+#define CALL(K) do {                                                                                           \
+    if (pipe) pair_stats_kernel<K, true><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks,        \
+        estimate_source_stride, target_source_stride, partial, counters, stats, f);                             \
+    else pair_stats_kernel<K, false><<<grid, kStatsThreads, 0, st>>>(estimate, target, meta, chunks,            \
+        estimate_source_stride, target_source_stride, partial, counters, stats, f);                             \
+  } while (0)
   switch (sources) {
     case 1: CALL(1); break;
     case 2: CALL(2); break;
@@ -876,6 +990,17 @@ int b2s_pair_stats_forward(const float* estimate, const float* target, const int
 #undef CALL
   B2S_LAUNCH_CHECK("pair_stats_kernel");
   return B2S_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b2s_pair_stats_forward(const float* estimate, const float* target, const int64_t* meta,
+                           int64_t groups, int64_t max_length, int sources,
+                           int64_t estimate_source_stride, int64_t target_source_stride, double* stats,
+                           void* workspace, b2s_stream stream) {
+  return pair_stats_launch(estimate, target, meta, groups, max_length, sources, estimate_source_stride,
+                           target_source_stride, stats, workspace, stream, nullptr, nullptr);
 }
 
 int b2s_pair_loss(const double* stats, const int64_t* meta, int64_t groups, int64_t inner, int sources,
@@ -948,6 +1073,40 @@ int b2s_pair_loss_set(const double* stats, const int64_t* meta, int64_t groups, 
     B2S_LAUNCH_CHECK("row_mean_kernel");
   }
   return B2S_OK;
+}
+
+int b2s_pair_stats_loss_set(const float* estimate, const float* target, const int64_t* meta, int64_t groups,
+                            int64_t max_length, int sources, int64_t estimate_source_stride,
+                            int64_t target_source_stride, int count, const int* kinds, const int* reductions,
+                            int flags, double tau, double* stats, float* loss, int32_t* perm, float* mean,
+                            void* workspace, b2s_stream stream) {
+  B2S_REQUIRE(count >= 1 && count <= B2S_MAX_LOSS_SET && kinds && reductions, "1..%d loss kinds per set (got %d)",
+              B2S_MAX_LOSS_SET, count);
+  B2S_REQUIRE(groups < kMaxTickets, "too many groups (%lld)", (long long)groups);
+  FusedLossSet f = {};
+  f.set.n = count;
+  for (int i = 0; i < count; ++i) {
+    B2S_REQUIRE(kinds[i] >= B2S_LOSS_MSE && kinds[i] < B2S_LOSS_SA_SDR, "loss kind %d has no PIT variant", kinds[i]);
+    B2S_REQUIRE(reductions[i] == B2S_REDUCE_SUM || reductions[i] == B2S_REDUCE_MEAN, "PIT needs reduction sum or mean");
+    B2S_REQUIRE(!(flags & B2S_FLAG_OFFSET_INVARIANT) || kinds[i] == B2S_LOSS_SI_SDR,
+                "offset_invariant exists for si_sdr only");
+    f.set.kind[i] = kinds[i];
+    f.set.reduction[i] = reductions[i];
+  }
+  if (groups == 0) return B2S_OK;
+  B2S_REQUIRE(loss && perm && mean, "NULL device pointer");
+  f.flags = flags;
+  f.tau = tau;
+  f.loss = loss;
+  f.perm = perm;
+  f.mean = mean;
+  f.examples = groups;
+  bool fused_done = false;
+  const int rc = pair_stats_launch(estimate, target, meta, groups, max_length, sources, estimate_source_stride,
+                                   target_source_stride, stats, workspace, stream, &f, &fused_done);
+  if (rc != B2S_OK || fused_done) return rc;
+  return b2s_pair_loss_set(stats, meta, groups, 1, sources, count, kinds, reductions, flags, tau, loss, perm, mean,
+                           stream);
 }
 
 int b2s_pair_backward(const float* estimate, const float* target, const int64_t* meta, int64_t groups,

@@ -1,6 +1,7 @@
 """Shared driver of the pair-statistics kernels (b2s_pair_stats_forward / b2s_pair_loss /
 b2s_pair_backward): every time-domain regression loss and its PIT variant goes through here."""
 import ctypes
+import os
 
 import torch
 
@@ -76,6 +77,35 @@ class PairProblem:
                                            _lib.ptr(perm), _lib.ptr(mean), _lib.stream_of(device))
             _lib.check(rc, 'b2s_pair_loss_set')
         return loss, perm, mean
+
+    def stats_loss_set(self, kinds, reductions, flags=0, tau=-1.0, one_launch=None):
+        """`stats()` + `loss_set()`: (stats, loss, perm, mean).  one_launch=True: b2s_pair_stats_loss_set (the CTA
+        that completes an example evaluates its losses, the last one the batch means).  Measured at batch 64 x 2 x
+        4 s: 22.6 us against 21.8 us for the two launches, whose second kernel is launched programmatically and
+        overlaps the tail of the first -- so two launches are the default (B2S_PAIR_ONE_LAUNCH=1 switches)."""
+        if one_launch is None:
+            one_launch = os.environ.get('B2S_PAIR_ONE_LAUNCH', '0') == '1'
+        if self.inner != 1 or not self.groups or not one_launch:
+            stats = self.stats()
+            return (stats,) + self.loss_set(stats, kinds, reductions, flags, tau)
+        lib = _lib.load()
+        device = self.estimate.device
+        n = len(kinds)
+        stats = torch.empty((self.groups, _stats_width(self.k)), dtype=torch.float64, device=device)
+        loss = torch.empty((n, self.groups), dtype=torch.float32, device=device)
+        perm = torch.empty((n, self.groups, self.k), dtype=torch.int32, device=device)
+        mean = torch.empty(n, dtype=torch.float32, device=device)
+        ws = workspace(device, lib.b2s_pair_workspace_bytes(self.groups, self.max_length, self.k), 'pair')
+        c_kinds = (ctypes.c_int * n)(*kinds)
+        c_reductions = (ctypes.c_int * n)(*reductions)
+        with torch.cuda.device(device):
+            rc = lib.b2s_pair_stats_loss_set(
+                _lib.ptr(self.estimate), _lib.ptr(self.target), _lib.ptr(self.meta), self.groups,
+                self.max_length, self.k, self.est_stride, self.tgt_stride, n, c_kinds, c_reductions, flags, tau,
+                _lib.ptr(stats), _lib.ptr(loss), _lib.ptr(perm), _lib.ptr(mean), _lib.ptr(ws),
+                _lib.stream_of(device))
+        _lib.check(rc, 'b2s_pair_stats_loss_set')
+        return stats, loss, perm, mean
 
     def backward(self, stats, kind, flags, tau, reduction, pit, perm, grad_loss, broadcast_scale=None):
         """broadcast_scale: `grad_loss` is ONE upstream value (the gradient of a batch mean) applied to

@@ -121,10 +121,9 @@ class _TasnetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, estimate, problem, names):
-        stats = problem.stats()
         kinds = [_TASNET_KINDS[name][0] for name in names]
         reductions = [_TASNET_KINDS[name][1] for name in names]
-        _, perms, means = problem.loss_set(stats, kinds, reductions)   # two launches for the whole forward
+        stats, _, perms, means = problem.stats_loss_set(kinds, reductions)   # two launches (or one: _pairs.py)
         ctx.problem, ctx.stats, ctx.perms, ctx.names = problem, stats, perms, names
         ctx.set_materialize_grads(False)   # losses without a weight get no backward pass
         return tuple(means[i] for i in range(len(names)))

@@ -445,6 +445,41 @@ def test_tasnet_losses_more_sources(b2s, K):
         assert float(grad[b, :, n:].abs().max()) == 0.0 if n < T else True
 
 
+@pytest.mark.parametrize('K,B,T,aligned', [(2, 64, 64000, True), (2, 5, 3001, True), (3, 7, 4096, True),
+                                          (4, 3, 2500, True), (2, 6, 3001, False), (5, 4, 1999, True),
+                                          (1, 9, 1200, True)])
+def test_pair_stats_loss_set_one_launch(b2s, K, B, T, aligned):
+    """b2s_pair_stats_loss_set (statistics + loss set + batch means in ONE launch) == b2s_pair_stats_forward followed by
+    b2s_pair_loss_set: identical statistics, losses and permutations, repeated calls (the tickets return to zero),
+    ragged lengths, rows that take the internal two-launch route (unaligned, K > 4)."""
+    from padertorch_b200 import _lib
+    from padertorch_b200._workspace import meta_tensor
+    from padertorch_b200.ops.losses import _pairs
+    g = torch.Generator(device='cpu').manual_seed(K * 1000 + B)
+    length = T if aligned else T + 1
+    s = torch.randn(B, K, length, generator=g).to(dev())
+    est = (s.flip(1) + 0.5 * torch.randn(B, K, length, generator=g).to(dev()))
+    if not aligned:   # rows start at odd float offsets
+        s, est = s[..., 1:], est[..., 1:]
+        assert s.data_ptr() % 16 != 0
+    num = [T - (37 * b) % (T // 3) for b in range(B)]
+    num[0] = T
+    stride_e, stride_t = est.stride(1), s.stride(1)
+    rows = [[num[b], b * est.stride(0), b * s.stride(0)] for b in range(B)]
+    meta = meta_tensor(rows, est.device)
+    problem = _pairs.PairProblem(est, s, meta, B, 1, K, max(num), stride_e, stride_t)
+    kinds = [_lib.LOSS_SI_SDR, _lib.LOSS_LOG_MSE, _lib.LOSS_LOG1P_MSE, _lib.LOSS_MSE, _lib.LOSS_SDR]
+    reductions = [_lib.REDUCE_MEAN, _lib.REDUCE_SUM, _lib.REDUCE_SUM, _lib.REDUCE_MEAN, _lib.REDUCE_SUM]
+    stats2 = problem.stats()
+    loss2, perm2, mean2 = problem.loss_set(stats2, kinds, reductions)
+    for _ in range(3):
+        stats1, loss1, perm1, mean1 = problem.stats_loss_set(kinds, reductions, one_launch=True)
+        assert torch.equal(stats1, stats2)
+        assert torch.equal(loss1, loss2) and torch.equal(perm1, perm2)
+        torch.testing.assert_close(mean1, mean2, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(mean1, loss1.double().mean(1).float(), rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize('size,shift,T,K', [(1024, 256, 5000, 2), (1024, 256, 5001, 2), (1024, 256, 9000, 3),
                                            (1024, 256, 4100, 1), (1024, 512, 6000, 2), (512, 128, 3001, 3)])
 def test_prepare_pit_targets(b2s, size, shift, T, K):
