@@ -71,7 +71,8 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 
 __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int E, int64_t N,
                                           double* __restrict__ partial, int* __restrict__ counters,
-                                          double* __restrict__ gram, float* __restrict__ loss) {
+                                          double* __restrict__ gram, float* __restrict__ loss, int chunk_slots = 0) {
+  if (chunk_slots == 0) chunk_slots = nchunks;   // partial matrices reserved per example
   __threadfence();
   __syncthreads();
   __shared__ int s_last;
@@ -85,7 +86,7 @@ __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int
   for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
     const int r = idx / C, c = idx - r * C;
     double s = 0.0;
-    const volatile double* p = partial + (int64_t)b * nchunks * cp * cp + r * cp + c;
+    const volatile double* p = partial + (int64_t)b * chunk_slots * cp * cp + r * cp + c;
     for (int ch = 0; ch < nchunks; ++ch) s += p[(int64_t)ch * cp * cp];
     gram[(int64_t)b * C * C + idx] = s;
     const bool re = r < E, ce = c < E;
@@ -435,6 +436,79 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
 // on the stage's `empty` mbarrier and runs on; no block barrier exists in the frame loop.  Warp 0 refills the
 // stage of frame f - 1 with frame f + 3 when it starts frame f (three frames of slack for everyone else).
 constexpr int kRgGroups = 4, kRgWarps = 3 * kRgGroups, kRgStages = 4;
+// Length-balanced chunking of a ragged batch on a one-dimensional grid of P slots: the smallest chunk length L with
+// sum_b ceil(T_b / L) <= P is found by bisection between sum(T) / P and sum(T) / (P - B), example b is split into
+// n_b = ceil(T_b / L) equal chunks -- no CTA carries more than L frames whatever the spread of the lengths (a uniform
+// number of chunks per example makes the CTAs of the longest example 1.6 x the mean at lengths uniform in 2 .. 8 s),
+// and all chunks are resident in ONE wave.  The batch's meta rows are staged in shared memory on the way (the slot's
+// own row is read from there: one global round trip in all).  Every thread calls it; slots beyond sum(n_b) return
+// b = -1.  Needs B <= P, B <= kBalMaxBatch.
+constexpr int kBalMaxBatch = 160;
+struct ChunkSlot { int b, chunk, nchunks; int64_t row[B2S_DC_META]; };   // row: the example's meta row
+__device__ inline ChunkSlot balanced_chunk_slot(const int64_t* __restrict__ meta, int B, int P, int max_chunks, int slot) {
+  __shared__ int64_t s_meta[kBalMaxBatch * B2S_DC_META];
+  __shared__ ChunkSlot s_slot;
+  for (int i = threadIdx.x; i < B * B2S_DC_META; i += blockDim.x) s_meta[i] = meta[i];
+  if (threadIdx.x == 0) s_slot.b = -1;
+  bool same = true;   // this thread's lengths equal example 0's (every thread re-reads its own staged values only)
+  for (int b = threadIdx.x; b < B; b += blockDim.x) same = same && meta[(int64_t)b * B2S_DC_META] == meta[0];
+  if (__syncthreads_and(same)) {
+    // equal lengths (dense batches): closed form, no reductions -- L = ceil(T / floor(P / B))
+    const int T = (int)s_meta[0];
+    const int m = max(1, min(max_chunks, P / B));
+    const int L = max(8, (T + m - 1) / m);
+    const int n = max(1, min(max_chunks, (T + L - 1) / L));
+    ChunkSlot r;
+    r.b = slot / n;
+    r.chunk = slot - r.b * n;
+    r.nchunks = n;
+    if (r.b >= B) { r.b = -1; return r; }
+#pragma unroll
+    for (int i = 0; i < B2S_DC_META; ++i) r.row[i] = s_meta[r.b * B2S_DC_META + i];
+    return r;
+  }
+  if (threadIdx.x < 32) {   // warp 0
+    const int lane = threadIdx.x;
+    int tmax = 0;
+    long long tsum = 0;
+    for (int b = lane; b < B; b += 32) { const int T = (int)s_meta[b * B2S_DC_META]; tmax = max(tmax, T); tsum += T; }
+    for (int off = 16; off >= 1; off >>= 1) {
+      tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+      tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+    }
+    auto chunks_of = [&](int T, int L) { return max(1, min(max_chunks, (T + L - 1) / L)); };
+    // at least eight frames per chunk; sum ceil(T_b / L) >= sum(T) / L and <= sum(T) / L + B bound L from both sides
+    int lo = (int)max((long long)8, (tsum + P - 1) / P);
+    int hi = max(lo, P > B ? (int)min((long long)tmax, (tsum + P - B - 1) / (P - B)) : tmax);
+    while (lo < hi) {                // warp-uniform
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+      for (int b = lane; b < B; b += 32) cnt += chunks_of((int)s_meta[b * B2S_DC_META], mid);
+      for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      if (cnt <= P) hi = mid; else lo = mid + 1;
+    }
+    int base = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {   // running sum over the examples, 32 at a time
+      const int b = b0 + lane;
+      const int n = b < B ? chunks_of((int)s_meta[b * B2S_DC_META], lo) : 0;
+      int incl = n;
+      for (int off = 1; off < 32; off <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += up;
+      }
+      const int first = base + incl - n;
+      if (b < B && slot >= first && slot < first + n) {
+        s_slot.b = b; s_slot.chunk = slot - first; s_slot.nchunks = n;
+#pragma unroll
+        for (int i = 0; i < B2S_DC_META; ++i) s_slot.row[i] = s_meta[b * B2S_DC_META + i];
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+      if (base > slot) break;   // warp-uniform
+    }
+  }
+  __syncthreads();
+  return s_slot;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
@@ -466,33 +540,48 @@ __device__ __forceinline__ void gram_ring_step(const float* be_, const float* bt
 template <int FT, int ET, int KT>
 __global__ void __launch_bounds__(32 * kRgWarps, 1)
 dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
-                    const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
-                    int K_rt, double* __restrict__ partial, int* __restrict__ counters,
-                    double* __restrict__ gram, float* __restrict__ loss) {
+                    const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int batch, int balance_ctas,
+                    int chunk_slots, int F_rt, int E_rt, int K_rt, double* __restrict__ partial,
+                    int* __restrict__ counters, double* __restrict__ gram, float* __restrict__ loss) {
   extern __shared__ __align__(16) float fsm[];   // [kRgStages][area_e + area_t] frame stages, then a row of zeros
   __shared__ __align__(8) uint64_t full[kRgStages], empty[kRgStages];
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
-  const int b = blockIdx.x, chunk = blockIdx.y;
+  // balance_ctas != 0: one-dimensional grid, chunks per example in proportion to its length; else grid (batch, chunks)
+  {   // barriers and the row of zeros first: independent of the slot, visible after the barriers below
+    const int area = frame_area(E, F) + frame_area(K, F);
+    for (int i = threadIdx.x; i < (F + 31) / 32 * 32; i += blockDim.x) fsm[kRgStages * area + i] = 0.f;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < kRgStages; ++s) {
+        tma::mbar_init(&full[s], 1);
+        tma::mbar_init(&empty[s], kRgWarps);
+      }
+      tma::fence_mbar_init();
+    }
+  }
+  int b = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+  int64_t row[3];
+  if (balance_ctas) {
+    const ChunkSlot slot = balanced_chunk_slot(meta, batch, balance_ctas, chunk_slots, (int)blockIdx.x);
+    if (slot.b < 0) return;
+    b = slot.b; chunk = slot.chunk; nchunks = slot.nchunks;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) row[i] = slot.row[i];
+  } else {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 3; ++i) row[i] = meta[(int64_t)b * B2S_DC_META + i];
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = E + K;
   const int area_e = frame_area(E, F), area_t = frame_area(K, F), buf_floats = area_e + area_t;
   float* zrow = fsm + kRgStages * buf_floats;
-  const int64_t T = meta[b * B2S_DC_META + 0];
-  const float* e_ = emb + meta[b * B2S_DC_META + 1];
-  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
+  const int64_t T = row[0];
+  const float* e_ = emb + row[1];
+  const float* t_ = tgt + row[2];
   const int64_t N = T * F;
   const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
   const int n = t1 - t0;
-  for (int i = threadIdx.x; i < (F + 31) / 32 * 32; i += blockDim.x) zrow[i] = 0.f;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kRgStages; ++s) {
-      tma::mbar_init(&full[s], 1);
-      tma::mbar_init(&empty[s], kRgWarps);
-    }
-    tma::fence_mbar_init();
-  }
-  __syncthreads();
   auto issue = [&](int t, int s) {   // one lane
     const uintptr_t ae = reinterpret_cast<uintptr_t>(e_ + (int64_t)t * se_t);
     const uintptr_t at = reinterpret_cast<uintptr_t>(t_ + (int64_t)t * st_t);
@@ -567,7 +656,7 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
     red[((group * 3 + role) * 4 + q) * 32 + lane] = warp_transpose_sum32(v, lane);
   }
   __syncthreads();
-  double* mine = partial + ((int64_t)b * nchunks + chunk) * kTC * kTC;
+  double* mine = partial + ((int64_t)b * chunk_slots + chunk) * kTC * kTC;
   {
     const int r = warp % 3, q = (warp / 3);   // thread = (role r, quarter q, lane): 3 x 4 x 32 = blockDim
     double sum = 0.0;
@@ -580,7 +669,7 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
       mine[(bb * BS + jx) * kTC + ba * BS + i] = sum;
     }
   }
-  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss, chunk_slots);
 }
 
 // grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
@@ -750,16 +839,29 @@ constexpr int kFbOut = 5;
 // FT / ET / KT != 0: bins / embedding channels / sources known at compile time (the reference's deep-clustering
 // configuration 513 / 20 / 2): every shared-memory access of the inner loops becomes base register + immediate.
 template <int FT, int ET, int KT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(ET ? 64 * ((ET + kFbOut - 1) / kFbOut) : 320, 1)
 dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
-                         const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
+                         const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks_arg, int batch,
+                         int balance_ctas, int F_rt, int E_rt,
                          int K_rt, const double* __restrict__ gram, const float* __restrict__ grad_loss,
                          float* __restrict__ grad_emb) {
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
   extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] inputs, [2][area_o] outputs
   __shared__ __align__(8) uint64_t full[2];
   __shared__ float coef[kTC][kTC + 1];           // [c][e], zero padded
-  const int b = blockIdx.x, chunk = blockIdx.y;
+  // balance_ctas != 0: one-dimensional grid, chunks per example in proportion to its length (balanced_chunk_slot)
+  int b = blockIdx.x, chunk = blockIdx.y, nchunks = nchunks_arg;
+  int64_t row[4];
+  if (balance_ctas) {
+    const ChunkSlot slot = balanced_chunk_slot(meta, batch, balance_ctas, 1 << 30, (int)blockIdx.x);
+    if (slot.b < 0) return;
+    b = slot.b; chunk = slot.chunk; nchunks = slot.nchunks;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[i] = slot.row[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[i] = meta[(int64_t)b * B2S_DC_META + i];
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = E + K;
   const int groups = (E + kFbOut - 1) / kFbOut;   // blockDim = 64 * groups
@@ -767,10 +869,10 @@ dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict_
   const int area_e = frame_area(E, F), area_t = frame_area(K, F), buf_floats = area_e + area_t;
   const int area_o = frame_area(E, F);
   float* outs = fsm + 2 * buf_floats;
-  const int64_t T = meta[b * B2S_DC_META + 0];
-  const float* e_ = emb + meta[b * B2S_DC_META + 1];
-  const float* t_ = tgt + meta[b * B2S_DC_META + 2];
-  float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
+  const int64_t T = row[0];
+  const float* e_ = emb + row[1];
+  const float* t_ = tgt + row[2];
+  float* g_ = grad_emb + row[3];
   const int64_t N = T * F;
   const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
   const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
@@ -927,7 +1029,11 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
     static const bool ring = [] { const char* e = getenv("B2S_DC_RING"); return e ? atoi(e) != 0 : true; }();
     const size_t ring_smem = sizeof(float) * (kRgStages * (frame_area(embedding_dim, (int)bins) + frame_area(sources, (int)bins)) +
                                              (bins + 31) / 32 * 32);
-    if (ring && ring_smem <= 200 * 1024) {
+    // (the run-time-geometry instance of the ring kernel spills at its 168-register budget and measured SLOWER than
+    // the six-warp kernel: 67 vs 59 us at 257 bins, 112 vs 70 us at E = 16 / K = 3 -- compile-time geometry only)
+    const bool reference_geometry = bins == 513 && embedding_dim == 20 && sources == 2;
+    static const bool ring_any = getenv("B2S_DC_RING_ANY") != nullptr;
+    if (ring && (reference_geometry || ring_any) && ring_smem <= 200 * 1024) {
       static bool ring_configured[64] = {};
       if (!ring_configured[dev & 63]) {
         B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -939,8 +1045,17 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
       rchunks = std::min(rchunks, g.nchunks);
       auto rkernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_gram_ring_kernel<513, 20, 2>
                                                                         : dc_gram_ring_kernel<0, 0, 0>;
-      rkernel<<<dim3((unsigned)batch, rchunks), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
-          embedding, target, meta, se.t, st.t, rchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss);
+      // length-balanced chunks on a one-dimensional grid (B2S_DC_BALANCE=0: the same number of chunks per example)
+      static const bool balance = [] { const char* e = getenv("B2S_DC_BALANCE"); return e ? atoi(e) != 0 : true; }();
+      if (balance && batch <= kBalMaxBatch && batch <= kNumSMs) {
+        rkernel<<<dim3((unsigned)kNumSMs), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
+            embedding, target, meta, se.t, st.t, (int)batch, kNumSMs, g.nchunks, (int)bins, embedding_dim, sources,
+            partial, counters, gram, loss);
+      } else {
+        rkernel<<<dim3((unsigned)batch, rchunks), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
+            embedding, target, meta, se.t, st.t, (int)batch, 0, rchunks, (int)bins, embedding_dim, sources,
+            partial, counters, gram, loss);
+      }
       B2S_LAUNCH_CHECK("dc_gram_ring_kernel");
       return B2S_OK;
     }
@@ -996,8 +1111,15 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
                                                                    (int64_t)kNumSMs / std::max<int64_t>(1, batch)));
     auto kernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_backward_frame_kernel<513, 20, 2>
                                                                      : dc_backward_frame_kernel<0, 0, 0>;
-    kernel<<<dim3((unsigned)batch, nchunks), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
-        embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, gram, grad_loss, grad_embedding);
+    static const bool balance = [] { const char* e = getenv("B2S_DC_BALANCE"); return e ? atoi(e) != 0 : true; }();
+    if (balance && batch <= kBalMaxBatch && batch <= kNumSMs)
+      kernel<<<dim3((unsigned)kNumSMs), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
+          embedding, target, meta, se.t, st.t, 0, (int)batch, kNumSMs, (int)bins, embedding_dim, sources, gram, grad_loss,
+          grad_embedding);
+    else
+      kernel<<<dim3((unsigned)batch, nchunks), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
+          embedding, target, meta, se.t, st.t, nchunks, (int)batch, 0, (int)bins, embedding_dim, sources, gram, grad_loss,
+          grad_embedding);
     B2S_LAUNCH_CHECK("dc_backward_frame_kernel");
     return B2S_OK;
   }
