@@ -219,7 +219,7 @@ class Pit3:
 class Dc:
     name = 'dc'
     batch, e_dim, sources = 16, 20, 2
-    workload = ('deep-clustering affinity loss forward + backward (dc_gram_frame_kernel + dc_backward_frame_kernel), '
+    workload = ('deep-clustering affinity loss forward + backward (dc_gram_ring_kernel + dc_backward_frame_kernel, length-balanced chunks), '
                 'batch 16 of 2..8 s (lengths uniform in [32000, 128000] samples -> 128..503 frames x 513 bins), E = 20, '
                 "K = 2, embeddings in the model's 't e f' layout, binary target masks; embedding network excluded")
 
@@ -290,7 +290,7 @@ class Dc:
                  'h2d_bytes_per_step': sum(t.numel() * 4 for t in host[0][0] + host[0][1]), 'd2h_bytes_per_step': 4,
                  'steps': e2e_steps},
             gpu_launches=2 * args.steps,
-            roofline={'bound': 'hbm', 'kernel': 'dc_gram_frame_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            roofline={'bound': 'hbm', 'kernel': 'dc_gram_ring_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                       'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind, 'kernel_ms': fwd_ms,
                       'algorithmic_bytes_per_launch': fwd_b},
             step_roofline={'achieved': step_gbs, 'frac': step_gbs / peak, 'unit': 'GB/s',

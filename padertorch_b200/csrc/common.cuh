@@ -100,6 +100,22 @@ __device__ __forceinline__ void block_sum_to_smem(const float (&v)[NV], double* 
 }
 
 // Next lexicographic permutation in place (the order of itertools.permutations(range(K))).
+// p[0] + p[stride] + ... (n values) added in index order, four loads in flight (the values come from L2: one round
+// trip per four values instead of one per value -- the fold of the chunk partials is a serial tail of every launch)
+__device__ __forceinline__ double ordered_sum(const volatile double* p, int n, int64_t stride) {
+  double s = 0.0;
+  int c = 0;
+  for (; c + 4 <= n; c += 4) {
+    const double d0 = p[(int64_t)c * stride];
+    const double d1 = p[(int64_t)(c + 1) * stride];
+    const double d2 = p[(int64_t)(c + 2) * stride];
+    const double d3 = p[(int64_t)(c + 3) * stride];
+    s += d0; s += d1; s += d2; s += d3;
+  }
+  for (; c < n; ++c) s += p[(int64_t)c * stride];
+  return s;
+}
+
 __device__ __forceinline__ bool next_permutation(int* p, int K) {
   int i = K - 2;
   while (i >= 0 && p[i] > p[i + 1]) --i;

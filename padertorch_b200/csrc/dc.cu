@@ -85,9 +85,7 @@ __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int
   double local = 0.0;
   for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
     const int r = idx / C, c = idx - r * C;
-    double s = 0.0;
-    const volatile double* p = partial + (int64_t)b * chunk_slots * cp * cp + r * cp + c;
-    for (int ch = 0; ch < nchunks; ++ch) s += p[(int64_t)ch * cp * cp];
+    const double s = ordered_sum(partial + (int64_t)b * chunk_slots * cp * cp + r * cp + c, nchunks, (int64_t)cp * cp);
     gram[(int64_t)b * C * C + idx] = s;
     const bool re = r < E, ce = c < E;
     const double w = (re == ce) ? 1.0 : -1.0;  // the two mixed blocks together give -2 |V^T Y|^2

@@ -297,7 +297,7 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
     for (int w = 0; w < nwarps; ++w) s += sm[i * nwarps + w];
     mine[i] = s;
   }
-  __threadfence();
+  if (threadIdx.x < NV) __threadfence();   // the writers of the partial sums
   __syncthreads();
   __shared__ int s_last;
   if (threadIdx.x == 0) s_last = atomicAdd(counters + g, 1) == nchunks - 1;
@@ -305,9 +305,7 @@ pair_stats_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
   if (!s_last) return;
   __threadfence();
   for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
-    double s = 0.0;
-    const volatile double* p = partial + (int64_t)g * nchunks * NV + i;
-    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
+    const double s = ordered_sum(partial + (int64_t)g * nchunks * NV + i, nchunks, NV);
     stats[(int64_t)g * NV + i] = s;
     sm[i] = s;
   }
@@ -459,9 +457,7 @@ pair_stats_seg_kernel(const float* __restrict__ est, const float* __restrict__ t
     if (s_last) {   // block-uniform
       __threadfence();
       for (int i = threadIdx.x; i < NV; i += kStatsThreads) {
-        double v = 0.0;
-        const volatile double* p = partial + g * slots * NV + i;
-        for (int c = 0; c < nparts; ++c) v += p[(int64_t)c * NV];
+        const double v = ordered_sum(partial + g * slots * NV + i, nparts, NV);
         stats[g * NV + i] = v;
       }
       if (threadIdx.x == 0) counters[g] = 0;

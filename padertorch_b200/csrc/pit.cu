@@ -82,9 +82,7 @@ __device__ __forceinline__ void pit_finish(const float (&acc)[(DUAL ? 2 : 1) * K
   // ---- last CTA of this example: fold the chunks in order, pick the permutation
   double* total = sm + NV * nwarps;
   for (int i = tid; i < NV; i += nthreads) {
-    double s = 0.0;
-    const volatile double* p = partial + (int64_t)b * nchunks * NV + i;
-    for (int c = 0; c < nchunks; ++c) s += p[(int64_t)c * NV];
+    const double s = ordered_sum(partial + (int64_t)b * nchunks * NV + i, nchunks, NV);
     total[i] = s;
     sse[(int64_t)b * NV + i] = s;
   }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The deep-clustering loss at config 3's fixed-length shape (batch 16 x 253 frames, E = 20, K = 2), forward + backward,
-three times -- for ncu:  ncu --set full -k regex:'dc_gram_frame|dc_backward_frame' -s 2 -c 2 -o gpurun_out/prof python tools/dc_probe.py"""
+three times -- for ncu:  ncu --set full -k regex:'dc_gram_ring|dc_backward_frame' -s 2 -c 2 -o gpurun_out/prof python tools/dc_probe.py"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
