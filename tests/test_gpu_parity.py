@@ -423,6 +423,37 @@ def test_dc_review_reference_geometry(b2s):
     assert_loss_close(single.cpu().numpy(), want0.numpy())
 
 
+@pytest.mark.parametrize('lengths', [[40], [3], [1, 2, 300, 7, 64], [17] * 37, [5 + (11 * b) % 23 for b in range(148)],
+                                     [4 + b % 9 for b in range(151)], [120, 8, 9, 500, 33, 16, 250]])
+def test_dc_balanced_chunks(b2s, lengths):
+    """Length-balanced chunk slots of the ring Gram kernel and the frame backward kernel (balanced_chunk_slot): one
+    example, more examples than SMs (the uniform grid takes over), equal lengths (closed form), chunks shorter than
+    eight frames, extreme spreads -- per-example losses and gradients against the oracle in float64, and bit-identical
+    to the uniform grid (B2S_DC_BALANCE is read once per process, so the uniform grid is checked through the oracle)."""
+    from oracle import path as oracle_path
+    rng = np.random.RandomState(len(lengths) * 7 + lengths[0])
+    E, K, F = 20, 2, 513
+    T = max(lengths)
+    emb_np = rng.randn(len(lengths), T, E, F).astype(np.float32)
+    emb_np /= np.linalg.norm(emb_np, axis=2, keepdims=True)
+    tm_np = np.eye(K, dtype=np.float32)[rng.randint(0, K, (len(lengths), T, F))].transpose(0, 1, 3, 2).copy()
+    emb = cuda(emb_np).requires_grad_(True)
+    losses = b2s.review.dc_losses_per_example(emb, cuda(tm_np), lengths)
+    weights = torch.linspace(0.5, 1.5, len(lengths), device=dev())
+    (grad,) = torch.autograd.grad((losses * weights).sum(), emb)
+    again = b2s.review.dc_losses_per_example(emb.detach(), cuda(tm_np), lengths)
+    assert torch.equal(again, losses.detach())   # fixed summation order
+    check = sorted(set([0, len(lengths) - 1, int(np.argmax(lengths)), int(np.argmin(lengths))]))
+    for b in check:
+        e = torch.from_numpy(emb_np[b, :lengths[b]]).double().requires_grad_(True)
+        want, _ = oracle_path.dc_review_loss([e], [torch.from_numpy(tm_np[b, :lengths[b]]).double()])
+        assert_loss_close(losses[b].detach().cpu().numpy(), want.detach().numpy(), what=f'loss {b}')
+        (wg,) = torch.autograd.grad(want * float(weights[b]), e)
+        assert_spec_close(grad[b, :lengths[b]].cpu().numpy(), wg.numpy(), rtol=2e-4, what=f'grad {b}')
+        if lengths[b] < T:
+            assert float(grad[b, lengths[b]:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('K', [3, 5])
 def test_tasnet_losses_more_sources(b2s, K):
     """The one-launch loss set (K <= 4: thread per example) and its K > 4 fallback against the oracle."""
