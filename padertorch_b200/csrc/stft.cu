@@ -1102,7 +1102,9 @@ template <int L, bool D, bool S, int NS = kPipeFrames, int CTAS = kPipeCtasPerSm
           int STAGES = kPipeStages, bool PAIR = false>
 int launch_pipe(const PipeArgs& a) {
   const int64_t units = a.rows * ceil_div(a.frames, NS);
-  const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)kNumSMs * CTAS);
+  // B2S_FWD_SMS (tuning aid): fewer SMs for the front-end, e.g. next to a fused kernel restricted by B2S_FUSED_SMS
+  static const int sms = [] { const char* e = getenv("B2S_FWD_SMS"); const int v = e ? atoi(e) : 0; return v > 0 && v < kNumSMs ? v : kNumSMs; }();
+  const int grid = (int)std::min<int64_t>(ceil_div(units, kPipeWarps), (int64_t)sms * CTAS);
   const int span = (NS - 1) * a.shift + fft::kSize;
   const int out_area = (NS * (L <= B2S_SPEC_CONCAT ? 2 * fft::kBins : fft::kBins) + 8 + 3) / 4 * 4;
   const size_t smem = kPipeWarps * (sizeof(float) * (STAGES * span + out_area) + sizeof(float2) * NS * rf::kTile1);
