@@ -984,6 +984,11 @@ dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict_
 
 }  // namespace
 
+// Geometries (bins, embedding channels, sources) with compile-time instances of the ring Gram kernel and the frame
+// backward kernel: the reference's deep-clustering model (tcl/dc.py:8-15: F = 257, E = 20) and the 1024-point STFT of
+// BASELINE.json's configurations, two and three speakers.
+#define B2S_DC_GEOMETRIES(X) X(513, 20, 2) X(257, 20, 2) X(513, 20, 3) X(257, 20, 3)
+
 extern "C" {
 
 int64_t b2s_dc_workspace_bytes(int64_t batch, int64_t max_frames, int64_t bins, int channels) {
@@ -1029,20 +1034,24 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
                                              (bins + 31) / 32 * 32);
     // (the run-time-geometry instance of the ring kernel spills at its 168-register budget and measured SLOWER than
     // the six-warp kernel: 67 vs 59 us at 257 bins, 112 vs 70 us at E = 16 / K = 3 -- compile-time geometry only)
-    const bool reference_geometry = bins == 513 && embedding_dim == 20 && sources == 2;
+    bool reference_geometry = false;
+    auto rkernel = dc_gram_ring_kernel<0, 0, 0>;
+#define X(F_, E_, K_) if (bins == F_ && embedding_dim == E_ && sources == K_) { rkernel = dc_gram_ring_kernel<F_, E_, K_>; reference_geometry = true; }
+    B2S_DC_GEOMETRIES(X)
+#undef X
     static const bool ring_any = getenv("B2S_DC_RING_ANY") != nullptr;
     if (ring && (reference_geometry || ring_any) && ring_smem <= 200 * 1024) {
       static bool ring_configured[64] = {};
       if (!ring_configured[dev & 63]) {
         B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define X(F_, E_, K_) B2S_CUDA(cudaFuncSetAttribute(dc_gram_ring_kernel<F_, E_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B2S_DC_GEOMETRIES(X)
+#undef X
         ring_configured[dev & 63] = true;
       }
       int rchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 8),
                                                                (int64_t)kNumSMs / std::max<int64_t>(1, batch)));
       rchunks = std::min(rchunks, g.nchunks);
-      auto rkernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_gram_ring_kernel<513, 20, 2>
-                                                                        : dc_gram_ring_kernel<0, 0, 0>;
       // length-balanced chunks on a one-dimensional grid (B2S_DC_BALANCE=0: the same number of chunks per example)
       static const bool balance = [] { const char* e = getenv("B2S_DC_BALANCE"); return e ? atoi(e) != 0 : true; }();
       if (balance && batch <= kBalMaxBatch && batch <= kNumSMs) {
@@ -1101,14 +1110,18 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
     B2S_CUDA(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
       B2S_CUDA(cudaFuncSetAttribute(dc_backward_frame_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      B2S_CUDA(cudaFuncSetAttribute(dc_backward_frame_kernel<513, 20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define X(F_, E_, K_) B2S_CUDA(cudaFuncSetAttribute(dc_backward_frame_kernel<F_, E_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B2S_DC_GEOMETRIES(X)
+#undef X
       configured[dev & 63] = true;
     }
     const int groups = (embedding_dim + kFbOut - 1) / kFbOut;
     const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, max_frames / 4),
                                                                    (int64_t)kNumSMs / std::max<int64_t>(1, batch)));
-    auto kernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_backward_frame_kernel<513, 20, 2>
-                                                                     : dc_backward_frame_kernel<0, 0, 0>;
+    auto kernel = dc_backward_frame_kernel<0, 0, 0>;
+#define X(F_, E_, K_) if (bins == F_ && embedding_dim == E_ && sources == K_) kernel = dc_backward_frame_kernel<F_, E_, K_>;
+    B2S_DC_GEOMETRIES(X)
+#undef X
     static const bool balance = [] { const char* e = getenv("B2S_DC_BALANCE"); return e ? atoi(e) != 0 : true; }();
     if (balance && batch <= kBalMaxBatch && batch <= kNumSMs)
       kernel<<<dim3((unsigned)kNumSMs), 64 * groups, frame_smem, (cudaStream_t)stream>>>(

@@ -454,6 +454,30 @@ def test_dc_balanced_chunks(b2s, lengths):
             assert float(grad[b, lengths[b]:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('F,E,K', [(257, 20, 2), (513, 20, 3), (257, 20, 3), (129, 20, 2), (257, 16, 2)])
+def test_dc_compile_time_geometries(b2s, F, E, K):
+    """The compile-time instances of the ring Gram / frame backward kernels beyond 513 / 20 / 2 (the reference model's
+    F = 257, three speakers) and two run-time geometries next to them, ragged batch, against the oracle in float64."""
+    from oracle import path as oracle_path
+    rng = np.random.RandomState(F + E + K)
+    lengths = [37, 9, 64, 21, 50]
+    T = max(lengths)
+    emb_np = rng.randn(len(lengths), T, E, F).astype(np.float32)
+    emb_np /= np.linalg.norm(emb_np, axis=2, keepdims=True)
+    tm_np = np.eye(K, dtype=np.float32)[rng.randint(0, K, (len(lengths), T, F))].transpose(0, 1, 3, 2).copy()
+    emb = cuda(emb_np).requires_grad_(True)
+    losses = b2s.review.dc_losses_per_example(emb, cuda(tm_np), lengths)
+    (grad,) = torch.autograd.grad(losses.sum(), emb)
+    for b in range(len(lengths)):
+        e = torch.from_numpy(emb_np[b, :lengths[b]]).double().requires_grad_(True)
+        want, _ = oracle_path.dc_review_loss([e], [torch.from_numpy(tm_np[b, :lengths[b]]).double()])
+        assert_loss_close(losses[b].detach().cpu().numpy(), want.detach().numpy(), what=f'loss {b}')
+        (wg,) = torch.autograd.grad(want, e)
+        assert_spec_close(grad[b, :lengths[b]].cpu().numpy(), wg.numpy(), rtol=2e-4, what=f'grad {b}')
+        if lengths[b] < T:
+            assert float(grad[b, lengths[b]:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('K', [3, 5])
 def test_tasnet_losses_more_sources(b2s, K):
     """The one-launch loss set (K <= 4: thread per example) and its K > 4 fallback against the oracle."""
