@@ -52,6 +52,16 @@ def _time_graphs(graphs, steps, distributed, device):
     return ms
 
 
+def _traffic(key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
+    try:
+        with open(path) as fd:
+            return json.load(fd).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def _capture(fn, sets):
     graphs, keep = [], []
     for data in sets:
@@ -291,7 +301,8 @@ class Dc:
                  'steps': e2e_steps},
             gpu_launches=2 * args.steps,
             roofline={'bound': 'hbm', 'kernel': 'dc_gram_ring_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                      'frac': achieved / peak, 'traffic': None, 'peak_kind': peak_kind, 'kernel_ms': fwd_ms,
+                      'frac': achieved / peak, 'traffic': _traffic('dc_gram_ring_kernel@config3'), 'peak_kind': peak_kind,
+                      'kernel_ms': fwd_ms,
                       'algorithmic_bytes_per_launch': fwd_b},
             step_roofline={'achieved': step_gbs, 'frac': step_gbs / peak, 'unit': 'GB/s',
                            'algorithmic_bytes_per_step': fwd_b + bwd_b},
