@@ -448,7 +448,8 @@ __device__ inline ChunkSlot balanced_chunk_slot(const int64_t* __restrict__ meta
   __shared__ ChunkSlot s_slot;
   for (int i = threadIdx.x; i < B * B2S_DC_META; i += blockDim.x) s_meta[i] = meta[i];
   if (threadIdx.x == 0) s_slot.b = -1;
-  bool same = true;   // this thread's lengths equal example 0's (every thread re-reads its own staged values only)
+  bool same = true;   // the lengths this thread looks at equal example 0's (read from global memory again: the
+                      // staged copies are not visible before the barrier; same addresses, so the loads merge)
   for (int b = threadIdx.x; b < B; b += blockDim.x) same = same && meta[(int64_t)b * B2S_DC_META] == meta[0];
   if (__syncthreads_and(same)) {
     // equal lengths (dense batches): closed form, no reductions -- L = ceil(T / floor(P / B))
