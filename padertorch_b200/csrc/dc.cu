@@ -457,11 +457,13 @@ __device__ inline ChunkSlot balanced_chunk_slot(const int64_t* __restrict__ meta
     const int m = max(1, min(max_chunks, P / B));
     const int L = max(8, (T + m - 1) / m);
     const int n = max(1, min(max_chunks, (T + L - 1) / L));
+    // example index fastest, as the (batch, chunks) grid enumerates its CTAs (consecutive slots on consecutive
+    // chunks of ONE example measured 1 us slower at batch 16 x 253 frames)
     ChunkSlot r;
-    r.b = slot / n;
-    r.chunk = slot - r.b * n;
+    r.chunk = slot / B;
+    r.b = slot - r.chunk * B;
     r.nchunks = n;
-    if (r.b >= B) { r.b = -1; return r; }
+    if (r.chunk >= n) { r.b = -1; return r; }
 #pragma unroll
     for (int i = 0; i < B2S_DC_META; ++i) r.row[i] = s_meta[r.b * B2S_DC_META + i];
     return r;
