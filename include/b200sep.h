@@ -263,12 +263,25 @@ B2S_API int b2s_dc_forward(const float* embedding, const float* target, const in
                    const int64_t* embedding_strides /*host [3]: frame, channel, bin*/,
                    const int64_t* target_strides /*host [3]*/, float* loss, double* gram,
                    void* workspace, b2s_stream stream);
+/* b2s_dc_forward plus mean[0] = mean_b loss[b] (dc_loss of DeepClusteringModel.review, tcl/dc.py:83-84) folded by
+ * the same launch: the CTA that finishes the last example adds the losses in a fixed order.  batch >= 1.          */
+B2S_API int b2s_dc_forward_mean(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                        int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                        const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
+                        float* mean, double* gram, void* workspace, b2s_stream stream);
 /* grad_embedding = grad_loss[b] * 4/N^2 (V V^T V - Y Y^T V), written with embedding's strides.      */
 B2S_API int b2s_dc_backward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
                     int64_t max_frames, int64_t bins, int embedding_dim, int sources,
                     const int64_t* embedding_strides, const int64_t* target_strides,
                     const double* gram, const float* grad_loss, float* grad_embedding,
                     b2s_stream stream);
+/* The same with the upstream gradient grad_scale * grad_loss[b * grad_loss_stride]: stride 0 broadcasts ONE value
+ * (the gradient of a batch mean: scale 1 / batch) -- no expand / divide kernels in front of the backward.         */
+B2S_API int b2s_dc_backward_scaled(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                           int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                           const int64_t* embedding_strides, const int64_t* target_strides,
+                           const double* gram, const float* grad_loss, int64_t grad_loss_stride,
+                           double grad_scale, float* grad_embedding, b2s_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The fused north-star kernel: STFT -> mask (*) |Y| -> PIT-MSE without materialising the target

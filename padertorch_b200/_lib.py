@@ -74,6 +74,12 @@ SIGNATURES = {
     'b2s_dc_backward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_int,
                                 ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_void,
                                 c_void]),
+    'b2s_dc_forward_mean': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_int,
+                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_void, c_void,
+                                    c_void]),
+    'b2s_dc_backward_scaled': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_i64, c_int, c_int,
+                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_void, c_void, c_i64, c_dbl,
+                                       c_void, c_void]),
     'b2s_mask_spectrum': (c_int, [c_void, c_void, c_i64, c_int, c_i64, c_i64, c_void, c_void]),
     'b2s_stft_pit_targets': (c_int, [c_void, c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64, c_void,
                                      c_void, c_void, c_void]),

@@ -71,7 +71,9 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 
 __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int E, int64_t N,
                                           double* __restrict__ partial, int* __restrict__ counters,
-                                          double* __restrict__ gram, float* __restrict__ loss, int chunk_slots = 0) {
+                                          double* __restrict__ gram, float* __restrict__ loss, int chunk_slots = 0,
+                                          float* __restrict__ mean = nullptr, int* __restrict__ done = nullptr,
+                                          int batch = 0) {
   if (chunk_slots == 0) chunk_slots = nchunks;   // partial matrices reserved per example
   __threadfence();
   __syncthreads();
@@ -100,6 +102,24 @@ __device__ __forceinline__ void dc_finish(int b, int nchunks, int cp, int C, int
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += red[w];
     loss[b] = (float)(s / ((double)N * (double)N));
     counters[b] = 0;
+  }
+  // b2s_dc_forward_mean: the CTA that finishes the LAST example folds the batch mean (dc_loss of
+  // DeepClusteringModel.review, tcl/dc.py:83-84) -- no separate reduction launch
+  if (mean == nullptr) return;   // kernel-uniform
+  __shared__ int s_all;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_all = atomicAdd(done, 1) == batch - 1;
+  }
+  __syncthreads();
+  if (!s_all) return;
+  __threadfence();
+  if (threadIdx.x < 32) {   // fixed order: lane-strided partial sums, warp tree
+    const volatile float* values = loss;
+    double local = 0.0;
+    for (int i = threadIdx.x; i < batch; i += 32) local += (double)values[i];
+    local = warp_sum(local);
+    if (threadIdx.x == 0) { *mean = (float)(local / (double)batch); *done = 0; }
   }
 }
 
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(32 * kFrWarps, 2)
 dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
                      const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks, int F_rt, int E_rt,
                      int K_rt, double* __restrict__ partial, int* __restrict__ counters,
-                     double* __restrict__ gram, float* __restrict__ loss) {
+                     double* __restrict__ gram, float* __restrict__ loss, float* __restrict__ mean) {
   extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] frame buffers, then a row of zeros
   __shared__ __align__(8) uint64_t full[2];
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
@@ -419,7 +439,7 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
       mine[(bb * BS + j) * kTC + ba * BS + i] = (double)sum;
     }
   }
-  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss);
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss, 0, mean, counters + (kMaxTickets - 1), (int)gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------- ring form of the frame kernel
@@ -543,7 +563,8 @@ __global__ void __launch_bounds__(32 * kRgWarps, 1)
 dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
                     const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int batch, int balance_ctas,
                     int chunk_slots, int F_rt, int E_rt, int K_rt, double* __restrict__ partial,
-                    int* __restrict__ counters, double* __restrict__ gram, float* __restrict__ loss) {
+                    int* __restrict__ counters, double* __restrict__ gram, float* __restrict__ loss,
+                    float* __restrict__ mean) {
   extern __shared__ __align__(16) float fsm[];   // [kRgStages][area_e + area_t] frame stages, then a row of zeros
   __shared__ __align__(8) uint64_t full[kRgStages], empty[kRgStages];
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
@@ -670,7 +691,7 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
       mine[(bb * BS + jx) * kTC + ba * BS + i] = sum;
     }
   }
-  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss, chunk_slots);
+  dc_finish(b, nchunks, kTC, C, E, N, partial, counters, gram, loss, chunk_slots, mean, counters + (kMaxTickets - 1), batch);
 }
 
 // grad_V[p][e] = coef * ( sum_{c<E} V[p][c] G[c][e] - sum_{k} Y[p][k] G[e][E+k] ),  coef = 4 g / N^2.
@@ -678,7 +699,7 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
 __global__ void __launch_bounds__(256)
 dc_backward_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
                    const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
-                   int K, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                   int K, const double* __restrict__ gram, const float* __restrict__ grad_loss, int64_t gl_stride, double gl_scale,
                    float* __restrict__ grad_emb) {
   extern __shared__ float coef[];  // [C][Ep], Ep = E rounded up to BS
   const int b = blockIdx.x, chunk = blockIdx.y;
@@ -689,7 +710,7 @@ dc_backward_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
   const float* t_ = tgt + meta[b * B2S_DC_META + 2];
   float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
   const int64_t N = T * F;
-  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  const double scale = 4.0 * gl_scale * (double)grad_loss[(int64_t)b * gl_stride] / ((double)N * (double)N);
   for (int idx = threadIdx.x; idx < C * Ep; idx += blockDim.x) {
     const int c = idx / Ep, e = idx - c * Ep;
     double v = 0.0;
@@ -746,7 +767,7 @@ constexpr int kBwdGroups = 4;    // output groups (covers E <= 20)
 __global__ void __launch_bounds__(kTiledThreads, 2)
 dc_backward_tiled_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
                          const int64_t* __restrict__ meta, Strides se, Strides st, int nchunks, int64_t F, int E,
-                         int K, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                         int K, const double* __restrict__ gram, const float* __restrict__ grad_loss, int64_t gl_stride, double gl_scale,
                          float* __restrict__ grad_emb) {
   __shared__ __align__(16) float tile[2][kTC][kTP];
   __shared__ float coef[kTC][kBwdGroups * kBwdOut];   // [c][e], zero padded
@@ -758,7 +779,7 @@ dc_backward_tiled_kernel(const float* __restrict__ emb, const float* __restrict_
   float* g_ = grad_emb + meta[b * B2S_DC_META + 3];
   const int64_t N = T * F;
   const int64_t q0 = N * chunk / nchunks, q1 = N * (chunk + 1) / nchunks;
-  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  const double scale = 4.0 * gl_scale * (double)grad_loss[(int64_t)b * gl_stride] / ((double)N * (double)N);
   for (int idx = threadIdx.x; idx < kTC * kBwdGroups * kBwdOut; idx += kTiledThreads) {
     const int c = idx / (kBwdGroups * kBwdOut), e = idx - c * (kBwdGroups * kBwdOut);
     double v = 0.0;
@@ -844,7 +865,7 @@ __global__ void __launch_bounds__(ET ? 64 * ((ET + kFbOut - 1) / kFbOut) : 320, 
 dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tgt,
                          const int64_t* __restrict__ meta, int64_t se_t, int64_t st_t, int nchunks_arg, int batch,
                          int balance_ctas, int F_rt, int E_rt,
-                         int K_rt, const double* __restrict__ gram, const float* __restrict__ grad_loss,
+                         int K_rt, const double* __restrict__ gram, const float* __restrict__ grad_loss, int64_t gl_stride, double gl_scale,
                          float* __restrict__ grad_emb) {
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
   extern __shared__ __align__(16) float fsm[];   // [2][area_e + area_t] inputs, [2][area_o] outputs
@@ -876,7 +897,7 @@ dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict_
   float* g_ = grad_emb + row[3];
   const int64_t N = T * F;
   const int t0 = (int)(T * chunk / nchunks), t1 = (int)(T * (chunk + 1) / nchunks);
-  const double scale = 4.0 * (double)grad_loss[b] / ((double)N * (double)N);
+  const double scale = 4.0 * gl_scale * (double)grad_loss[(int64_t)b * gl_stride] / ((double)N * (double)N);
   for (int idx = threadIdx.x; idx < kTC * (kTC + 1); idx += blockDim.x) {
     const int c = idx / (kTC + 1), e = idx - c * (kTC + 1);
     double v = 0.0;
@@ -1002,15 +1023,28 @@ int64_t b2s_dc_workspace_bytes(int64_t batch, int64_t max_frames, int64_t bins, 
   return kTicketBytes + (int64_t)sizeof(double) * batch * cells + 16;
 }
 
-int b2s_dc_forward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
-                   int64_t max_frames, int64_t bins, int embedding_dim, int sources,
-                   const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
-                   double* gram, void* workspace, b2s_stream stream) {
+}  // extern "C"
+
+namespace {
+// mean of loss[0 .. batch): the fallback of b2s_dc_forward_mean behind the kernels that do not fold it themselves
+__global__ void __launch_bounds__(32)
+dc_mean_kernel(const float* __restrict__ loss, int batch, float* __restrict__ mean) {
+  double local = 0.0;
+  for (int i = threadIdx.x; i < batch; i += 32) local += (double)loss[i];
+  local = warp_sum(local);
+  if (threadIdx.x == 0) *mean = (float)(local / (double)batch);
+}
+
+int dc_forward_impl(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                    int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                    const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
+                    double* gram, void* workspace, b2s_stream stream, float* mean) {
   const int C = embedding_dim + sources;
   B2S_REQUIRE(embedding_dim >= 1 && sources >= 1 && C <= B2S_DC_MAX_CHANNELS,
               "embedding_dim + sources = %d outside 2..%d", C, B2S_DC_MAX_CHANNELS);
   B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
   if (batch == 0) return B2S_OK;
+  bool mean_folded = false;   // the Gram kernel folds the batch mean itself (ring / frame kernels)
   B2S_REQUIRE(embedding && target && meta && embedding_strides && target_strides && loss && gram &&
               workspace, "NULL pointer");
   const DcGrid g = dc_grid(batch, max_frames, bins, C, embedding_strides[2] == 1 && target_strides[2] == 1);
@@ -1060,11 +1094,11 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
       if (balance && batch <= kBalMaxBatch && batch <= kNumSMs) {
         rkernel<<<dim3((unsigned)kNumSMs), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
             embedding, target, meta, se.t, st.t, (int)batch, kNumSMs, g.nchunks, (int)bins, embedding_dim, sources,
-            partial, counters, gram, loss);
+            partial, counters, gram, loss, mean);
       } else {
         rkernel<<<dim3((unsigned)batch, rchunks), 32 * kRgWarps, ring_smem, (cudaStream_t)stream>>>(
             embedding, target, meta, se.t, st.t, (int)batch, 0, rchunks, (int)bins, embedding_dim, sources,
-            partial, counters, gram, loss);
+            partial, counters, gram, loss, mean);
       }
       B2S_LAUNCH_CHECK("dc_gram_ring_kernel");
       return B2S_OK;
@@ -1076,7 +1110,8 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
     auto kernel = bins == 513 && embedding_dim == 20 && sources == 2 ? dc_gram_frame_kernel<513, 20, 2>
                                                                      : dc_gram_frame_kernel<0, 0, 0>;
     kernel<<<dim3((unsigned)batch, nchunks), 32 * kFrWarps, frame_smem, (cudaStream_t)stream>>>(
-        embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss);
+        embedding, target, meta, se.t, st.t, nchunks, (int)bins, embedding_dim, sources, partial, counters, gram, loss, mean);
+    mean_folded = true;
   } else if (g.tiled) {
     dc_gram_tiled_kernel<<<dim3((unsigned)batch, g.nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
         embedding, target, meta, se, st, g.nchunks, bins, embedding_dim, sources, partial, counters, gram, loss);
@@ -1086,13 +1121,41 @@ int b2s_dc_forward(const float* embedding, const float* target, const int64_t* m
         counters, gram, loss);
   }
   B2S_LAUNCH_CHECK("dc_gram_kernel");
+  if (mean && !mean_folded) {
+    dc_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss, (int)batch, mean);
+    B2S_LAUNCH_CHECK("dc_mean_kernel");
+  }
   return B2S_OK;
 }
+}  // namespace
 
-int b2s_dc_backward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
-                    int64_t max_frames, int64_t bins, int embedding_dim, int sources,
-                    const int64_t* embedding_strides, const int64_t* target_strides, const double* gram,
-                    const float* grad_loss, float* grad_embedding, b2s_stream stream) {
+extern "C" {
+
+int b2s_dc_forward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                   int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                   const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
+                   double* gram, void* workspace, b2s_stream stream) {
+  return dc_forward_impl(embedding, target, meta, batch, max_frames, bins, embedding_dim, sources, embedding_strides,
+                         target_strides, loss, gram, workspace, stream, nullptr);
+}
+
+int b2s_dc_forward_mean(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                        int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                        const int64_t* embedding_strides, const int64_t* target_strides, float* loss,
+                        float* mean, double* gram, void* workspace, b2s_stream stream) {
+  B2S_REQUIRE(mean != nullptr && batch >= 1 && batch < kMaxTickets, "b2s_dc_forward_mean needs batch >= 1 and a mean pointer");
+  return dc_forward_impl(embedding, target, meta, batch, max_frames, bins, embedding_dim, sources, embedding_strides,
+                         target_strides, loss, gram, workspace, stream, mean);
+}
+
+}  // extern "C"
+
+namespace {
+int dc_backward_impl(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                     int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                     const int64_t* embedding_strides, const int64_t* target_strides, const double* gram,
+                     const float* grad_loss, int64_t gl_stride, double gl_scale, float* grad_embedding,
+                     b2s_stream stream) {
   const int C = embedding_dim + sources;
   B2S_REQUIRE(embedding_dim >= 1 && sources >= 1 && C <= B2S_DC_MAX_CHANNELS,
               "embedding_dim + sources = %d outside 2..%d", C, B2S_DC_MAX_CHANNELS);
@@ -1128,11 +1191,11 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
     static const bool balance = [] { const char* e = getenv("B2S_DC_BALANCE"); return e ? atoi(e) != 0 : true; }();
     if (balance && batch <= kBalMaxBatch && batch <= kNumSMs)
       kernel<<<dim3((unsigned)kNumSMs), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
-          embedding, target, meta, se.t, st.t, 0, (int)batch, kNumSMs, (int)bins, embedding_dim, sources, gram, grad_loss,
+          embedding, target, meta, se.t, st.t, 0, (int)batch, kNumSMs, (int)bins, embedding_dim, sources, gram, grad_loss, gl_stride, gl_scale,
           grad_embedding);
     else
       kernel<<<dim3((unsigned)batch, nchunks), 64 * groups, frame_smem, (cudaStream_t)stream>>>(
-          embedding, target, meta, se.t, st.t, nchunks, (int)batch, 0, (int)bins, embedding_dim, sources, gram, grad_loss,
+          embedding, target, meta, se.t, st.t, nchunks, (int)batch, 0, (int)bins, embedding_dim, sources, gram, grad_loss, gl_stride, gl_scale,
           grad_embedding);
     B2S_LAUNCH_CHECK("dc_backward_frame_kernel");
     return B2S_OK;
@@ -1141,7 +1204,7 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
     const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(points / 1024,
                                                std::max<int64_t>(1, (int64_t)kNumSMs * 2 * 4 / batch)));
     dc_backward_tiled_kernel<<<dim3((unsigned)batch, nchunks), kTiledThreads, 0, (cudaStream_t)stream>>>(
-        embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss, grad_embedding);
+        embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss, gl_stride, gl_scale, grad_embedding);
     B2S_LAUNCH_CHECK("dc_backward_tiled_kernel");
     return B2S_OK;
   }
@@ -1149,10 +1212,32 @@ int b2s_dc_backward(const float* embedding, const float* target, const int64_t* 
   const int Ep = (embedding_dim + BS - 1) / BS * BS;
   const size_t smem = sizeof(float) * C * Ep;
   dc_backward_kernel<<<dim3((unsigned)batch, nchunks), 256, smem, (cudaStream_t)stream>>>(
-      embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss,
+      embedding, target, meta, se, st, nchunks, bins, embedding_dim, sources, gram, grad_loss, gl_stride, gl_scale,
       grad_embedding);
   B2S_LAUNCH_CHECK("dc_backward_kernel");
   return B2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2s_dc_backward(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                    int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                    const int64_t* embedding_strides, const int64_t* target_strides, const double* gram,
+                    const float* grad_loss, float* grad_embedding, b2s_stream stream) {
+  return dc_backward_impl(embedding, target, meta, batch, max_frames, bins, embedding_dim, sources, embedding_strides,
+                          target_strides, gram, grad_loss, 1, 1.0, grad_embedding, stream);
+}
+
+int b2s_dc_backward_scaled(const float* embedding, const float* target, const int64_t* meta, int64_t batch,
+                           int64_t max_frames, int64_t bins, int embedding_dim, int sources,
+                           const int64_t* embedding_strides, const int64_t* target_strides, const double* gram,
+                           const float* grad_loss, int64_t grad_loss_stride, double grad_scale,
+                           float* grad_embedding, b2s_stream stream) {
+  B2S_REQUIRE(grad_loss_stride == 0 || grad_loss_stride == 1, "grad_loss_stride must be 0 (broadcast) or 1");
+  return dc_backward_impl(embedding, target, meta, batch, max_frames, bins, embedding_dim, sources, embedding_strides,
+                          target_strides, gram, grad_loss, grad_loss_stride, grad_scale, grad_embedding, stream);
 }
 
 }  // extern "C"

@@ -33,25 +33,37 @@ class DcProblem:
         ts = (ctypes.c_int64 * 3)(*self.tgt_strides)
         return es, ts
 
-    def forward(self):
+    def forward(self, with_mean=False):
+        """(loss [batch], gram) or, with_mean, (loss, gram, mean [1]): the batch mean folded by the same launch."""
         lib = _lib.load()
         device = self.emb_base.device
         c = self.e_dim + self.k
         loss = torch.empty(self.batch, dtype=torch.float32, device=device)
         gram = torch.empty((self.batch, c, c), dtype=torch.float64, device=device)
+        mean = torch.empty(1, dtype=torch.float32, device=device) if with_mean else None
         if self.batch:
             nbytes = lib.b2s_dc_workspace_bytes(self.batch, self.max_frames, self.bins, c)
             ws = workspace(device, nbytes, 'dc')
             es, ts = self._strides()
             with torch.cuda.device(device):
-                rc = lib.b2s_dc_forward(_lib.ptr(self.emb_base), _lib.ptr(self.tgt_base),
-                                        _lib.ptr(self.meta), self.batch, self.max_frames, self.bins,
-                                        self.e_dim, self.k, es, ts, _lib.ptr(loss), _lib.ptr(gram),
-                                        _lib.ptr(ws), _lib.stream_of(device))
+                if with_mean:
+                    rc = lib.b2s_dc_forward_mean(_lib.ptr(self.emb_base), _lib.ptr(self.tgt_base),
+                                                 _lib.ptr(self.meta), self.batch, self.max_frames, self.bins,
+                                                 self.e_dim, self.k, es, ts, _lib.ptr(loss), _lib.ptr(mean),
+                                                 _lib.ptr(gram), _lib.ptr(ws), _lib.stream_of(device))
+                else:
+                    rc = lib.b2s_dc_forward(_lib.ptr(self.emb_base), _lib.ptr(self.tgt_base),
+                                            _lib.ptr(self.meta), self.batch, self.max_frames, self.bins,
+                                            self.e_dim, self.k, es, ts, _lib.ptr(loss), _lib.ptr(gram),
+                                            _lib.ptr(ws), _lib.stream_of(device))
             _lib.check(rc, 'b2s_dc_forward')
-        return loss, gram
+        elif with_mean:
+            mean.fill_(float('nan'))   # torch.mean of an empty batch
+        return (loss, gram, mean) if with_mean else (loss, gram)
 
-    def backward(self, gram, grad_loss):
+    def backward(self, gram, grad_loss, broadcast_scale=None):
+        """broadcast_scale: `grad_loss` is ONE upstream value (the gradient of the batch mean) applied to every
+        example times this factor."""
         lib = _lib.load()
         device = self.emb_base.device
         alloc = torch.empty if self.covers_all and self.batch else torch.zeros
@@ -59,13 +71,15 @@ class DcProblem:
         if self.batch:
             es, ts = self._strides()
             grad_loss = grad_loss.to(torch.float32).contiguous()
+            stride, scale = (1, 1.0) if broadcast_scale is None else (0, float(broadcast_scale))
             # the gradient buffer uses the embedding's strides; blocks start at meta's off_grad
             with torch.cuda.device(device):
-                rc = lib.b2s_dc_backward(_lib.ptr(self.emb_base), _lib.ptr(self.tgt_base),
-                                         _lib.ptr(self.meta), self.batch, self.max_frames, self.bins,
-                                         self.e_dim, self.k, es, ts, _lib.ptr(gram),
-                                         _lib.ptr(grad_loss), _lib.ptr(grad), _lib.stream_of(device))
-            _lib.check(rc, 'b2s_dc_backward')
+                rc = lib.b2s_dc_backward_scaled(_lib.ptr(self.emb_base), _lib.ptr(self.tgt_base),
+                                                _lib.ptr(self.meta), self.batch, self.max_frames, self.bins,
+                                                self.e_dim, self.k, es, ts, _lib.ptr(gram),
+                                                _lib.ptr(grad_loss), stride, scale, _lib.ptr(grad),
+                                                _lib.stream_of(device))
+            _lib.check(rc, 'b2s_dc_backward_scaled')
         return [grad[start:start + numel].view(shape) for start, numel, shape in self.grad_splits]
 
 
@@ -79,6 +93,23 @@ class DcFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         return (None, *ctx.problem.backward(ctx.gram, grad_loss))
+
+
+class DcMeanFunction(torch.autograd.Function):
+    """Batch mean of the per-example losses (dc_loss of DeepClusteringModel.review, tcl/dc.py:83-84): the mean is folded by
+    the Gram launch, the backward takes the one upstream value with the factor 1 / batch -- no reduction, expand or divide
+    kernels around the two launches."""
+
+    @staticmethod
+    def forward(ctx, problem, *embeddings):
+        _, gram, mean = problem.forward(with_mean=True)
+        ctx.problem, ctx.gram = problem, gram
+        return mean.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_mean):
+        scale = 1.0 / max(ctx.problem.batch, 1)
+        return (None, *ctx.problem.backward(ctx.gram, grad_mean.reshape(1), broadcast_scale=scale))
 
 
 def _check_dc_target(t):

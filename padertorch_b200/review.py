@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._workspace import meta_tensor, workspace
 from .ops.losses import _pairs, _sse
-from .ops.losses.source_separation import DcFunction, DcProblem, _check_dc_target
+from .ops.losses.source_separation import DcFunction, DcMeanFunction, DcProblem, _check_dc_target
 from .ops._stft import STFT
 
 
@@ -59,10 +59,9 @@ def pit_review_losses(masks, observations, targets, cos_phase_difference=None, l
     return out
 
 
-def dc_losses_per_example(embeddings, target_masks, lengths=None):
-    """Per-example deep-clustering losses.  embeddings: list of [T_b, E, F] (the model's native
-    't e f' layout, tcl/dc.py:66-74) or padded [B, T, E, F] with `lengths`; target_masks likewise
-    [T_b, K, F]."""
+def _dc_problem(embeddings, target_masks, lengths):
+    """(DcProblem, autograd inputs) of a minibatch.  embeddings: list of [T_b, E, F] (the model's native
+    't e f' layout, tcl/dc.py:66-74) or padded [B, T, E, F] with `lengths`; target_masks likewise [T_b, K, F]."""
     emb_list = _as_list(embeddings)
     if emb_list is not None:
         tgt_list = _as_list(target_masks)
@@ -85,7 +84,7 @@ def dc_losses_per_example(embeddings, target_masks, lengths=None):
                             max(e.shape[0] for e in emb_list), bins, e_dim, k,
                             (e_dim * bins, bins, 1), (k * bins, bins, 1), cursor, splits,
                             (emb_list, tgt_list))
-        return DcFunction.apply(problem, *emb_list)
+        return problem, emb_list
     emb = _lib.require_cuda_float(embeddings, 'embedding').contiguous()
     tgt = _lib.require_cuda_float(target_masks, 'target_mask').contiguous()
     _check_dc_target(tgt)
@@ -101,12 +100,22 @@ def dc_losses_per_example(embeddings, target_masks, lengths=None):
     problem = DcProblem(emb, tgt, meta, batch, frames, bins, e_dim, k, (e_dim * bins, bins, 1),
                         (k * bins, bins, 1), emb.numel(), [(0, emb.numel(), emb.shape)],
                         covers_all=all(n == frames for n in lengths))
-    return DcFunction.apply(problem, emb)
+    return problem, [emb]
+
+
+def dc_losses_per_example(embeddings, target_masks, lengths=None):
+    """Per-example deep-clustering losses [B] (inputs as `_dc_problem`)."""
+    problem, inputs = _dc_problem(embeddings, target_masks, lengths)
+    return DcFunction.apply(problem, *inputs)
 
 
 def dc_review_loss(embeddings, target_masks, lengths=None):
-    """``dc_loss`` of DeepClusteringModel.review (tcl/dc.py:83-84): batch mean."""
-    return dc_losses_per_example(embeddings, target_masks, lengths).mean()
+    """``dc_loss`` of DeepClusteringModel.review (tcl/dc.py:83-84): batch mean, folded by the Gram launch; the backward
+    launch takes the mean's upstream gradient directly (two launches per training step in all)."""
+    problem, inputs = _dc_problem(embeddings, target_masks, lengths)
+    if problem.batch == 0:
+        return DcFunction.apply(problem, *inputs).mean()
+    return DcMeanFunction.apply(problem, *inputs)
 
 
 _TASNET_KINDS = {

@@ -454,6 +454,37 @@ def test_dc_balanced_chunks(b2s, lengths):
             assert float(grad[b, lengths[b]:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('F,E,K,lengths', [(513, 20, 2, [40, 12, 33, 7]), (513, 20, 2, [25] * 6), (65, 7, 3, [5, 9, 4]),
+                                            (513, 30, 2, [6, 11]), (513, 20, 2, [19])])
+def test_dc_review_loss_folded_mean(b2s, F, E, K, lengths):
+    """dc_review_loss (batch mean folded by the Gram launch, b2s_dc_forward_mean; backward with the broadcast upstream
+    gradient, b2s_dc_backward_scaled) == mean of dc_losses_per_example and its autograd, for the ring kernel, the
+    six-warp kernel and the generic kernels (mean by the fallback kernel); repeated calls (the ticket returns to zero)."""
+    rng = np.random.RandomState(F + E + len(lengths))
+    T = max(lengths)
+    emb_np = rng.randn(len(lengths), T, E, F).astype(np.float32)
+    emb_np /= np.linalg.norm(emb_np, axis=2, keepdims=True)
+    tm = cuda(np.eye(K, dtype=np.float32)[rng.randint(0, K, (len(lengths), T, F))].transpose(0, 1, 3, 2).copy())
+    emb = cuda(emb_np).requires_grad_(True)
+    want = b2s.review.dc_losses_per_example(emb, tm, lengths).mean()
+    (want_grad,) = torch.autograd.grad(2.5 * want, emb)
+    # the upstream factor 2.5 / B is rounded to float32 on one route and applied in float64 on the other
+    atol = 1e-6 * float(want_grad.abs().max())
+    for _ in range(3):
+        got = b2s.review.dc_review_loss(emb, tm, lengths)
+        assert got.shape == ()
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=0)
+        (grad,) = torch.autograd.grad(2.5 * got, emb)
+        torch.testing.assert_close(grad, want_grad, rtol=1e-5, atol=atol)
+    # list entry point (the model's own call)
+    emb_list = [cuda(emb_np[b, :n]).requires_grad_(True) for b, n in enumerate(lengths)]
+    got = b2s.review.dc_review_loss(emb_list, [tm[b, :n].contiguous() for b, n in enumerate(lengths)])
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=0)
+    grads = torch.autograd.grad(2.5 * got, emb_list)
+    for b, n in enumerate(lengths):
+        torch.testing.assert_close(grads[b], want_grad[b, :n], rtol=1e-5, atol=atol)
+
+
 @pytest.mark.parametrize('F,E,K', [(257, 20, 2), (513, 20, 3), (257, 20, 3), (129, 20, 2), (257, 16, 2)])
 def test_dc_compile_time_geometries(b2s, F, E, K):
     """The compile-time instances of the ring Gram / frame backward kernels beyond 513 / 20 / 2 (the reference model's
