@@ -152,6 +152,20 @@ B2S_API int b2s_pit_sse_backward(const float* mask, const float* observation, co
                          int sources, int64_t bins, int dual, const int32_t* perm,
                          const float* grad_loss, float* grad_mask, float* grad_target,
                          b2s_stream stream);
+/* The same with the upstream gradient grad_scale * grad_loss[...]: grad_loss_stride 1 = [slots][batch] as above,
+ * 0 = ONE value per slot ([slots]; the gradients of the batch means of b2s_pit_sse_forward_mean, scale 1 / batch).   */
+B2S_API int b2s_pit_sse_backward_scaled(const float* mask, const float* observation, const float* target,
+                         const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                         int sources, int64_t bins, int dual, const int32_t* perm,
+                         const float* grad_loss, int64_t grad_loss_stride, double grad_scale,
+                         float* grad_mask, float* grad_target, b2s_stream stream);
+/* b2s_pit_sse_forward followed by mean[slot] = mean_b loss[slot][b] (the `losses` entry of
+ * PermutationInvariantTrainingModel.review, pit/model.py:137-140): one extra one-warp-per-slot launch instead of a
+ * reduction per loss; fixed summation order.  batch >= 1.                                                        */
+B2S_API int b2s_pit_sse_forward_mean(const float* mask, const float* observation, const float* target,
+                         const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                         int sources, int64_t bins, int dual, float* loss, float* mean, int32_t* perm,
+                         double* sse, void* workspace, b2s_stream stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pair statistics for the time-domain regression losses

@@ -46,6 +46,10 @@ SIGNATURES = {
                                     c_i64, c_int, c_void, c_void, c_void, c_void, c_void]),
     'b2s_pit_sse_backward': (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int,
                                      c_i64, c_int, c_void, c_void, c_void, c_void, c_void]),
+    'b2s_pit_sse_backward_scaled': (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int,
+                                            c_i64, c_int, c_void, c_void, c_i64, c_dbl, c_void, c_void, c_void]),
+    'b2s_pit_sse_forward_mean': (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_i64, c_int,
+                                         c_i64, c_int, c_void, c_void, c_void, c_void, c_void, c_void]),
     'b2s_pair_workspace_bytes': (c_i64, [c_i64, c_i64, c_int]),
     'b2s_pair_stats_forward': (c_int, [c_void, c_void, c_void, c_i64, c_i64, c_int, c_i64, c_i64,
                                        c_void, c_void, c_void]),

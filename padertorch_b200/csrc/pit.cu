@@ -28,6 +28,13 @@ struct PitGrid {
   int nchunks() const { return tchunks * fchunks; }
 };
 
+// Upstream gradient of the backward kernels: value (slot, example) = scale * p[slot * slot_stride + example * stride];
+// stride 0 broadcasts one value per slot (the gradient of a batch mean, scale 1 / batch: b2s_pit_sse_backward_scaled).
+struct GradLoss {
+  const float* p; int64_t stride, slot_stride; double scale;
+  __device__ __forceinline__ double at(int slot, int64_t b) const { return scale * (double)p[slot * slot_stride + b * stride]; }
+};
+
 constexpr int64_t kBinsPerChunk = 16384;
 
 PitGrid pit_grid(int64_t batch, int64_t max_frames, int64_t bins) {
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kPitThreads, kPitCtasPerSm)
 pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
                         const float* __restrict__ tgt, const float* __restrict__ scale,
                         const int64_t* __restrict__ meta, int tchunks, int fchunks, int64_t F,
-                        const int32_t* __restrict__ perm, const float* __restrict__ grad_loss,
+                        const int32_t* __restrict__ perm, const GradLoss grad_loss,
                         float* __restrict__ grad_mask, float* __restrict__ grad_target, int64_t batch) {
   const int b = blockIdx.x;
   const int chunk = blockIdx.y;
@@ -339,8 +346,8 @@ pit_sse_backward_kernel(const float* __restrict__ mask, const float* __restrict_
       for (int i = 0; i < K; ++i) if (i == i1) inv1[i] = k;
     }
   }
-  const float c0 = (float)(2.0 * (double)grad_loss[b] / count);
-  const float c1 = DUAL ? (float)(2.0 * (double)grad_loss[batch + b] / count) : 0.f;
+  const float c0 = (float)(2.0 * grad_loss.at(0, b) / count);
+  const float c1 = DUAL ? (float)(2.0 * grad_loss.at(1, b) / count) : 0.f;
   constexpr int U = 2;
   for (int64_t t = t0 + warp; t < t1; t += kPitWarps) {
     const float* mrow = m_ + t * K * F;
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(kPitThreads, 2)
 pit_sse_backward_frame_kernel(const float* __restrict__ mask, const float* __restrict__ obs,
                               const float* __restrict__ tgt, const float* __restrict__ scale,
                               const int64_t* __restrict__ meta, int tchunks, int G, int F,
-                              const int32_t* __restrict__ perm, const float* __restrict__ grad_loss,
+                              const int32_t* __restrict__ perm, const GradLoss grad_loss,
                               float* __restrict__ grad_mask, int64_t batch) {
   extern __shared__ __align__(16) float stage_sm[];   // [2][mask | target | (scale) | (observation)], [2][gradient]
   __shared__ __align__(8) uint64_t full[2];
@@ -439,8 +446,8 @@ pit_sse_backward_frame_kernel(const float* __restrict__ mask, const float* __res
       for (int i = 0; i < K; ++i) if (i == i1) inv1[i] = k;
     }
   }
-  const float c0 = (float)(2.0 * (double)grad_loss[b] / count);
-  const float c1 = DUAL ? (float)(2.0 * (double)grad_loss[batch + b] / count) : 0.f;
+  const float c0 = (float)(2.0 * grad_loss.at(0, b) / count);
+  const float c1 = DUAL ? (float)(2.0 * grad_loss.at(1, b) / count) : 0.f;
   if (threadIdx.x == 0) {
     tma::mbar_init(&full[0], 1);
     tma::mbar_init(&full[1], 1);
@@ -584,7 +591,7 @@ int launch_forward_k(const float* mask, const float* obs, const float* tgt, cons
 template <int K>
 int launch_backward_k(const float* mask, const float* obs, const float* tgt, const float* scale,
                       const int64_t* meta, int64_t batch, int64_t max_frames, int64_t F, int dual,
-                      const int32_t* perm, const float* grad_loss, float* grad_mask,
+                      const int32_t* perm, const GradLoss grad_loss, float* grad_mask,
                       float* grad_target, cudaStream_t stream) {
   static const bool no_frame = getenv("B2S_PIT_NO_FRAME") != nullptr;
   const int G = (!grad_target && F <= 16384 && max_frames < (1 << 30))
@@ -657,18 +664,21 @@ int b2s_pit_sse_forward(const float* mask, const float* observation, const float
 #undef CALL_FWD
 }
 
-int b2s_pit_sse_backward(const float* mask, const float* observation, const float* target,
-                         const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
-                         int sources, int64_t bins, int dual, const int32_t* perm,
-                         const float* grad_loss, float* grad_mask, float* grad_target,
-                         b2s_stream stream) {
+}  // extern "C"
+
+namespace {
+int pit_sse_backward_impl(const float* mask, const float* observation, const float* target,
+                          const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                          int sources, int64_t bins, int dual, const int32_t* perm,
+                          const GradLoss grad_loss, float* grad_mask, float* grad_target,
+                          b2s_stream stream) {
   B2S_REQUIRE(sources >= 1 && sources <= B2S_MAX_SOURCES,
               "sources=%d outside the supported range 1..%d", sources, B2S_MAX_SOURCES);
   B2S_REQUIRE(batch >= 0 && batch <= kMaxTickets && bins >= 1 && max_frames >= 0, "bad extents");
   B2S_REQUIRE(!(dual && grad_target), "grad_target is not available in dual mode");
   B2S_REQUIRE(!dual || scale, "dual PIT needs the target scale");
   if (batch == 0) return B2S_OK;
-  B2S_REQUIRE(mask && target && meta && perm && grad_loss && grad_mask, "NULL device pointer");
+  B2S_REQUIRE(mask && target && meta && perm && grad_loss.p && grad_mask, "NULL device pointer");
 #define CALL_BWD(K) launch_backward_k<K>(mask, observation, target, scale, meta, batch, max_frames, bins, \
                                          dual, perm, grad_loss, grad_mask, grad_target, (cudaStream_t)stream)
   switch (sources) {
@@ -682,6 +692,52 @@ int b2s_pit_sse_backward(const float* mask, const float* observation, const floa
     default: return CALL_BWD(8);
   }
 #undef CALL_BWD
+}
+
+// mean[slot] = mean_b loss[slot][b], fixed order (lane-strided partial sums, warp tree); one warp per slot
+__global__ void __launch_bounds__(32)
+pit_mean_kernel(const float* __restrict__ loss, int64_t batch, float* __restrict__ mean) {
+  const float* row = loss + blockIdx.x * batch;
+  double local = 0.0;
+  for (int64_t i = threadIdx.x; i < batch; i += 32) local += (double)row[i];
+  local = warp_sum(local);
+  if (threadIdx.x == 0) mean[blockIdx.x] = (float)(local / (double)batch);
+}
+}  // namespace
+
+extern "C" {
+
+int b2s_pit_sse_backward(const float* mask, const float* observation, const float* target,
+                         const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                         int sources, int64_t bins, int dual, const int32_t* perm,
+                         const float* grad_loss, float* grad_mask, float* grad_target,
+                         b2s_stream stream) {
+  return pit_sse_backward_impl(mask, observation, target, scale, meta, batch, max_frames, sources, bins, dual, perm,
+                               GradLoss{grad_loss, 1, batch, 1.0}, grad_mask, grad_target, stream);
+}
+
+int b2s_pit_sse_backward_scaled(const float* mask, const float* observation, const float* target,
+                                const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                                int sources, int64_t bins, int dual, const int32_t* perm,
+                                const float* grad_loss, int64_t grad_loss_stride, double grad_scale,
+                                float* grad_mask, float* grad_target, b2s_stream stream) {
+  B2S_REQUIRE(grad_loss_stride == 0 || grad_loss_stride == 1, "grad_loss_stride must be 0 (one value per slot) or 1");
+  return pit_sse_backward_impl(mask, observation, target, scale, meta, batch, max_frames, sources, bins, dual, perm,
+                               GradLoss{grad_loss, grad_loss_stride, grad_loss_stride ? batch : 1, grad_scale},
+                               grad_mask, grad_target, stream);
+}
+
+int b2s_pit_sse_forward_mean(const float* mask, const float* observation, const float* target,
+                             const float* scale, const int64_t* meta, int64_t batch, int64_t max_frames,
+                             int sources, int64_t bins, int dual, float* loss, float* mean, int32_t* perm,
+                             double* sse, void* workspace, b2s_stream stream) {
+  B2S_REQUIRE(mean != nullptr && batch >= 1, "b2s_pit_sse_forward_mean needs batch >= 1 and a mean pointer");
+  const int rc = b2s_pit_sse_forward(mask, observation, target, scale, meta, batch, max_frames, sources, bins, dual,
+                                     loss, perm, sse, workspace, stream);
+  if (rc != B2S_OK) return rc;
+  pit_mean_kernel<<<dual ? 2 : 1, 32, 0, (cudaStream_t)stream>>>(loss, batch, mean);
+  B2S_LAUNCH_CHECK("pit_mean_kernel");
+  return B2S_OK;
 }
 
 }  // extern "C"

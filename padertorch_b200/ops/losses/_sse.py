@@ -23,39 +23,53 @@ class SseProblem:
     def device(self):
         return self.mask_base.device
 
-    def forward(self):
+    def forward(self, with_mean=False):
+        """(loss [slots, B], perm, sse) or, with_mean, (loss, perm, sse, mean [slots])."""
         lib = _lib.load()
         slots = 2 if self.dual else 1
         k = self.sources
         loss = torch.empty((slots, self.batch), dtype=torch.float32, device=self.device)
         perm = torch.empty((slots, self.batch, k), dtype=torch.int32, device=self.device)
         sse = torch.empty((self.batch, slots, k, k), dtype=torch.float64, device=self.device)
+        mean = torch.empty(slots, dtype=torch.float32, device=self.device) if with_mean else None
         if self.batch:
             nbytes = lib.b2s_pit_workspace_bytes(self.batch, self.max_frames, self.bins, k, int(self.dual))
             ws = workspace(self.device, nbytes, 'pit')
             with torch.cuda.device(self.device):
-                rc = lib.b2s_pit_sse_forward(
-                    _lib.ptr(self.mask_base), _lib.ptr(self.obs_base), _lib.ptr(self.target_base),
-                    _lib.ptr(self.scale_base), _lib.ptr(self.meta), self.batch, self.max_frames, k,
-                    self.bins, int(self.dual), _lib.ptr(loss), _lib.ptr(perm), _lib.ptr(sse),
-                    _lib.ptr(ws), _lib.stream_of(self.device))
+                if with_mean:
+                    rc = lib.b2s_pit_sse_forward_mean(
+                        _lib.ptr(self.mask_base), _lib.ptr(self.obs_base), _lib.ptr(self.target_base),
+                        _lib.ptr(self.scale_base), _lib.ptr(self.meta), self.batch, self.max_frames, k,
+                        self.bins, int(self.dual), _lib.ptr(loss), _lib.ptr(mean), _lib.ptr(perm), _lib.ptr(sse),
+                        _lib.ptr(ws), _lib.stream_of(self.device))
+                else:
+                    rc = lib.b2s_pit_sse_forward(
+                        _lib.ptr(self.mask_base), _lib.ptr(self.obs_base), _lib.ptr(self.target_base),
+                        _lib.ptr(self.scale_base), _lib.ptr(self.meta), self.batch, self.max_frames, k,
+                        self.bins, int(self.dual), _lib.ptr(loss), _lib.ptr(perm), _lib.ptr(sse),
+                        _lib.ptr(ws), _lib.stream_of(self.device))
             _lib.check(rc, 'b2s_pit_sse_forward')
-        return loss, perm, sse
+        elif with_mean:
+            mean.fill_(float('nan'))   # torch.mean of an empty batch
+        return (loss, perm, sse, mean) if with_mean else (loss, perm, sse)
 
-    def backward(self, perm, grad_loss, want_target_grad=False):
+    def backward(self, perm, grad_loss, want_target_grad=False, broadcast_scale=None):
+        """broadcast_scale: `grad_loss` holds ONE upstream value per slot (the gradients of the batch means), applied to
+        every example times this factor."""
         lib = _lib.load()
         alloc = torch.empty if self.covers_all and self.batch else torch.zeros
         grad_mask = alloc(self.grad_numel, dtype=torch.float32, device=self.device)
         grad_target = alloc(self.grad_numel, dtype=torch.float32, device=self.device) if want_target_grad else None
         if self.batch:
             grad_loss = grad_loss.to(torch.float32).contiguous()
+            stride, scale = (1, 1.0) if broadcast_scale is None else (0, float(broadcast_scale))
             with torch.cuda.device(self.device):
-                rc = lib.b2s_pit_sse_backward(
+                rc = lib.b2s_pit_sse_backward_scaled(
                     _lib.ptr(self.mask_base), _lib.ptr(self.obs_base), _lib.ptr(self.target_base),
                     _lib.ptr(self.scale_base), _lib.ptr(self.meta), self.batch, self.max_frames,
-                    self.sources, self.bins, int(self.dual), _lib.ptr(perm), _lib.ptr(grad_loss),
+                    self.sources, self.bins, int(self.dual), _lib.ptr(perm), _lib.ptr(grad_loss), stride, scale,
                     _lib.ptr(grad_mask), _lib.ptr(grad_target), _lib.stream_of(self.device))
-            _lib.check(rc, 'b2s_pit_sse_backward')
+            _lib.check(rc, 'b2s_pit_sse_backward_scaled')
         return grad_mask, grad_target
 
     def split(self, flat):
@@ -82,6 +96,25 @@ class PitSseFunction(torch.autograd.Function):
         if ctx.n_tensors > ctx.n_masks:
             grads = grads + ([grad_target.view(problem.grad_splits[0][2])] if want_target else [None])
         return (None, None, *grads)
+
+
+class PitSseMeanFunction(torch.autograd.Function):
+    """(problem, n_masks, *mask tensors) -> (mean [slots], perm): the batch means of the per-example PIT losses (the
+    `losses` entry of PermutationInvariantTrainingModel.review, pit/model.py:137-140) from one extra one-warp launch;
+    the backward takes the means' upstream gradients directly (factor 1 / batch inside the kernel)."""
+
+    @staticmethod
+    def forward(ctx, problem, n_masks, *tensors):
+        _, perm, _, mean = problem.forward(with_mean=True)
+        ctx.problem, ctx.perm = problem, perm
+        ctx.mark_non_differentiable(perm)
+        return mean, perm
+
+    @staticmethod
+    def backward(ctx, grad_mean, _grad_perm):
+        problem = ctx.problem
+        grad_mask, _ = problem.backward(ctx.perm, grad_mean, False, broadcast_scale=1.0 / max(problem.batch, 1))
+        return (None, None, *problem.split(grad_mask))
 
 
 def _offset(tensor, base):

@@ -24,13 +24,9 @@ def _as_list(x):
     return list(x) if isinstance(x, (list, tuple)) else None
 
 
-def pit_losses_per_example(masks, observations, targets, cos_phase_difference=None, lengths=None):
-    """Per-example PIT losses of a minibatch.
-
-    masks / targets / cos_phase_difference: lists of [T_b, K, F] tensors, or padded [B, T, K, F]
-    tensors with `lengths`; observations: list of [T_b, F] or padded [B, T, F].
-    Returns (mse [B], mse_perm [B, K] int32, ips [B] or None, ips_perm or None).
-    """
+def _pit_problem(masks, observations, targets, cos_phase_difference, lengths):
+    """(SseProblem, autograd inputs, dual) of a minibatch.  masks / targets / cos_phase_difference: lists of [T_b, K, F]
+    tensors, or padded [B, T, K, F] tensors with `lengths`; observations: list of [T_b, F] or padded [B, T, F]."""
     dual = cos_phase_difference is not None
     mask_list = _as_list(masks)
     if mask_list is not None:
@@ -38,12 +34,19 @@ def pit_losses_per_example(masks, observations, targets, cos_phase_difference=No
             _lib.require_cuda_float(m, 'mask')
         problem, inputs = _sse.list_problem(mask_list, _as_list(observations), _as_list(targets),
                                             _as_list(cos_phase_difference) if dual else None, dual)
-        loss, perm, _ = _sse.PitSseFunction.apply(problem, len(inputs), *inputs)
-    else:
-        _lib.require_cuda_float(masks, 'mask')
-        problem, dense = _sse.padded_problem(masks, observations, targets,
-                                             cos_phase_difference if dual else None, lengths, dual)
-        loss, perm, _ = _sse.PitSseFunction.apply(problem, 1, dense)
+        return problem, list(inputs), dual
+    _lib.require_cuda_float(masks, 'mask')
+    problem, dense = _sse.padded_problem(masks, observations, targets,
+                                         cos_phase_difference if dual else None, lengths, dual)
+    return problem, [dense], dual
+
+
+def pit_losses_per_example(masks, observations, targets, cos_phase_difference=None, lengths=None):
+    """Per-example PIT losses of a minibatch (inputs as `_pit_problem`).
+    Returns (mse [B], mse_perm [B, K] int32, ips [B] or None, ips_perm or None).
+    """
+    problem, inputs, dual = _pit_problem(masks, observations, targets, cos_phase_difference, lengths)
+    loss, perm, _ = _sse.PitSseFunction.apply(problem, len(inputs), *inputs)
     if dual:
         return loss[0], perm[0], loss[1], perm[1]
     return loss[0], perm[0], None, None
@@ -51,11 +54,18 @@ def pit_losses_per_example(masks, observations, targets, cos_phase_difference=No
 
 def pit_review_losses(masks, observations, targets, cos_phase_difference=None, lengths=None):
     """``dict(pit_mse_loss=..., pit_ips_loss=...)`` exactly as the ``losses`` entry of
-    PermutationInvariantTrainingModel.review (pit/model.py:137-140): batch means."""
-    mse, _, ips, _ = pit_losses_per_example(masks, observations, targets, cos_phase_difference, lengths)
-    out = {'pit_mse_loss': mse.mean()}
-    if ips is not None:
-        out['pit_ips_loss'] = ips.mean()
+    PermutationInvariantTrainingModel.review (pit/model.py:137-140): batch means -- both from ONE one-warp-per-loss
+    launch behind the loss kernel, their gradients taken by the backward kernel directly (no ATen mean / expand /
+    divide kernels)."""
+    problem, inputs, dual = _pit_problem(masks, observations, targets, cos_phase_difference, lengths)
+    if problem.batch == 0:
+        loss, _, _ = _sse.PitSseFunction.apply(problem, len(inputs), *inputs)
+        means = loss.mean(dim=1)
+    else:
+        means, _ = _sse.PitSseMeanFunction.apply(problem, len(inputs), *inputs)
+    out = {'pit_mse_loss': means[0]}
+    if dual:
+        out['pit_ips_loss'] = means[1]
     return out
 
 

@@ -454,6 +454,43 @@ def test_dc_balanced_chunks(b2s, lengths):
             assert float(grad[b, lengths[b]:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('K,F,lengths,dual', [(2, 513, [30, 11, 25], True), (2, 513, [17] * 5, False), (3, 257, [9, 5], True),
+                                              (2, 40000, [3], False)])
+def test_pit_review_losses_folded_means(b2s, K, F, lengths, dual):
+    """pit_review_losses (means from b2s_pit_sse_forward_mean, backward through b2s_pit_sse_backward_scaled with one upstream
+    value per loss) == means of pit_losses_per_example and their autograd: padded and list entry points, ragged lengths,
+    frame-staged and direct kernels, repeated calls."""
+    g = torch.Generator().manual_seed(K * 100 + len(lengths))
+    T = max(lengths)
+    B = len(lengths)
+    masks = torch.rand(B, T, K, F, generator=g).to(dev()).requires_grad_(True)
+    yab = torch.rand(B, T, F, generator=g).to(dev())
+    xab = torch.rand(B, T, K, F, generator=g).to(dev())
+    cpd = (torch.rand(B, T, K, F, generator=g) * 2 - 1).to(dev()) if dual else None
+    mse, _, ips, _ = b2s.review.pit_losses_per_example(masks, yab, xab, cpd, lengths)
+    want = 1.5 * mse.mean() + (0.25 * ips.mean() if dual else 0.0)
+    (want_grad,) = torch.autograd.grad(want, masks)
+    atol = 1e-6 * float(want_grad.abs().max())
+    for _ in range(2):
+        out = b2s.review.pit_review_losses(masks, yab, xab, cpd, lengths)
+        torch.testing.assert_close(out['pit_mse_loss'], mse.mean(), rtol=1e-6, atol=0)
+        got = 1.5 * out['pit_mse_loss']
+        if dual:
+            torch.testing.assert_close(out['pit_ips_loss'], ips.mean(), rtol=1e-6, atol=0)
+            got = got + 0.25 * out['pit_ips_loss']
+        (grad,) = torch.autograd.grad(got, masks)
+        torch.testing.assert_close(grad, want_grad, rtol=1e-5, atol=atol)
+    mask_list = [masks[b, :n].detach().clone().requires_grad_(True) for b, n in enumerate(lengths)]
+    out = b2s.review.pit_review_losses(mask_list, [yab[b, :n].contiguous() for b, n in enumerate(lengths)],
+                                       [xab[b, :n].contiguous() for b, n in enumerate(lengths)],
+                                       [cpd[b, :n].contiguous() for b, n in enumerate(lengths)] if dual else None)
+    got = 1.5 * out['pit_mse_loss'] + (0.25 * out['pit_ips_loss'] if dual else 0.0)
+    torch.testing.assert_close(got, want.detach(), rtol=1e-6, atol=0)
+    grads = torch.autograd.grad(got, mask_list)
+    for b, n in enumerate(lengths):
+        torch.testing.assert_close(grads[b], want_grad[b, :n], rtol=1e-5, atol=atol)
+
+
 @pytest.mark.parametrize('F,E,K,lengths', [(513, 20, 2, [40, 12, 33, 7]), (513, 20, 2, [25] * 6), (65, 7, 3, [5, 9, 4]),
                                             (513, 30, 2, [6, 11]), (513, 20, 2, [19])])
 def test_dc_review_loss_folded_mean(b2s, F, E, K, lengths):

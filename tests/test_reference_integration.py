@@ -96,9 +96,9 @@ def test_reference_trainer_test_run_on_gpu(patched):
     from padertorch_b200.ops.losses import _sse
     original = _sse.SseProblem.forward
 
-    def counting(self):
+    def counting(self, *args, **kwargs):
         calls['n'] += 1
-        return original(self)
+        return original(self, *args, **kwargs)
     _sse.SseProblem.forward = counting
     try:
         torch.manual_seed(0)
@@ -190,7 +190,9 @@ def test_model_patch_pit_review_batched(patched):
         losses_ours, images_ours, grads_ours = step()
     finally:
         _lib.load = real_load
-    assert counts.get('b2s_pit_sse_forward') == 1 and counts.get('b2s_pit_sse_backward') == 1, counts
+    # one loss launch (+ the one-warp mean launch behind it) forward, one backward
+    assert counts.get('b2s_pit_sse_forward_mean') == 1 and counts.get('b2s_pit_sse_backward_scaled') == 1, counts
+    assert 'b2s_pit_sse_forward' not in counts and 'b2s_pit_sse_backward' not in counts, counts
     b2s.unpatch_padertorch()
     losses_ref, images_ref, grads_ref = step()          # the unmodified reference on the GPU
     assert images_ours == images_ref
