@@ -450,9 +450,10 @@ dc_gram_frame_kernel(const float* __restrict__ emb, const float* __restrict__ tg
 // packed products per step for every warp, 16 operand loads for both blocks (48 LDS per 32 bins) -- and four such
 // role triples (12 warps, one CTA per SM) share the 32-bin steps of the frames round robin over a running step
 // counter, so all warps carry the same work whatever the number of bins.  Frames travel through a ring of four
-// whole-frame stages (TMA bulk copies as above, `full` mbarrier per stage); a warp releases a stage by one arrival
-// on the stage's `empty` mbarrier and runs on; no block barrier exists in the frame loop.  Warp 0 refills the
-// stage of frame f - 1 with frame f + 3 when it starts frame f (three frames of slack for everyone else).
+// whole-frame stages (TMA bulk copies as above, `full` mbarrier per stage); a warp releases a stage by one non-blocking
+// arrival on the stage's named barrier (bar.arrive) and runs on; no block-wide wait exists in the frame loop.  Warp 0
+// refills the stage of frame f - 1 with frame f + 3 when it starts frame f (bar.sync on that stage's barrier: three
+// frames of slack for everyone else).
 constexpr int kRgGroups = 4, kRgWarps = 3 * kRgGroups, kRgStages = 4;
 // Length-balanced chunking of a ragged batch on a one-dimensional grid of P slots: the smallest chunk length L with
 // sum_b ceil(T_b / L) <= P is found by bisection between sum(T) / P and sum(T) / (P - B), example b is split into
@@ -531,10 +532,6 @@ __device__ inline ChunkSlot balanced_chunk_slot(const int64_t* __restrict__ meta
   return s_slot;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
-}
-
 // One 32-bin step of the blocks (BA, BA) [upper triangle] and (BA, BB).
 template <int FT, int ET, int KT, int BA, int BB>
 __device__ __forceinline__ void gram_ring_step(const float* be_, const float* bt_, const float* zrow, int F, int E,
@@ -566,7 +563,7 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
                     int* __restrict__ counters, double* __restrict__ gram, float* __restrict__ loss,
                     float* __restrict__ mean) {
   extern __shared__ __align__(16) float fsm[];   // [kRgStages][area_e + area_t] frame stages, then a row of zeros
-  __shared__ __align__(8) uint64_t full[kRgStages], empty[kRgStages];
+  __shared__ __align__(8) uint64_t full[kRgStages];
   const int F = FT ? FT : F_rt, E = ET ? ET : E_rt, K = KT ? KT : K_rt;
   // balance_ctas != 0: one-dimensional grid, chunks per example in proportion to its length; else grid (batch, chunks)
   {   // barriers and the row of zeros first: independent of the slot, visible after the barriers below
@@ -576,7 +573,6 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
 #pragma unroll
       for (int s = 0; s < kRgStages; ++s) {
         tma::mbar_init(&full[s], 1);
-        tma::mbar_init(&empty[s], kRgWarps);
       }
       tma::fence_mbar_init();
     }
@@ -631,11 +627,11 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
   for (int f = 0; f < n; ++f) {
     const int s = f & (kRgStages - 1);
     if (warp == 0 && f >= 1 && f + kRgStages - 1 < n) {
-      if (lane == 0) {
-        const int r = (f - 1) & (kRgStages - 1);
-        tma::mbar_wait(&empty[r], (unsigned)((f - 1) / kRgStages) & 1u);
-        issue(t0 + f + kRgStages - 1, r);
-      }
+      // stage r is free once the other eleven warps have arrived on its named barrier (producer / consumer form of
+      // bar.arrive / bar.sync: the consumers do not wait); warp 0's own loads of frame f - 1 precede this in program order
+      const int r = (f - 1) & (kRgStages - 1);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + r), "n"(32 * kRgWarps) : "memory");
+      if (lane == 0) issue(t0 + f + kRgStages - 1, r);
       __syncwarp();
     }
     tma::mbar_wait(&full[s], (unsigned)(f / kRgStages) & 1u);
@@ -659,8 +655,8 @@ dc_gram_ring_kernel(const float* __restrict__ emb, const float* __restrict__ tgt
       default: frame_steps([&](int off) { gram_ring_step<FT, ET, KT, 2, 0>(be_, bt_, z_, F, E, C, off, accd, acco); }); break;
     }
     first = (first + kRgGroups * nsteps - nsteps) % kRgGroups;   // (group - (f + 1) * nsteps) mod kRgGroups
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    // release the stage if it will be refilled (frame f + kRgStages exists): one non-blocking arrival per warp
+    if (warp != 0 && f + kRgStages < n) asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"(32 * kRgWarps) : "memory");
   }
   __syncthreads();   // every stage has been consumed by every warp: the stages are free for the reduction
   // Each warp reduces its 2 x 64 sums (transposed: lane l ends up with entries l and 32 + l of either block); the four

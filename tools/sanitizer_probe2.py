@@ -21,6 +21,13 @@ for lengths in ([70, 33, 9], [24, 24], [300]):
     loss = b2s.review.dc_review_loss(emb, tm, lengths)
     loss.backward()
     print('dc', lengths, float(loss))
+for K_, F_, lens in ((2, 513, [30, 11, 25]), (3, 257, [9, 5])):
+    Tm = max(lens)
+    masks = torch.rand(len(lens), Tm, K_, F_, device=dev, requires_grad=True)
+    out = b2s.review.pit_review_losses(masks, torch.rand(len(lens), Tm, F_, device=dev), torch.rand(len(lens), Tm, K_, F_, device=dev),
+                                       torch.rand(len(lens), Tm, K_, F_, device=dev) * 2 - 1, lens)
+    (out['pit_mse_loss'] + 0.5 * out['pit_ips_loss']).backward()
+    print('pit review', lens, float(out['pit_mse_loss']))
 B, K, T = 3, 2, 40000
 s = torch.randn(B, K, T, device=dev)
 est = (s + 0.3 * torch.randn_like(s)).requires_grad_(True)
