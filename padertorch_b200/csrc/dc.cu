@@ -948,12 +948,14 @@ dc_backward_frame_kernel(const float* __restrict__ emb, const float* __restrict_
       for (int j = 0; j < kFbOut; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
 #pragma unroll
       for (int c = 0; c < kTC; ++c) {
-        if (c < C) {   // uniform
-          const float* r = row(c);
-          const float z0 = r[0], z1 = r[32];
+        // compile-time geometry: the test folds away.  Run-time geometry: channels beyond C re-read channel 0 against
+        // their zero coefficients instead of branching -- straight-line code whose operand loads the scheduler can
+        // move ahead of the products (with a uniform branch per channel every load was consumed at once)
+        if (ET != 0 && c >= C) continue;
+        const float* r = row(ET != 0 || c < C ? c : 0);
+        const float z0 = r[0], z1 = r[32];
 #pragma unroll
-          for (int j = 0; j < kFbOut; ++j) { a0[j] = fmaf(z0, cf[c][j], a0[j]); a1[j] = fmaf(z1, cf[c][j], a1[j]); }
-        }
+        for (int j = 0; j < kFbOut; ++j) { a0[j] = fmaf(z0, cf[c][j], a0[j]); a1[j] = fmaf(z1, cf[c][j], a1[j]); }
       }
 #pragma unroll
       for (int j = 0; j < kFbOut; ++j) {
